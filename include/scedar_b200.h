@@ -1,0 +1,192 @@
+/*
+ * scedar_b200 -- C ABI of the B200 (sm_100a) distance-matrix / kNN path.
+ *
+ * This is the drop-in boundary for the ONE hot path of scedar
+ * (TaylorResearchLab/scedar v0.2.0): the dense cell x cell distance matrix
+ * behind scedar.eda.SampleDistanceMatrix and the row-wise k-nearest-neighbour
+ * selection that consumes it.  The reference has no FFI of its own (it is pure
+ * Python over NumPy / SciPy / scikit-learn); each entry point below names the
+ * reference call site (file:line under scedar/) whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes binding a scedar maintainer would add.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only, no torch / C++ types.
+ *  - Every data pointer is a DEVICE pointer unless the function name ends in
+ *    _host.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *    stream).  Device-pointer calls are asynchronous on that stream.
+ *  - The caller owns every input and output buffer.  The library allocates
+ *    only scratch, stream-ordered (cudaMallocAsync) and released before return,
+ *    plus the working copy inside a scedar_cells_t, released by
+ *    scedar_cells_free.  Inputs are never modified.
+ *  - All matrices are row-major float64; indices out are int64 (NumPy's
+ *    argsort dtype); CSR indices are int32, indptr int32 or int64.
+ *  - Return value: 0 on success, a SCEDAR_ERR_* code otherwise; nothing throws
+ *    across the ABI.  scedar_last_error() gives the message for the calling
+ *    thread's last failure.
+ *  - There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SCEDAR_B200_H
+#define SCEDAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCEDAR_ABI_VERSION 1
+
+/* metric: SampleDistanceMatrix(metric=...), scedar/eda/sdm.py:1211-1217 */
+enum {
+  SCEDAR_METRIC_COSINE = 0,      /* cosine_pdist,      sdm.py:1223-1266 */
+  SCEDAR_METRIC_CORRELATION = 1, /* correlation_pdist, sdm.py:1268-1287 */
+  SCEDAR_METRIC_EUCLIDEAN = 2    /* sklearn pairwise_distances, sdm.py:1216 */
+};
+
+/* precision of the Gram contraction */
+enum {
+  SCEDAR_PRECISION_FP64 = 0, /* float64 tensor-core (DMMA) path, <=1e-10 rel */
+  SCEDAR_PRECISION_FAST = 1  /* split-BF16 tcgen05 path, stated tolerance    */
+};
+
+/* which of the k+1 nearest is dropped */
+enum {
+  SCEDAR_EXCLUDE_FIRST = 0, /* rank 0 of the stable sort: s_knn_ind_lut,
+                               sdm.py:764 (_col_argsorted_d[1:k+1])          */
+  SCEDAR_EXCLUDE_SELF = 1   /* the row itself, else rank 0: sklearn
+                               kneighbors(None), sdm.py:1078-1079            */
+};
+
+enum {
+  SCEDAR_OK = 0,
+  SCEDAR_ERR_ARG = 1,         /* bad argument (Python side: ValueError)   */
+  SCEDAR_ERR_CUDA = 2,        /* a CUDA call failed                       */
+  SCEDAR_ERR_UNSUPPORTED = 3, /* valid request outside this build's range */
+  SCEDAR_ERR_NOMEM = 4        /* device scratch allocation failed         */
+};
+
+/* flags written by scedar_num_correct_dist_mat */
+#define SCEDAR_NCDM_BAD_DIAG 1 /* some |diag| > 1e-5           (sdm.py:196-203) */
+#define SCEDAR_NCDM_ASYMMETRIC 2 /* triangles differ, rtol 1e-3 (sdm.py:205-213) */
+
+int scedar_abi_version(void);
+const char* scedar_last_error(void);
+
+/* Largest k accepted by the streaming top-k kernels (k+1 <= 128 entries kept
+ * per row in registers); larger k is served by scedar_col_sort. */
+int scedar_max_k(void);
+
+/* ------------------------------------------------------------------------
+ * Prepared cells: the device-resident working copy of x that the Gram kernels
+ * read (rows padded to a multiple of 128 cells, genes to a multiple of 16,
+ * zero filled; centred on the row mean for correlation, sdm.py:1286) plus the
+ * per-cell statistic of the metric epilogue (sqrt(1/|x|^2) with 0 for zero
+ * vectors, sdm.py:1249-1261; |x|^2 for euclidean), taken from the diagonal of
+ * the same Gram contraction as the reference does (np.diag(pdot_prod)).
+ * Replaces the input contract of SampleFeatureMatrix.__init__, sfm.py:43-75.
+ * ---------------------------------------------------------------------- */
+typedef struct scedar_cells scedar_cells_t;
+
+/* x: [n, p] float64, row stride ldx (elements). */
+int scedar_cells_from_dense(const double* x, int64_t n, int64_t p, int64_t ldx,
+                            int metric, void* stream, scedar_cells_t** out);
+
+/* CSR cells (cosine / euclidean only, as sdm.py:1196-1204): indptr has n+1
+ * entries of int32 (indptr_is_64 = 0) or int64 (1); duplicates are summed. */
+int scedar_cells_from_csr(const void* indptr, int indptr_is_64,
+                          const int32_t* indices, const double* data,
+                          int64_t n, int64_t p, int metric, void* stream,
+                          scedar_cells_t** out);
+
+int scedar_cells_free(scedar_cells_t* cells);
+int64_t scedar_cells_n(const scedar_cells_t* cells);
+int64_t scedar_cells_p(const scedar_cells_t* cells);
+int scedar_cells_metric(const scedar_cells_t* cells);
+
+/* ------------------------------------------------------------------------
+ * Distance matrix: rows [row_begin, row_end) of the n x n matrix `_d`
+ * (sdm.py:1193-1221) into d_out[(row_end-row_begin), n] with row stride ldd.
+ * The epilogue applies the metric formula in the reference's operation order
+ * and num_correct_dist_mat's clean-up (sdm.py:215-221): negatives -> 0, exact
+ * zero diagonal, value of the lower triangle on both sides.
+ * ---------------------------------------------------------------------- */
+int scedar_pdist_stripe(const scedar_cells_t* cells, int precision,
+                        int64_t row_begin, int64_t row_end, double* d_out,
+                        int64_t ldd, void* stream);
+
+/* Whole matrix at once, computing only the lower-triangle tiles and writing
+ * each tile and its transpose (half the contraction work). */
+int scedar_pdist_symmetric(const scedar_cells_t* cells, int precision,
+                           double* d_out, int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------
+ * k nearest neighbours of rows [row_begin, row_end) without materialising D:
+ * Gram tile -> metric epilogue -> streaming top-(k+1) per row, ordered by
+ * (distance, index) -- the order of np.argsort(kind="mergesort")
+ * (sdm.py:1298-1305).  idx_out / dist_out: [(row_end-row_begin), k].
+ * Replaces s_knn_ind_lut (sdm.py:751-790) and _s_knns_skl (sdm.py:1053-1083).
+ * ---------------------------------------------------------------------- */
+int scedar_knn_stripe(const scedar_cells_t* cells, int precision, int k,
+                      int exclude, int64_t row_begin, int64_t row_end,
+                      int64_t* idx_out, double* dist_out, void* stream);
+
+/* Same selection from an already materialised stripe of D:
+ * d is [(row_end-row_begin), n_cols] with row stride ldd; row r of d is cell
+ * row_begin + r.  (NearestNeighbors(metric="precomputed"), sdm.py:1070-1072.) */
+int scedar_knn_from_d(const double* d, int64_t ldd, int64_t n_cols,
+                      int64_t row_begin, int64_t row_end, int k, int exclude,
+                      int64_t* idx_out, double* dist_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Full stable sort of every column of a symmetric D (sdm.py:1289-1305,
+ * np.sort / np.argsort(kind="mergesort", axis=0)).  Column j of a symmetric D
+ * is row j, so the sort works on rows: d is a stripe [rows, n_cols] (row
+ * stride ldd) and sorted_out / argsorted_out are [rows, n_cols], entry
+ * (j, r) = r-th nearest of the j-th cell of the stripe -- the TRANSPOSE of the
+ * reference's (rank, cell) arrays.  Either output may be NULL.
+ * ---------------------------------------------------------------------- */
+int scedar_col_sort(const double* d, int64_t ldd, int64_t rows, int64_t n_cols,
+                    double* sorted_out, int64_t* argsorted_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * num_correct_dist_mat (sdm.py:187-222) in place on a user-supplied n x n
+ * matrix: *flags_out (device int32) receives SCEDAR_NCDM_* bits for the two
+ * warnings; then negatives -> 0, diagonal -> 0, optional clamp to upper_bound,
+ * upper triangle := lower triangle.
+ * ---------------------------------------------------------------------- */
+int scedar_num_correct_dist_mat(double* d, int64_t ldd, int64_t n,
+                                int has_upper_bound, double upper_bound,
+                                int32_t* flags_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * One-shot forms (prepare + run + free), the signatures SURVEY.md 8b lists.
+ * ---------------------------------------------------------------------- */
+int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric,
+                       int precision, int64_t row_begin, int64_t row_end,
+                       double* d_out, void* stream);
+int scedar_pdist_csr(const void* indptr, int indptr_is_64,
+                     const int32_t* indices, const double* data, int64_t n,
+                     int64_t p, int metric, int precision, int64_t row_begin,
+                     int64_t row_end, double* d_out, void* stream);
+int scedar_knn_dense(const double* x, int64_t n, int64_t p, int metric,
+                     int precision, int k, int exclude, int64_t row_begin,
+                     int64_t row_end, int64_t* idx_out, double* dist_out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer forms: x, d_out, idx_out, dist_out are HOST pointers; the call
+ * does the host<->device copies itself on `device` and returns when the
+ * outputs are complete.  D is produced and copied back stripe by stripe, so
+ * the n x n matrix never has to fit in device memory.
+ * ---------------------------------------------------------------------- */
+int scedar_pdist_dense_host(const double* x, int64_t n, int64_t p, int metric,
+                            int precision, double* d_out, int device);
+int scedar_knn_dense_host(const double* x, int64_t n, int64_t p, int metric,
+                          int precision, int k, int exclude, int64_t* idx_out,
+                          double* dist_out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCEDAR_B200_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI in ``include/scedar_b200.h``.
+
+The shared library is built in-tree (``scedar_b200/csrc/libscedar_b200.so``,
+``__graft_entry__.build()``).  There is no fallback: if the library is missing
+the import of any compute entry point raises.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_int, c_int32, c_int64,
+                    c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libscedar_b200.so")
+
+METRIC_IDS = {"cosine": 0, "correlation": 1, "euclidean": 2}
+PRECISION_IDS = {"fp64": 0, "fast": 1}
+EXCLUDE_FIRST, EXCLUDE_SELF = 0, 1
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4
+NCDM_BAD_DIAG, NCDM_ASYMMETRIC = 1, 2
+
+# name -> (restype, argtypes); every symbol the header declares
+SIGNATURES = {
+    "scedar_abi_version": (c_int, []),
+    "scedar_last_error": (c_char_p, []),
+    "scedar_max_k": (c_int, []),
+    "scedar_cells_from_dense": (c_int, [c_void_p, c_int64, c_int64, c_int64,
+                                        c_int, c_void_p, POINTER(c_void_p)]),
+    "scedar_cells_from_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int, c_void_p,
+                                      POINTER(c_void_p)]),
+    "scedar_cells_free": (c_int, [c_void_p]),
+    "scedar_cells_n": (c_int64, [c_void_p]),
+    "scedar_cells_p": (c_int64, [c_void_p]),
+    "scedar_cells_metric": (c_int, [c_void_p]),
+    "scedar_pdist_stripe": (c_int, [c_void_p, c_int, c_int64, c_int64,
+                                    c_void_p, c_int64, c_void_p]),
+    "scedar_pdist_symmetric": (c_int, [c_void_p, c_int, c_void_p, c_int64,
+                                       c_void_p]),
+    "scedar_knn_stripe": (c_int, [c_void_p, c_int, c_int, c_int, c_int64,
+                                  c_int64, c_void_p, c_void_p, c_void_p]),
+    "scedar_knn_from_d": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                  c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "scedar_col_sort": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                c_void_p, c_void_p]),
+    "scedar_num_correct_dist_mat": (c_int, [c_void_p, c_int64, c_int64, c_int,
+                                            c_double, c_void_p, c_void_p]),
+    "scedar_pdist_dense": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int,
+                                   c_int64, c_int64, c_void_p, c_void_p]),
+    "scedar_pdist_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64,
+                                 c_int64, c_int, c_int, c_int64, c_int64,
+                                 c_void_p, c_void_p]),
+    "scedar_knn_dense": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int,
+                                 c_int, c_int, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_void_p]),
+    "scedar_pdist_dense_host": (c_int, [c_void_p, c_int64, c_int64, c_int,
+                                        c_int, c_void_p, c_int]),
+    "scedar_knn_dense_host": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int,
+                                      c_int, c_int, c_void_p, c_void_p,
+                                      c_int]),
+}
+
+_lib = None
+
+
+class ScedarError(RuntimeError):
+    """A non-argument failure inside the CUDA library."""
+
+
+def load():
+    """Load the shared library once; raise loudly if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "scedar_b200: {} is missing -- build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)".format(LIB_PATH))
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.scedar_abi_version() != 1:
+            raise ImportError("scedar_b200: ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    """Turn a return code into the reference's error convention: argument
+    errors are ``ValueError``, the rest RuntimeError."""
+    if rc == OK:
+        return
+    msg = load().scedar_last_error().decode("utf-8", "replace")
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    raise ScedarError(msg)

@@ -1,0 +1,400 @@
+// C ABI of libscedar_b200 (declared in include/scedar_b200.h): argument
+// checking, scratch management and the sequencing of the kernels.  No compute
+// happens on the host and there is no CPU fallback.
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+namespace scedar {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int Scratch::alloc(size_t bytes, cudaStream_t s) {
+  stream = s;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
+  if (e != cudaSuccess) {
+    ptr = nullptr;
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? SCEDAR_ERR_NOMEM : SCEDAR_ERR_CUDA,
+                std::string("cudaMallocAsync(") + std::to_string(bytes) +
+                    "): " + cudaGetErrorString(e));
+  }
+  return SCEDAR_OK;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+namespace {
+
+int check_metric(int metric) {
+  if (metric != SCEDAR_METRIC_COSINE && metric != SCEDAR_METRIC_CORRELATION &&
+      metric != SCEDAR_METRIC_EUCLIDEAN)
+    return fail(SCEDAR_ERR_ARG, "metric must be cosine (0), correlation (1) or euclidean (2)");
+  return SCEDAR_OK;
+}
+
+int check_precision(int precision) {
+  if (precision == SCEDAR_PRECISION_FP64) return SCEDAR_OK;
+  if (precision == SCEDAR_PRECISION_FAST)
+    return fail(SCEDAR_ERR_UNSUPPORTED, "fast precision is not built in this version");
+  return fail(SCEDAR_ERR_ARG, "precision must be 0 (fp64) or 1 (fast)");
+}
+
+int check_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (row_begin < 0 || row_end < row_begin || row_end > c->n)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n");
+  return SCEDAR_OK;
+}
+
+int new_cells(int64_t n, int64_t p, int metric, scedar_cells** out) {
+  if (!out) return fail(SCEDAR_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  SCEDAR_CHECK(check_metric(metric));
+  if (n < 0 || p < 0) return fail(SCEDAR_ERR_ARG, "n and p must be >= 0");
+  if (n >= 0x7fffffffLL - 256) return fail(SCEDAR_ERR_UNSUPPORTED, "n must fit in int32");
+  scedar_cells* c = new (std::nothrow) scedar_cells();
+  if (!c) return fail(SCEDAR_ERR_NOMEM, "host allocation failed");
+  c->n = n;
+  c->p = p;
+  c->metric = metric;
+  c->n_pad = std::max<int64_t>(round_up(n, kRowPad), kRowPad);
+  c->p_pad = std::max<int64_t>(round_up(p, kColPad), kColPad);
+  cudaGetDevice(&c->device);
+  cudaError_t e = cudaMalloc(&c->xw, sizeof(double) * c->n_pad * c->p_pad);
+  if (e == cudaSuccess) e = cudaMalloc(&c->stat, sizeof(double) * c->n_pad);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    scedar_cells_free(c);
+    return fail(e == cudaErrorMemoryAllocation ? SCEDAR_ERR_NOMEM : SCEDAR_ERR_CUDA,
+                std::string("allocating the working copy: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return SCEDAR_OK;
+}
+
+}  // namespace
+}  // namespace scedar
+
+using namespace scedar;
+
+extern "C" {
+
+int scedar_abi_version(void) { return SCEDAR_ABI_VERSION; }
+const char* scedar_last_error(void) { return g_last_error.c_str(); }
+int scedar_max_k(void) { return 127; }
+
+int scedar_cells_from_dense(const double* x, int64_t n, int64_t p, int64_t ldx, int metric,
+                            void* stream, scedar_cells_t** out) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n > 0 && p > 0 && !x) return fail(SCEDAR_ERR_ARG, "x is NULL");
+  if (ldx < p) return fail(SCEDAR_ERR_ARG, "ldx must be >= p");
+  SCEDAR_CHECK(new_cells(n, p, metric, out));
+  scedar_cells* c = *out;
+  int rc = launch_prep_dense(x, n, p, ldx, metric, c->xw, c->n_pad, c->p_pad, s);
+  if (rc == SCEDAR_OK) rc = launch_gram_diag(c, s);
+  if (rc != SCEDAR_OK) {
+    scedar_cells_free(c);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int scedar_cells_from_csr(const void* indptr, int indptr_is_64, const int32_t* indices,
+                          const double* data, int64_t n, int64_t p, int metric, void* stream,
+                          scedar_cells_t** out) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (metric == SCEDAR_METRIC_CORRELATION)
+    return fail(SCEDAR_ERR_ARG, "correlation is not defined for sparse cells (sdm.py:1196-1204)");
+  if (!indptr) return fail(SCEDAR_ERR_ARG, "indptr is NULL");
+  SCEDAR_CHECK(new_cells(n, p, metric, out));
+  scedar_cells* c = *out;
+  int rc = launch_prep_csr(indptr, indptr_is_64, indices, data, n, p, c->xw, c->n_pad, c->p_pad, s);
+  if (rc == SCEDAR_OK) rc = launch_gram_diag(c, s);
+  if (rc != SCEDAR_OK) {
+    scedar_cells_free(c);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int scedar_cells_free(scedar_cells_t* c) {
+  if (!c) return SCEDAR_OK;
+  if (c->xw) cudaFree(c->xw);
+  if (c->stat) cudaFree(c->stat);
+  delete c;
+  return SCEDAR_OK;
+}
+
+int64_t scedar_cells_n(const scedar_cells_t* c) { return c ? c->n : -1; }
+int64_t scedar_cells_p(const scedar_cells_t* c) { return c ? c->p : -1; }
+int scedar_cells_metric(const scedar_cells_t* c) { return c ? c->metric : -1; }
+
+int scedar_pdist_stripe(const scedar_cells_t* c, int precision, int64_t row_begin,
+                        int64_t row_end, double* d_out, int64_t ldd, void* stream) {
+  SCEDAR_CHECK(check_rows(c, row_begin, row_end));
+  SCEDAR_CHECK(check_precision(precision));
+  if (row_end == row_begin) return SCEDAR_OK;
+  if (!d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  return launch_gram_stripe(c, row_begin, row_end, d_out, ldd, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_pdist_symmetric(const scedar_cells_t* c, int precision, double* d_out, int64_t ldd,
+                           void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  SCEDAR_CHECK(check_precision(precision));
+  if (c->n == 0) return SCEDAR_OK;
+  if (!d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  return launch_gram_symmetric(c, d_out, ldd, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_knn_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row_begin,
+                      int64_t row_end, int k, int exclude, int64_t* idx_out, double* dist_out,
+                      void* stream) {
+  if (row_begin < 0 || row_end < row_begin || row_end > n_cols)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n_cols");
+  if (k < 0 || k > n_cols - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
+  if (exclude != SCEDAR_EXCLUDE_FIRST && exclude != SCEDAR_EXCLUDE_SELF)
+    return fail(SCEDAR_ERR_ARG, "exclude must be 0 (first) or 1 (self)");
+  if (k == 0 || row_end == row_begin) return SCEDAR_OK;
+  if (!d || !idx_out || !dist_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  if (ldd < n_cols) return fail(SCEDAR_ERR_ARG, "ldd must be >= n_cols");
+  return launch_topk_from_d(d, ldd, n_cols, row_begin, row_end, k, exclude, idx_out, dist_out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int scedar_knn_stripe(const scedar_cells_t* c, int precision, int k, int exclude,
+                      int64_t row_begin, int64_t row_end, int64_t* idx_out, double* dist_out,
+                      void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SCEDAR_CHECK(check_rows(c, row_begin, row_end));
+  SCEDAR_CHECK(check_precision(precision));
+  if (k < 0 || k > c->n - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
+  if (exclude != SCEDAR_EXCLUDE_FIRST && exclude != SCEDAR_EXCLUDE_SELF)
+    return fail(SCEDAR_ERR_ARG, "exclude must be 0 (first) or 1 (self)");
+  const int64_t rows = row_end - row_begin;
+  if (k == 0 || rows == 0) return SCEDAR_OK;
+  if (!idx_out || !dist_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  const int K = k + 1;
+  if (K <= 32) {
+    // fused: Gram tile -> epilogue -> per-row lists in shared memory, D never
+    // reaches HBM; column splits give every SM work, then one merge pass
+    const int splits = gram_topk_splits(c, rows);
+    Scratch pd, pi;
+    SCEDAR_CHECK(pd.alloc(sizeof(double) * splits * rows * K, s));
+    SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * splits * rows * K, s));
+    SCEDAR_CHECK(launch_gram_topk(c, row_begin, row_end, K, splits, pd.as<double>(),
+                                  pi.as<int32_t>(), s));
+    return launch_topk_merge(pd.as<double>(), pi.as<int32_t>(), splits, rows, K, row_begin, k,
+                             exclude, idx_out, dist_out, s);
+  }
+  if (K > 128) return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
+  // wider lists: materialise D in row chunks that stay L2-sized, select per chunk
+  int64_t chunk = (int64_t(256) << 20) / (8 * std::max<int64_t>(c->n, 1));
+  chunk = std::max<int64_t>(128, chunk / 128 * 128);
+  chunk = std::min(chunk, round_up(rows, 128));
+  Scratch dbuf;
+  SCEDAR_CHECK(dbuf.alloc(sizeof(double) * chunk * c->n, s));
+  for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk) {
+    const int64_t r1 = std::min(row_end, r0 + chunk);
+    SCEDAR_CHECK(launch_gram_stripe(c, r0, r1, dbuf.as<double>(), c->n, s));
+    SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), c->n, c->n, r0, r1, k, exclude,
+                                    idx_out + (r0 - row_begin) * k,
+                                    dist_out + (r0 - row_begin) * k, s));
+  }
+  return SCEDAR_OK;
+}
+
+int scedar_col_sort(const double* d, int64_t ldd, int64_t rows, int64_t n_cols,
+                    double* sorted_out, int64_t* argsorted_out, void* stream) {
+  if (rows < 0 || n_cols < 0 || ldd < n_cols)
+    return fail(SCEDAR_ERR_ARG, "need rows >= 0, n_cols >= 0 and ldd >= n_cols");
+  if (n_cols >= 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "n_cols must fit in int32");
+  if (rows == 0 || n_cols == 0 || (!sorted_out && !argsorted_out)) return SCEDAR_OK;
+  if (!d) return fail(SCEDAR_ERR_ARG, "d is NULL");
+  return launch_col_sort(d, ldd, rows, n_cols, sorted_out, argsorted_out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int scedar_num_correct_dist_mat(double* d, int64_t ldd, int64_t n, int has_upper_bound,
+                                double upper_bound, int32_t* flags_out, void* stream) {
+  if (n < 0 || ldd < n) return fail(SCEDAR_ERR_ARG, "dmat must be a 2D (n_samples, n_samples) array");
+  if (!flags_out) return fail(SCEDAR_ERR_ARG, "flags_out is NULL");
+  if (n > 0 && !d) return fail(SCEDAR_ERR_ARG, "d is NULL");
+  return launch_ncdm(d, ldd, n, has_upper_bound, upper_bound, flags_out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+// ---- one-shot forms --------------------------------------------------------
+int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric, int precision,
+                       int64_t row_begin, int64_t row_end, double* d_out, void* stream) {
+  scedar_cells_t* c = nullptr;
+  SCEDAR_CHECK(scedar_cells_from_dense(x, n, p, p, metric, stream, &c));
+  int rc = scedar_pdist_stripe(c, precision, row_begin, row_end, d_out, n, stream);
+  if (rc == SCEDAR_OK && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    rc = fail(SCEDAR_ERR_CUDA, "stream synchronize failed");
+  scedar_cells_free(c);
+  return rc;
+}
+
+int scedar_pdist_csr(const void* indptr, int indptr_is_64, const int32_t* indices,
+                     const double* data, int64_t n, int64_t p, int metric, int precision,
+                     int64_t row_begin, int64_t row_end, double* d_out, void* stream) {
+  scedar_cells_t* c = nullptr;
+  SCEDAR_CHECK(scedar_cells_from_csr(indptr, indptr_is_64, indices, data, n, p, metric, stream, &c));
+  int rc = scedar_pdist_stripe(c, precision, row_begin, row_end, d_out, n, stream);
+  if (rc == SCEDAR_OK && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    rc = fail(SCEDAR_ERR_CUDA, "stream synchronize failed");
+  scedar_cells_free(c);
+  return rc;
+}
+
+int scedar_knn_dense(const double* x, int64_t n, int64_t p, int metric, int precision, int k,
+                     int exclude, int64_t row_begin, int64_t row_end, int64_t* idx_out,
+                     double* dist_out, void* stream) {
+  scedar_cells_t* c = nullptr;
+  SCEDAR_CHECK(scedar_cells_from_dense(x, n, p, p, metric, stream, &c));
+  int rc = scedar_knn_stripe(c, precision, k, exclude, row_begin, row_end, idx_out, dist_out, stream);
+  if (rc == SCEDAR_OK && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    rc = fail(SCEDAR_ERR_CUDA, "stream synchronize failed");
+  scedar_cells_free(c);
+  return rc;
+}
+
+// ---- host-buffer forms -----------------------------------------------------
+int scedar_pdist_dense_host(const double* x, int64_t n, int64_t p, int metric, int precision,
+                            double* d_out, int device) {
+  SCEDAR_CHECK(check_metric(metric));
+  SCEDAR_CHECK(check_precision(precision));
+  if (n < 0 || p < 0) return fail(SCEDAR_ERR_ARG, "n and p must be >= 0");
+  if (n == 0) return SCEDAR_OK;
+  if (!d_out || (p > 0 && !x)) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  SCEDAR_CUDA(cudaSetDevice(device));
+  cudaStream_t s0 = nullptr, s1 = nullptr;
+  double* xd = nullptr;
+  double* dbuf[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  scedar_cells_t* c = nullptr;
+  int rc = SCEDAR_OK;
+  auto cleanup = [&]() {
+    if (c) scedar_cells_free(c);
+    if (xd) cudaFree(xd);
+    for (int b = 0; b < 2; ++b) {
+      if (dbuf[b]) cudaFree(dbuf[b]);
+      if (done[b]) cudaEventDestroy(done[b]);
+    }
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+  };
+#define HOST_CUDA(expr)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      rc = fail(e__ == cudaErrorMemoryAllocation ? SCEDAR_ERR_NOMEM : SCEDAR_ERR_CUDA, \
+                std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+      cleanup();                                                               \
+      return rc;                                                               \
+    }                                                                          \
+  } while (0)
+  HOST_CUDA(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking));
+  HOST_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+  HOST_CUDA(cudaMalloc(&xd, sizeof(double) * std::max<int64_t>(n * p, 1)));
+  HOST_CUDA(cudaMemcpyAsync(xd, x, sizeof(double) * n * p, cudaMemcpyHostToDevice, s0));
+  rc = scedar_cells_from_dense(xd, n, p, p, metric, s0, &c);
+  if (rc != SCEDAR_OK) {
+    cleanup();
+    return rc;
+  }
+  // stripes of <= 1 GiB, double buffered: compute on s0, copy back on s1
+  int64_t chunk = (int64_t(1) << 30) / (8 * n);
+  chunk = std::max<int64_t>(128, chunk / 128 * 128);
+  chunk = std::min(chunk, round_up(n, 128));
+  for (int b = 0; b < 2; ++b) {
+    HOST_CUDA(cudaMalloc(&dbuf[b], sizeof(double) * chunk * n));
+    HOST_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+  }
+  cudaEvent_t ready = nullptr;
+  HOST_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  int b = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk, b ^= 1) {
+    const int64_t r1 = std::min(n, r0 + chunk);
+    // the copy that last used this buffer must have drained
+    cudaStreamWaitEvent(s0, done[b], 0);
+    rc = launch_gram_stripe(c, r0, r1, dbuf[b], n, s0);
+    if (rc != SCEDAR_OK) break;
+    cudaEventRecord(ready, s0);
+    cudaStreamWaitEvent(s1, ready, 0);
+    cudaMemcpyAsync(d_out + r0 * n, dbuf[b], sizeof(double) * (r1 - r0) * n,
+                    cudaMemcpyDeviceToHost, s1);
+    cudaEventRecord(done[b], s1);
+  }
+  cudaError_t e0 = cudaStreamSynchronize(s0), e1 = cudaStreamSynchronize(s1);
+  cudaEventDestroy(ready);
+  if (rc == SCEDAR_OK && (e0 != cudaSuccess || e1 != cudaSuccess))
+    rc = fail(SCEDAR_ERR_CUDA, std::string("pdist stripes: ") +
+                                   cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+  cleanup();
+  return rc;
+}
+
+int scedar_knn_dense_host(const double* x, int64_t n, int64_t p, int metric, int precision, int k,
+                          int exclude, int64_t* idx_out, double* dist_out, int device) {
+  SCEDAR_CHECK(check_metric(metric));
+  SCEDAR_CHECK(check_precision(precision));
+  if (n < 0 || p < 0) return fail(SCEDAR_ERR_ARG, "n and p must be >= 0");
+  if (k < 0 || k > n - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
+  if (n == 0 || k == 0) return SCEDAR_OK;
+  if (!idx_out || !dist_out || (p > 0 && !x)) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  SCEDAR_CUDA(cudaSetDevice(device));
+  cudaStream_t s = nullptr;
+  double* xd = nullptr;
+  int64_t* id = nullptr;
+  double* dd = nullptr;
+  scedar_cells_t* c = nullptr;
+  int rc = SCEDAR_OK;
+  auto cleanup = [&]() {
+    if (c) scedar_cells_free(c);
+    if (xd) cudaFree(xd);
+    if (id) cudaFree(id);
+    if (dd) cudaFree(dd);
+    if (s) cudaStreamDestroy(s);
+  };
+  HOST_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  HOST_CUDA(cudaMalloc(&xd, sizeof(double) * std::max<int64_t>(n * p, 1)));
+  HOST_CUDA(cudaMalloc(&id, sizeof(int64_t) * n * k));
+  HOST_CUDA(cudaMalloc(&dd, sizeof(double) * n * k));
+  HOST_CUDA(cudaMemcpyAsync(xd, x, sizeof(double) * n * p, cudaMemcpyHostToDevice, s));
+  rc = scedar_cells_from_dense(xd, n, p, p, metric, s, &c);
+  if (rc == SCEDAR_OK) rc = scedar_knn_stripe(c, precision, k, exclude, 0, n, id, dd, s);
+  if (rc != SCEDAR_OK) {
+    cleanup();
+    return rc;
+  }
+  HOST_CUDA(cudaMemcpyAsync(idx_out, id, sizeof(int64_t) * n * k, cudaMemcpyDeviceToHost, s));
+  HOST_CUDA(cudaMemcpyAsync(dist_out, dd, sizeof(double) * n * k, cudaMemcpyDeviceToHost, s));
+  HOST_CUDA(cudaStreamSynchronize(s));
+  cleanup();
+  return rc;
+#undef HOST_CUDA
+}
+
+}  // extern "C"

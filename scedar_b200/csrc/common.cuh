@@ -1,0 +1,108 @@
+// Shared declarations of the scedar_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "scedar_b200.h"
+
+namespace scedar {
+
+// ---- tile geometry of the working copy -----------------------------------
+constexpr int kRowPad = 128;  // cells padded to a multiple of the Gram tile
+constexpr int kColPad = 16;   // genes padded to a multiple of the K slab
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define SCEDAR_CUDA(expr)                                                     \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      return ::scedar::fail(                                                  \
+          e__ == cudaErrorMemoryAllocation ? SCEDAR_ERR_NOMEM                 \
+                                           : SCEDAR_ERR_CUDA,                 \
+          std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+    }                                                                         \
+  } while (0)
+
+#define SCEDAR_CHECK(call)            \
+  do {                                \
+    int rc__ = (call);                \
+    if (rc__ != SCEDAR_OK) return rc__; \
+  } while (0)
+
+// stream-ordered scratch, released on scope exit
+struct Scratch {
+  void* ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  ~Scratch() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+  int alloc(size_t bytes, cudaStream_t s);
+  template <typename T>
+  T* as() const { return static_cast<T*>(ptr); }
+};
+
+int num_sms();
+
+}  // namespace scedar
+
+// The prepared cells handle (opaque in the C header).
+struct scedar_cells {
+  int64_t n = 0, p = 0;          // logical shape
+  int64_t n_pad = 0, p_pad = 0;  // padded shape of xw
+  int metric = 0;
+  int device = 0;
+  double* xw = nullptr;    // [n_pad, p_pad] working copy (centred if correlation)
+  double* stat = nullptr;  // [n_pad] sqrt(1/|x|^2) (0 for zero rows) or |x|^2
+};
+
+namespace scedar {
+
+// ---- kernel launchers (each in its own .cu) --------------------------------
+// prep.cu
+int launch_prep_dense(const double* x, int64_t n, int64_t p, int64_t ldx,
+                      int metric, double* xw, int64_t n_pad, int64_t p_pad,
+                      cudaStream_t s);
+int launch_prep_csr(const void* indptr, int indptr_is_64,
+                    const int32_t* indices, const double* data, int64_t n,
+                    int64_t p, double* xw, int64_t n_pad, int64_t p_pad,
+                    cudaStream_t s);
+
+// gram_f64.cu
+int launch_gram_diag(const scedar_cells* c, cudaStream_t s);
+int launch_gram_stripe(const scedar_cells* c, int64_t row_begin,
+                       int64_t row_end, double* d_out, int64_t ldd,
+                       cudaStream_t s);
+int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
+                          cudaStream_t s);
+// fused Gram -> top-K; part_d/part_i: [splits, rows, K] partial lists
+int gram_topk_splits(const scedar_cells* c, int64_t rows);
+int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                     int K, int splits, double* part_d, int32_t* part_i,
+                     cudaStream_t s);
+
+// topk.cu
+int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols,
+                       int64_t row_begin, int64_t row_end, int k, int exclude,
+                       int64_t* idx_out, double* dist_out, cudaStream_t s);
+int launch_topk_merge(const double* part_d, const int32_t* part_i, int splits,
+                      int64_t rows, int K, int64_t row_begin, int k,
+                      int exclude, int64_t* idx_out, double* dist_out,
+                      cudaStream_t s);
+int launch_col_sort(const double* d, int64_t ldd, int64_t rows, int64_t n,
+                    double* sorted_out, int64_t* argsorted_out,
+                    cudaStream_t s);
+
+// ncdm.cu
+int launch_ncdm(double* d, int64_t ldd, int64_t n, int has_ub, double ub,
+                int32_t* flags, cudaStream_t s);
+
+}  // namespace scedar

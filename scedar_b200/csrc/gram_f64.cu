@@ -1,0 +1,435 @@
+// K2 (FP64 path) -- Gram contraction X.Xt on the float64 tensor-core pipe
+// (mma.sync m8n8k4 f64, "DMMA") with the metric epilogue fused, and the fused
+// streaming top-k (K3) that consumes tiles without writing D.
+//
+// tcgen05.mma has no f64 kind (CUDA 12.9: f16/tf32/i8/f8f6f4/mx*), so the path
+// that must match the reference's float64 to 1e-10 runs on DMMA; the tcgen05
+// path is the split-BF16 fast path in gram_tc.cu.
+//
+// Reference arithmetic replaced (scedar/eda/sdm.py):
+//   np.dot(x, x.T)                                   1245-1247
+//   inv = sqrt(1/ss or 0); (P*inv).T*inv; 1 - S       1249-1266
+//   sklearn euclidean: (-2P + |x_i|^2) + |x_j|^2, max 0, sqrt      1216
+//   num_correct_dist_mat: <0 -> 0, diag 0, upper := lower           215-221
+// The lower triangle survives the mirror, so entry (i, j) is evaluated as the
+// reference evaluates (max(i,j), min(i,j)): scale by the statistic of the
+// larger index first, then the smaller -- bit-identical on both sides of the
+// diagonal by construction.  Products are kept out of FMA contraction with
+// __dmul_rn/__dadd_rn so exact ties in integer data stay exact ties.
+//
+// Tiling: CTA 128x128, 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA fragments,
+// K slab 16 doubles (one 128-byte line per row), 3-stage cp.async pipeline.
+// smem rows are padded to 20 doubles so the 64-bit fragment loads of a
+// half-warp (4 rows x 4 k) hit 16 distinct 8-byte banks.
+// Roofline: FP64 tensor pipe; algorithmic flops 2*rows*n*p per stripe
+// (n(n+1)p for the symmetric variant).  HBM traffic is bounded by the tile
+// swizzle (16 row panels stay in L2 while the column panels stream once).
+#include "common.cuh"
+
+namespace scedar {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3;
+constexpr int LDK = 20;   // padded K stride of a smem row (doubles)
+constexpr int NT = 256;
+constexpr int STAGE_DOUBLES = (BM + BN) * LDK;
+constexpr int LDT = 129;  // odd stride: conflict-free row and column sweeps
+constexpr int TILE_DOUBLES = BM * LDT;
+constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;
+constexpr int TILE_BYTES = TILE_DOUBLES * 8;
+constexpr int MAIN_BYTES = PIPE_BYTES > TILE_BYTES ? PIPE_BYTES : TILE_BYTES;
+constexpr int KFUSED = 32;  // entries kept per row by the fused top-k
+constexpr int LIST_BYTES = BM * KFUSED * (8 + 4);
+constexpr int GROUP_ROWS = 16;  // row tiles per L2 swizzle group
+
+enum Mode { MODE_STORE = 0, MODE_SYM = 1, MODE_DIAG = 2, MODE_TOPK = 3 };
+
+struct GramArgs {
+  const double* xw;
+  const double* stat;
+  int64_t n, n_pad, p_pad;
+  int64_t row_begin, row_end;  // rows of D this launch owns
+  double* out;                 // D stripe (STORE/SYM) or stat (DIAG)
+  int64_t ldd;
+  int euclid;
+  // TOPK
+  int K, splits;
+  double* part_d;
+  int32_t* part_i;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+// one K slab (16 doubles) of the A and B row panels -> stage buffer
+__device__ __forceinline__ void load_stage(double* stage, const double* __restrict__ xw,
+                                           int64_t p_pad, int64_t i0, int64_t j0,
+                                           int64_t k0, int tid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * NT;
+    const int r = idx >> 3, c = idx & 7;
+    cp_async16(stage + r * LDK + c * 2, xw + (i0 + r) * p_pad + k0 + c * 2);
+    cp_async16(stage + (BM + r) * LDK + c * 2, xw + (j0 + r) * p_pad + k0 + c * 2);
+  }
+}
+
+// acc[mf][nf][2] += A(i0.., :) . B(j0.., :)^T over the whole padded K range
+__device__ __forceinline__ void gram_mainloop(double (&acc)[8][4][2], double* smem,
+                                              const double* __restrict__ xw,
+                                              int64_t p_pad, int64_t i0, int64_t j0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mf = 0; mf < 8; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+
+  const int KT = (int)(p_pad / BK);
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage(smem + s * STAGE_DOUBLES, xw, p_pad, i0, j0, (int64_t)s * BK, tid);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = kt + STAGES - 1;
+    if (nxt < KT)
+      load_stage(smem + (nxt % STAGES) * STAGE_DOUBLES, xw, p_pad, i0, j0, (int64_t)nxt * BK, tid);
+    cp_async_commit();
+    const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64 + g) * LDK + t;
+    const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + (BM + wn * 32 + g) * LDK + t;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[8], b[4];
+#pragma unroll
+      for (int mf = 0; mf < 8; ++mf) a[mf] = As[mf * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) b[nf] = Bs[nf * 8 * LDK + kk * 4];
+#pragma unroll
+      for (int mf = 0; mf < 8; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) dmma(acc[mf][nf], a[mf], b[nf]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // pipeline buffers are free: the epilogue tile aliases them
+}
+
+__device__ __forceinline__ double finish_entry(double P, double s_hi, double s_lo,
+                                               bool diag, int euclid) {
+  double d;
+  if (euclid) {
+    double t2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, P), s_hi), s_lo);
+    t2 = t2 < 0.0 ? 0.0 : t2;
+    d = __dsqrt_rn(t2);
+  } else {
+    d = __dsub_rn(1.0, __dmul_rn(__dmul_rn(P, s_hi), s_lo));
+    d = d < 0.0 ? 0.0 : d;
+  }
+  return diag ? 0.0 : d;
+}
+
+// accumulators -> metric epilogue -> smem tile T[r][c] (stride LDT)
+template <bool RAW>
+__device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], double* T,
+                                             const double* __restrict__ stat,
+                                             int64_t i0, int64_t j0, int euclid) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+  double sr[8], sc[4][2];
+  if (!RAW) {
+#pragma unroll
+    for (int mf = 0; mf < 8; ++mf) sr[mf] = __ldg(stat + i0 + wm * 64 + mf * 8 + g);
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      sc[nf][0] = __ldg(stat + j0 + wn * 32 + nf * 8 + 2 * t);
+      sc[nf][1] = __ldg(stat + j0 + wn * 32 + nf * 8 + 2 * t + 1);
+    }
+  }
+#pragma unroll
+  for (int mf = 0; mf < 8; ++mf) {
+    const int r = wm * 64 + mf * 8 + g;
+    const int64_t gi = i0 + r;
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = wn * 32 + nf * 8 + 2 * t + e;
+        double v = acc[mf][nf][e];
+        if (!RAW) {
+          const int64_t gj = j0 + c;
+          const bool lower = gi >= gj;
+          v = finish_entry(v, lower ? sr[mf] : sc[nf][e], lower ? sc[nf][e] : sr[mf],
+                           gi == gj, euclid);
+        }
+        T[r * LDT + c] = v;
+      }
+    }
+  }
+}
+
+// ---- warp-resident sorted list (one entry per lane), order (d, idx) --------
+__device__ __forceinline__ bool before(double d, int j, double td, int tj) {
+  return d < td || (d == td && j < tj);
+}
+__device__ __forceinline__ void warp_insert(double& ld, int& li, double d, int j, int lane) {
+  const unsigned less = __ballot_sync(0xffffffffu, before(ld, li, d, j));
+  const int pos = __popc(less);
+  const double pd = __shfl_up_sync(0xffffffffu, ld, 1);
+  const int pi = __shfl_up_sync(0xffffffffu, li, 1);
+  if (lane > pos) {
+    ld = pd;
+    li = pi;
+  } else if (lane == pos) {
+    ld = d;
+    li = j;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t CT = a.n_pad / BN;
+
+  if (MODE == MODE_TOPK) {
+    // this CTA owns row tile I and the column tiles [J0, J1)
+    double* Ld = smem + MAIN_BYTES / 8;
+    int* Li = reinterpret_cast<int*>(Ld + BM * KFUSED);
+    const int64_t I = a.row_begin / BM + blockIdx.x;
+    const int64_t i0 = I * BM;
+    const int64_t J0 = CT * blockIdx.y / a.splits, J1 = CT * (blockIdx.y + 1) / a.splits;
+    for (int e = tid; e < BM * KFUSED; e += NT) {
+      Ld[e] = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+      Li[e] = 0x7fffffff;
+    }
+    __syncthreads();
+    const int K = a.K;
+    for (int64_t J = J0; J < J1; ++J) {
+      const int64_t j0 = J * BN;
+      double acc[8][4][2];
+      gram_mainloop(acc, smem, a.xw, a.p_pad, i0, j0);
+      tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid);
+      __syncthreads();
+      // warp w scans rows w, w+8, ...; lane l holds entry l of the row's list
+      for (int r = warp; r < BM; r += NT / 32) {
+        const int64_t gi = i0 + r;
+        if (gi < a.row_begin || gi >= a.row_end) continue;
+        double ld = Ld[r * KFUSED + lane];
+        int li = Li[r * KFUSED + lane];
+        double td = __shfl_sync(0xffffffffu, ld, K - 1);
+        int tj = __shfl_sync(0xffffffffu, li, K - 1);
+        bool dirty = false;
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q) {
+          const int c = lane + 32 * q;
+          const int64_t gj = j0 + c;
+          const double v = smem[r * LDT + c];
+          unsigned m = __ballot_sync(0xffffffffu, gj < a.n && before(v, (int)gj, td, tj));
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double d = __shfl_sync(0xffffffffu, v, src);
+            const int j = (int)(j0 + src + 32 * q);
+            if (before(d, j, td, tj)) {
+              warp_insert(ld, li, d, j, lane);
+              td = __shfl_sync(0xffffffffu, ld, K - 1);
+              tj = __shfl_sync(0xffffffffu, li, K - 1);
+              dirty = true;
+            }
+          }
+        }
+        if (dirty) {
+          Ld[r * KFUSED + lane] = ld;
+          Li[r * KFUSED + lane] = li;
+        }
+      }
+      __syncthreads();
+    }
+    // partial lists out: part[split][row - row_begin][K]
+    const int64_t rows = a.row_end - a.row_begin;
+    for (int e = tid; e < BM * K; e += NT) {
+      const int r = e / K, l = e % K;
+      const int64_t gi = i0 + r;
+      if (gi < a.row_begin || gi >= a.row_end) continue;
+      const int64_t o = ((int64_t)blockIdx.y * rows + (gi - a.row_begin)) * K + l;
+      a.part_d[o] = Ld[r * KFUSED + l];
+      a.part_i[o] = Li[r * KFUSED + l];
+    }
+    return;
+  }
+
+  // ---- tile coordinates --------------------------------------------------
+  int64_t I, J;
+  if (MODE == MODE_DIAG) {
+    I = J = blockIdx.x;
+  } else {
+    const int64_t rt0 = a.row_begin / BM;
+    const int64_t RT = (a.row_end + BM - 1) / BM - rt0;
+    const int64_t per_group = (int64_t)GROUP_ROWS * CT;
+    const int64_t grp = blockIdx.x / per_group, rem = blockIdx.x % per_group;
+    const int64_t left = RT - grp * GROUP_ROWS;
+    const int64_t rows_here = left < GROUP_ROWS ? left : GROUP_ROWS;
+    I = rt0 + grp * GROUP_ROWS + rem % rows_here;
+    J = rem / rows_here;
+    if (MODE == MODE_SYM && J > I) return;  // upper tiles come from the mirror
+  }
+  const int64_t i0 = I * BM, j0 = J * BN;
+
+  double acc[8][4][2];
+  gram_mainloop(acc, smem, a.xw, a.p_pad, i0, j0);
+
+  if (MODE == MODE_DIAG) {
+    tile_to_smem<true>(acc, smem, nullptr, i0, j0, 0);
+    __syncthreads();
+    if (tid < BM) {
+      const double ss = smem[tid * LDT + tid];
+      double s;
+      if (a.euclid) {
+        s = ss;  // |x|^2
+      } else {
+        // sqrt(1/ss), 0 for a zero vector (sdm.py:1259-1261)
+        s = __dsqrt_rn(ss != 0.0 ? __ddiv_rn(1.0, ss) : 0.0);
+      }
+      a.out[i0 + tid] = s;
+    }
+    return;
+  }
+
+  tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid);
+  __syncthreads();
+  // rows of the tile -> rows of D (256-byte coalesced warp stores)
+  for (int r = warp; r < BM; r += NT / 32) {
+    const int64_t gi = i0 + r;
+    if (gi < a.row_begin || gi >= a.row_end) continue;
+    double* __restrict__ dst = a.out + (gi - a.row_begin) * a.ldd + j0;
+#pragma unroll
+    for (int q = 0; q < BN / 32; ++q) {
+      const int c = lane + 32 * q;
+      if (j0 + c < a.n) dst[c] = smem[r * LDT + c];
+    }
+  }
+  if (MODE == MODE_SYM && I != J) {
+    // mirrored tile: column c of T is row j0+c of D
+    for (int c = warp; c < BN; c += NT / 32) {
+      const int64_t gj = j0 + c;
+      if (gj >= a.n) continue;
+      double* __restrict__ dst = a.out + gj * a.ldd + i0;
+#pragma unroll
+      for (int q = 0; q < BM / 32; ++q) {
+        const int r = lane + 32 * q;
+        if (i0 + r < a.n) dst[r] = smem[r * LDT + c];
+      }
+    }
+  }
+}
+
+template <int MODE>
+int launch(const GramArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    SCEDAR_CUDA(cudaFuncSetAttribute(gram_f64_kernel<MODE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     MAIN_BYTES + LIST_BYTES));
+    configured = true;
+  }
+  gram_f64_kernel<MODE><<<grid, NT, smem_bytes, s>>>(a);
+  SCEDAR_CUDA(cudaGetLastError());
+  return SCEDAR_OK;
+}
+
+GramArgs base_args(const scedar_cells* c) {
+  GramArgs a{};
+  a.xw = c->xw;
+  a.stat = c->stat;
+  a.n = c->n;
+  a.n_pad = c->n_pad;
+  a.p_pad = c->p_pad;
+  a.euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
+  return a;
+}
+
+}  // namespace
+
+int launch_gram_diag(const scedar_cells* c, cudaStream_t s) {
+  GramArgs a = base_args(c);
+  a.row_begin = 0;
+  a.row_end = c->n_pad;
+  a.out = c->stat;
+  return launch<MODE_DIAG>(a, dim3((unsigned)(c->n_pad / BM)), MAIN_BYTES, s);
+}
+
+int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                       double* d_out, int64_t ldd, cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  GramArgs a = base_args(c);
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.out = d_out;
+  a.ldd = ldd;
+  const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
+  const int64_t tiles = RT * (c->n_pad / BN);
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");
+  return launch<MODE_STORE>(a, dim3((unsigned)tiles), MAIN_BYTES, s);
+}
+
+int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
+                          cudaStream_t s) {
+  if (c->n == 0) return SCEDAR_OK;
+  GramArgs a = base_args(c);
+  a.row_begin = 0;
+  a.row_end = c->n;
+  a.out = d_out;
+  a.ldd = ldd;
+  const int64_t RT = (c->n + BM - 1) / BM;
+  const int64_t tiles = RT * (c->n_pad / BN);
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "matrix too large for one launch");
+  return launch<MODE_SYM>(a, dim3((unsigned)tiles), MAIN_BYTES, s);
+}
+
+int gram_topk_splits(const scedar_cells* c, int64_t rows) {
+  // enough CTAs for ~2 waves of the SMs, at most one split per column tile
+  const int64_t row_tiles = (rows + BM - 1) / BM + 1;
+  const int64_t CT = c->n_pad / BN;
+  int64_t s = (2 * (int64_t)num_sms() + row_tiles - 1) / row_tiles;
+  if (s < 1) s = 1;
+  if (s > CT) s = CT;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+
+int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                     int K, int splits, double* part_d, int32_t* part_i,
+                     cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  if (K < 1 || K > KFUSED) return fail(SCEDAR_ERR_UNSUPPORTED, "fused top-k keeps at most 32 entries");
+  GramArgs a = base_args(c);
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.K = K;
+  a.splits = splits;
+  a.part_d = part_d;
+  a.part_i = part_i;
+  const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
+  return launch<MODE_TOPK>(a, dim3((unsigned)RT, (unsigned)splits), MAIN_BYTES + LIST_BYTES, s);
+}
+
+}  // namespace scedar

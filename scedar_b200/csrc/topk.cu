@@ -1,0 +1,348 @@
+// K3 -- row-wise k-nearest-neighbour selection (HBM-bound) and the full stable
+// column sort.
+//
+// Order everywhere is (distance, index) ascending: the order of
+// np.argsort(kind="mergesort") on a column of D (scedar/eda/sdm.py:1298-1305),
+// i.e. exact ties go to the lower cell index.
+//
+//   topk_from_d : one warp streams one row of a materialised D stripe
+//                 (8*n bytes per row, coalesced 256-byte warp loads, 8 loads in
+//                 flight per lane) and keeps the k+1 best in registers -- a
+//                 sorted list striped over the lanes, threshold-gated so almost
+//                 every element costs one compare; insertions are warp-shuffle
+//                 shifts.  Replaces sdm.py:764 and NearestNeighbors
+//                 (metric="precomputed") sdm.py:1070-1079.
+//   topk_merge  : merges the per-column-split partial lists of the fused
+//                 Gram->top-k kernel and applies the same exclusion rule.
+//   col_sort    : bitonic sort of (distance, index) pairs per row, shared
+//                 memory for spans <= 4096 and global passes above
+//                 (np.sort / np.argsort(kind="mergesort", axis=0), 1289-1305).
+#include "common.cuh"
+
+namespace scedar {
+namespace {
+
+constexpr int kMaxR = 4;  // registers per lane -> up to 128 entries per row
+
+__device__ __forceinline__ bool before(double d, int j, double td, int tj) {
+  return d < td || (d == td && j < tj);
+}
+__device__ __forceinline__ double pos_inf() {
+  return __longlong_as_double(0x7ff0000000000000LL);
+}
+
+// Sorted list of 32*R (distance, index) entries; entry e lives in register
+// e/32 of lane e%32.
+template <int R>
+struct WarpList {
+  double d[R];
+  int i[R];
+  double td;  // threshold = entry K-1
+  int tj;
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      d[r] = pos_inf();
+      i[r] = 0x7fffffff;
+    }
+    td = pos_inf();
+    tj = 0x7fffffff;
+  }
+  __device__ __forceinline__ void refresh(int K) {
+    const int kr = (K - 1) >> 5, kl = (K - 1) & 31;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double x = __shfl_sync(0xffffffffu, d[r], kl);
+      const int y = __shfl_sync(0xffffffffu, i[r], kl);
+      if (r == kr) {
+        td = x;
+        tj = y;
+      }
+    }
+  }
+  // warp-uniform (nd, nj); caller has checked before(nd, nj, td, tj)
+  __device__ __forceinline__ void insert(double nd, int nj, int lane) {
+    int pos = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      pos += __popc(__ballot_sync(0xffffffffu, before(d[r], i[r], nd, nj)));
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+      double pd = __shfl_up_sync(0xffffffffu, d[r], 1);
+      int pi = __shfl_up_sync(0xffffffffu, i[r], 1);
+      if (r > 0) {
+        const double cd = __shfl_sync(0xffffffffu, d[r - 1], 31);
+        const int ci = __shfl_sync(0xffffffffu, i[r - 1], 31);
+        if (lane == 0) {
+          pd = cd;
+          pi = ci;
+        }
+      }
+      const int e = r * 32 + lane;
+      if (e > pos) {
+        d[r] = pd;
+        i[r] = pi;
+      } else if (e == pos) {
+        d[r] = nd;
+        i[r] = nj;
+      }
+    }
+  }
+  // offer a per-lane candidate (v, j); `ok` masks lanes without one
+  __device__ __forceinline__ void offer(double v, int j, bool ok, int K, int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, ok && before(v, j, td, tj));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const double nd = __shfl_sync(0xffffffffu, v, src);
+      const int nj = __shfl_sync(0xffffffffu, j, src);
+      if (before(nd, nj, td, tj)) {
+        insert(nd, nj, lane);
+        refresh(K);
+      }
+    }
+  }
+  // write the k survivors of the k+1 kept: drop the row itself when present
+  // (exclude == SELF), otherwise rank 0
+  __device__ __forceinline__ void emit(int K, int exclude, int self, int64_t* idx_out,
+                                       double* dist_out, int lane) {
+    int drop = 0;
+    if (exclude == SCEDAR_EXCLUDE_SELF) {
+      int found = 0x7fffffff;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int e = r * 32 + lane;
+        const unsigned hit = __ballot_sync(0xffffffffu, e < K && i[r] == self);
+        if (hit && found == 0x7fffffff) found = r * 32 + __ffs(hit) - 1;
+      }
+      if (found != 0x7fffffff) drop = found;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int e = r * 32 + lane;
+      if (e < K && e != drop) {
+        const int o = e < drop ? e : e - 1;
+        idx_out[o] = i[r] == 0x7fffffff ? -1 : (int64_t)i[r];
+        dist_out[o] = d[r];
+      }
+    }
+  }
+};
+
+template <int R>
+__global__ void __launch_bounds__(256)
+topk_from_d_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols,
+                   int64_t row_begin, int64_t rows, int k, int exclude,
+                   int64_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int K = k + 1;
+  const double* __restrict__ src = d + row * ldd;
+  WarpList<R> L;
+  L.init();
+  constexpr int U = 8;
+  for (int64_t base = 0; base < n_cols; base += 32 * U) {
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t c = base + u * 32 + lane;
+      v[u] = c < n_cols ? __ldcs(src + c) : pos_inf();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t c = base + u * 32 + lane;
+      L.offer(v[u], (int)c, c < n_cols, K, lane);
+    }
+  }
+  L.emit(K, exclude, (int)(row_begin + row), idx_out + row * k, dist_out + row * k, lane);
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+topk_merge_kernel(const double* __restrict__ part_d, const int32_t* __restrict__ part_i,
+                  int splits, int64_t rows, int K, int64_t row_begin, int k, int exclude,
+                  int64_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  WarpList<R> L;
+  L.init();
+  for (int s = 0; s < splits; ++s) {
+    const int64_t o = ((int64_t)s * rows + row) * K;
+    for (int e0 = 0; e0 < K; e0 += 32) {
+      const int e = e0 + lane;
+      const bool ok = e < K;
+      const double v = ok ? part_d[o + e] : pos_inf();
+      const int j = ok ? part_i[o + e] : 0x7fffffff;
+      L.offer(v, j, ok, K, lane);
+    }
+  }
+  L.emit(K, exclude, (int)(row_begin + row), idx_out + row * k, dist_out + row * k, lane);
+}
+
+// ---------------------------------------------------------------------------
+// full sort
+// ---------------------------------------------------------------------------
+constexpr int SORT_BLK = 4096;  // elements sorted in shared memory per CTA
+constexpr int SORT_NT = 512;
+
+__device__ __forceinline__ void cmp_swap(double& ad, int& ai, double& bd, int& bi, bool up) {
+  // ascending span (up): the smaller goes first
+  if (before(bd, bi, ad, ai) == up) {
+    const double t = ad;
+    ad = bd;
+    bd = t;
+    const int u = ai;
+    ai = bi;
+    bi = u;
+  }
+}
+
+// k_lo == 2: full local sort of each SORT_BLK span (directions follow the
+// global index so spans alternate as the bitonic network needs);
+// k_lo == k_hi > SORT_BLK: the j < SORT_BLK tail of merge stage k.
+__global__ void __launch_bounds__(SORT_NT)
+bitonic_local_kernel(double* __restrict__ kd, int* __restrict__ ki, int64_t N2,
+                     int64_t k_lo, int64_t k_hi) {
+  __shared__ double sd[SORT_BLK];
+  __shared__ int si[SORT_BLK];
+  const int64_t spans = N2 / SORT_BLK;
+  const int64_t row = blockIdx.x / spans, span = blockIdx.x % spans;
+  const int64_t g0 = span * SORT_BLK;
+  double* __restrict__ gd = kd + row * N2 + g0;
+  int* __restrict__ gi = ki + row * N2 + g0;
+  for (int e = threadIdx.x; e < SORT_BLK; e += SORT_NT) {
+    sd[e] = gd[e];
+    si[e] = gi[e];
+  }
+  __syncthreads();
+  for (int64_t k = k_lo; k <= k_hi; k <<= 1) {
+    int64_t jstart = k >> 1;
+    if (jstart >= SORT_BLK) jstart = SORT_BLK >> 1;
+    for (int64_t j = jstart; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < SORT_BLK / 2; t += SORT_NT) {
+        const int lo = (int)(((t & ~(j - 1)) << 1) | (t & (j - 1)));
+        const int hi = lo | (int)j;
+        const bool up = ((g0 + lo) & k) == 0;
+        cmp_swap(sd[lo], si[lo], sd[hi], si[hi], up);
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = threadIdx.x; e < SORT_BLK; e += SORT_NT) {
+    gd[e] = sd[e];
+    gi[e] = si[e];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bitonic_global_kernel(double* __restrict__ kd, int* __restrict__ ki, int64_t N2,
+                      int64_t rows, int64_t k, int64_t j) {
+  const int64_t half = N2 >> 1;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * half) return;
+  const int64_t row = gid / half, t = gid % half;
+  const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+  const int64_t hi = lo | j;
+  const bool up = (lo & k) == 0;
+  double* __restrict__ d = kd + row * N2;
+  int* __restrict__ i = ki + row * N2;
+  double ad = d[lo], bd = d[hi];
+  int ai = i[lo], bi = i[hi];
+  if (before(bd, bi, ad, ai) == up) {
+    d[lo] = bd;
+    d[hi] = ad;
+    i[lo] = bi;
+    i[hi] = ai;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sort_fill_kernel(const double* __restrict__ d, int64_t ldd, int64_t n, int64_t row0,
+                 int64_t rows, int64_t N2, double* __restrict__ kd, int* __restrict__ ki) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * N2) return;
+  const int64_t r = gid / N2, c = gid % N2;
+  // column j of a symmetric D == row j: read rows (coalesced)
+  kd[gid] = c < n ? d[(row0 + r) * ldd + c] : pos_inf();
+  ki[gid] = c < n ? (int)c : 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(256)
+sort_emit_kernel(const double* __restrict__ kd, const int* __restrict__ ki, int64_t n,
+                 int64_t row0, int64_t rows, int64_t N2, double* __restrict__ sorted_out,
+                 int64_t* __restrict__ arg_out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * n) return;
+  const int64_t r = gid / n, c = gid % n;
+  if (sorted_out) sorted_out[(row0 + r) * n + c] = kd[r * N2 + c];
+  if (arg_out) arg_out[(row0 + r) * n + c] = ki[r * N2 + c];
+}
+
+}  // namespace
+
+int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row_begin,
+                       int64_t row_end, int k, int exclude, int64_t* idx_out,
+                       double* dist_out, cudaStream_t s) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0 || k == 0) return SCEDAR_OK;
+  const int K = k + 1;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (K <= 32)
+    topk_from_d_kernel<1><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out);
+  else if (K <= 64)
+    topk_from_d_kernel<2><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out);
+  else if (K <= 32 * kMaxR)
+    topk_from_d_kernel<4><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out);
+  else
+    return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
+  SCEDAR_CUDA(cudaGetLastError());
+  return SCEDAR_OK;
+}
+
+int launch_topk_merge(const double* part_d, const int32_t* part_i, int splits, int64_t rows,
+                      int K, int64_t row_begin, int k, int exclude, int64_t* idx_out,
+                      double* dist_out, cudaStream_t s) {
+  if (rows <= 0 || k == 0) return SCEDAR_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (K <= 32)
+    topk_merge_kernel<1><<<grid, 256, 0, s>>>(part_d, part_i, splits, rows, K, row_begin, k, exclude, idx_out, dist_out);
+  else
+    return fail(SCEDAR_ERR_UNSUPPORTED, "merge of more than 32 entries per row");
+  SCEDAR_CUDA(cudaGetLastError());
+  return SCEDAR_OK;
+}
+
+int launch_col_sort(const double* d, int64_t ldd, int64_t total_rows, int64_t n,
+                    double* sorted_out, int64_t* argsorted_out, cudaStream_t s) {
+  if (n == 0 || total_rows == 0) return SCEDAR_OK;
+  int64_t N2 = SORT_BLK;
+  while (N2 < n) N2 <<= 1;
+  // rows per pass: keep the (8+4)-byte pair workspace under ~2 GiB
+  int64_t chunk = (int64_t(2) << 30) / (N2 * 12);
+  if (chunk < 1) chunk = 1;
+  if (chunk > total_rows) chunk = total_rows;
+  Scratch wd, wi;
+  SCEDAR_CHECK(wd.alloc(sizeof(double) * chunk * N2, s));
+  SCEDAR_CHECK(wi.alloc(sizeof(int) * chunk * N2, s));
+  double* kd = wd.as<double>();
+  int* ki = wi.as<int>();
+  for (int64_t row0 = 0; row0 < total_rows; row0 += chunk) {
+    const int64_t rows = (total_rows - row0) < chunk ? (total_rows - row0) : chunk;
+    sort_fill_kernel<<<(unsigned)((rows * N2 + 255) / 256), 256, 0, s>>>(d, ldd, n, row0, rows, N2, kd, ki);
+    const unsigned local_grid = (unsigned)(rows * (N2 / SORT_BLK));
+    bitonic_local_kernel<<<local_grid, SORT_NT, 0, s>>>(kd, ki, N2, 2, SORT_BLK);
+    for (int64_t k = 2 * SORT_BLK; k <= N2; k <<= 1) {
+      for (int64_t j = k >> 1; j >= SORT_BLK; j >>= 1)
+        bitonic_global_kernel<<<(unsigned)((rows * (N2 / 2) + 255) / 256), 256, 0, s>>>(kd, ki, N2, rows, k, j);
+      bitonic_local_kernel<<<local_grid, SORT_NT, 0, s>>>(kd, ki, N2, k, k);
+    }
+    sort_emit_kernel<<<(unsigned)((rows * n + 255) / 256), 256, 0, s>>>(kd, ki, n, row0, rows, N2, sorted_out, argsorted_out);
+    SCEDAR_CUDA(cudaGetLastError());
+  }
+  return SCEDAR_OK;
+}
+
+}  // namespace scedar

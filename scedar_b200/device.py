@@ -1,0 +1,185 @@
+"""Device-level operators: torch tensors in HBM in, torch tensors out.
+
+torch is only the allocator / stream provider here; every kernel is in
+``csrc/`` behind the C ABI.  All functions run on the current CUDA device and
+the current torch stream.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import EXCLUDE_FIRST, EXCLUDE_SELF, METRIC_IDS, PRECISION_IDS
+
+_INIT_PID = os.getpid()
+
+
+def _guard():
+    """A CUDA context does not survive fork(); the reference's ``parmap``
+    (scedar/utils.py:45-52) forks.  Refuse instead of crashing the GPU."""
+    if os.getpid() != _INIT_PID and torch.cuda.is_initialized():
+        raise RuntimeError(
+            "scedar_b200: CUDA was initialised in the parent process; the GPU "
+            "path cannot be entered from a forked child (run with nprocs=1)")
+    if not torch.cuda.is_available():
+        raise RuntimeError("scedar_b200: no CUDA device -- this package has no "
+                           "CPU fallback")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _f64(t):
+    assert t.is_cuda and t.dtype == torch.float64, "need a CUDA float64 tensor"
+    return t
+
+
+class Cells(object):
+    """Prepared cells x genes matrix resident in HBM (``scedar_cells_t``).
+
+    The constructor arguments are kept alive until the preparation kernels
+    have been enqueued; the handle owns its own padded working copy.
+    """
+
+    def __init__(self, handle, n, p, metric):
+        self._h = handle
+        self.n, self.p, self.metric = int(n), int(p), metric
+
+    @classmethod
+    def from_dense(cls, x, metric):
+        _guard()
+        lib = _capi.load()
+        x = _f64(x)
+        if x.dim() != 2:
+            raise ValueError("x has shape (n_samples, n_features)")
+        if x.stride(1) != 1 and x.shape[1] > 1:
+            x = x.contiguous()
+        n, p = x.shape
+        ldx = x.stride(0) if n > 1 and p > 0 else max(p, 1)
+        if ldx < p:
+            x, ldx = x.contiguous(), max(p, 1)
+        h = ctypes.c_void_p()
+        _capi.check(lib.scedar_cells_from_dense(
+            _ptr(x), n, p, ldx, METRIC_IDS[metric], _stream(),
+            ctypes.byref(h)))
+        return cls(h, n, p, metric)
+
+    @classmethod
+    def from_csr(cls, indptr, indices, data, shape, metric):
+        _guard()
+        lib = _capi.load()
+        n, p = shape
+        assert indptr.dtype in (torch.int32, torch.int64)
+        assert indices.dtype == torch.int32 and data.dtype == torch.float64
+        h = ctypes.c_void_p()
+        _capi.check(lib.scedar_cells_from_csr(
+            _ptr(indptr), int(indptr.dtype == torch.int64), _ptr(indices),
+            _ptr(data), n, p, METRIC_IDS[metric], _stream(), ctypes.byref(h)))
+        torch.cuda.current_stream().synchronize()  # inputs may now be freed
+        return cls(h, n, p, metric)
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _capi.load().scedar_cells_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- distance matrix ----------------------------------------------------
+    def pdist_stripe(self, row_begin=0, row_end=None, out=None,
+                     precision="fp64"):
+        """Rows [row_begin, row_end) of D -> float64 tensor [rows, n]."""
+        row_end = self.n if row_end is None else row_end
+        rows = row_end - row_begin
+        if out is None:
+            out = torch.empty((max(rows, 0), self.n), dtype=torch.float64,
+                              device="cuda")
+        _capi.check(_capi.load().scedar_pdist_stripe(
+            self._h, PRECISION_IDS[precision], row_begin, row_end, _ptr(out),
+            out.stride(0) if out.dim() == 2 and out.shape[0] > 1 else self.n,
+            _stream()))
+        return out
+
+    def pdist_symmetric(self, out=None, precision="fp64"):
+        """All of D, lower-triangle tiles computed once and mirrored."""
+        if out is None:
+            out = torch.empty((self.n, self.n), dtype=torch.float64,
+                              device="cuda")
+        _capi.check(_capi.load().scedar_pdist_symmetric(
+            self._h, PRECISION_IDS[precision], _ptr(out),
+            out.stride(0) if self.n > 1 else self.n, _stream()))
+        return out
+
+    # -- kNN without D ------------------------------------------------------
+    def knn_stripe(self, k, exclude=EXCLUDE_SELF, row_begin=0, row_end=None,
+                   precision="fp64"):
+        row_end = self.n if row_end is None else row_end
+        rows = max(row_end - row_begin, 0)
+        idx = torch.empty((rows, k), dtype=torch.int64, device="cuda")
+        dist = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+        _capi.check(_capi.load().scedar_knn_stripe(
+            self._h, PRECISION_IDS[precision], k, exclude, row_begin, row_end,
+            _ptr(idx), _ptr(dist), _stream()))
+        return idx, dist
+
+
+def knn_from_d(d, k, exclude=EXCLUDE_SELF, row_begin=0):
+    """Top-k of every row of a materialised stripe ``d`` [rows, n]; row r is
+    cell ``row_begin + r``."""
+    _guard()
+    d = _f64(d)
+    rows, n = d.shape
+    idx = torch.empty((rows, k), dtype=torch.int64, device="cuda")
+    dist = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+    _capi.check(_capi.load().scedar_knn_from_d(
+        _ptr(d), d.stride(0) if rows > 1 else n, n, row_begin,
+        row_begin + rows, k, exclude, _ptr(idx), _ptr(dist), _stream()))
+    return idx, dist
+
+
+def col_sort(d, want_sorted=True, want_arg=True):
+    """Stable sort of every row of a stripe ``d`` [rows, n] of a symmetric D
+    (row j of D == column j).  Returns cell-major [rows, n] tensors -- the
+    transpose of the reference's (rank, cell) layout; either may be None."""
+    _guard()
+    d = _f64(d)
+    rows, n = d.shape
+    srt = (torch.empty((rows, n), dtype=torch.float64, device="cuda")
+           if want_sorted else None)
+    arg = (torch.empty((rows, n), dtype=torch.int64, device="cuda")
+           if want_arg else None)
+    _capi.check(_capi.load().scedar_col_sort(
+        _ptr(d), d.stride(0) if rows > 1 else max(n, 1), rows, n, _ptr(srt),
+        _ptr(arg), _stream()))
+    return srt, arg
+
+
+def num_correct_dist_mat_(d, upper_bound=None):
+    """In-place clean-up of a device matrix; returns the warning flag bits."""
+    _guard()
+    d = _f64(d)
+    n = d.shape[0]
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _capi.check(_capi.load().scedar_num_correct_dist_mat(
+        _ptr(d), d.stride(0) if n > 1 else max(n, 1), n,
+        int(upper_bound is not None),
+        float(upper_bound) if upper_bound is not None else 0.0, _ptr(flags),
+        _stream()))
+    return int(flags.item())
+
+
+def to_device(a):
+    """Host ndarray -> CUDA tensor through pinned memory."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.pin_memory().cuda(non_blocking=True) if t.numel() else t.cuda()

@@ -1,0 +1,466 @@
+"""Drop-in ``SampleDistanceMatrix`` for the distance-matrix / kNN hot path.
+
+Mirrors the reference interface for this path (scedar/eda/sdm.py:42-146,
+187-222, 729-947, 1053-1083, 1189-1305 and the input contract of
+scedar/eda/sfm.py:43-75): same constructor, same lazy ``_d`` / ``d`` property,
+same kNN accessors, same cache slot names, same error conventions.  The
+arithmetic the reference delegates to NumPy / SciPy / scikit-learn runs in the
+CUDA library behind ``include/scedar_b200.h``; there is no CPU fallback, and
+metrics outside cosine / correlation / euclidean raise.
+
+Plotting, t-SNE / UMAP / PCA, HNSW and the classified-sample subclasses are
+not part of this path and are not provided here; see
+INTEGRATION.md for patching these hooks into an installed scedar instead.
+"""
+import warnings
+from collections import defaultdict
+
+import numpy as np
+import scipy.sparse as spsparse
+import torch
+
+from . import device as dev
+from ._capi import (EXCLUDE_FIRST, EXCLUDE_SELF, METRIC_IDS, NCDM_ASYMMETRIC,
+                    NCDM_BAD_DIAG)
+
+# D up to this many bytes is also kept resident in HBM between accessors
+DEVICE_D_CACHE_BYTES = 48 << 30
+# stripe size used when D is streamed to the host in pieces
+STRIPE_BYTES = 2 << 30
+MAX_TOPK = 127
+
+
+def _check_is_valid_sfids(sfids):
+    """scedar/eda/mtype.py:52-71."""
+    if sfids is None:
+        raise ValueError("[sf]ids cannot be None")
+    if type(sfids) != list:
+        raise ValueError("[sf]ids must be a homogenous list of int or str")
+    kinds = set(map(type, sfids))
+    if len(kinds) > 1 or (len(kinds) == 1 and
+                          type(sfids[0]) not in (str, int)):
+        raise ValueError("[sf]ids must be a homogenous list of int or str")
+    arr = np.array(sfids)
+    if arr.ndim != 1 or np.unique(arr).shape[0] != arr.shape[0]:
+        raise ValueError("[sf]ids must not contain duplicated values")
+
+
+class SampleDistanceMatrix(object):
+    """Cells x genes matrix with a lazily computed cell x cell distance matrix
+    and k-nearest-neighbour accessors, computed on one B200.
+
+    Parameters are the reference's (sdm.py:93-94).  ``nprocs`` is accepted and
+    stored for compatibility; the device is the current CUDA device.
+    """
+
+    def __init__(self, x, d=None, metric="cosine", use_pdist=True,
+                 sids=None, fids=None, nprocs=None):
+        super(SampleDistanceMatrix, self).__init__()
+        # -- input contract, sfm.py:43-75 (np.asarray instead of
+        #    np.array(copy=False), which NumPy 2 rejects for lists) ----------
+        if x is None:
+            raise ValueError("x cannot be None")
+        if spsparse.issparse(x):
+            x = spsparse.csr_matrix(x, dtype="float64")
+        else:
+            try:
+                x = np.asarray(x, dtype="float64")
+            except ValueError as e:
+                raise ValueError("Features must be float. {}".format(e))
+        if x.ndim != 2:
+            raise ValueError("x has shape (n_samples, n_features)")
+        if sids is None:
+            sids = list(range(x.shape[0]))
+        else:
+            _check_is_valid_sfids(sids)
+            if len(sids) != x.shape[0]:
+                raise ValueError("x has shape (n_samples, n_features)")
+        if fids is None:
+            fids = list(range(x.shape[1]))
+        else:
+            _check_is_valid_sfids(fids)
+            if len(fids) != x.shape[1]:
+                raise ValueError("x has shape (n_samples, n_features)")
+        self._x = x
+        self._sids = np.array(sids)
+        self._fids = np.array(fids)
+
+        # -- sdm.py:97-146 ----------------------------------------------------
+        if d is not None:
+            if not use_pdist:
+                raise ValueError("pdist cannot be provided when "
+                                 "use pdist = False")
+            try:
+                d = np.array(d, dtype="float64")
+            except ValueError as e:
+                raise ValueError("d must be float. {}".format(e))
+            if (d.ndim != 2 or d.shape[0] != d.shape[1]
+                    or d.shape[0] != self._x.shape[0]):
+                raise ValueError("d should have shape (n_samples, n_samples)")
+            d = self.num_correct_dist_mat(d)
+        else:
+            if metric == "precomputed":
+                raise ValueError("metric cannot be precomputed when "
+                                 "d is None.")
+        self._nprocs = 1 if nprocs is None else max(int(nprocs), 1)
+        self._lazy_load_d = d
+        self._metric = metric
+        self._use_pdist = use_pdist
+        self._lazy_load_col_sorted_d = None
+        self._lazy_load_col_argsorted_d = None
+        self._knn_ng_lut = {}
+        self._last_k = None
+        self._last_knns = None
+        # device-side caches (not part of the reference's state)
+        self._cells_lut = {}
+        self._d_dev = None
+
+    # ------------------------------------------------------------------ ids
+    @property
+    def sids(self):
+        return self._sids.tolist()
+
+    @property
+    def fids(self):
+        return self._fids.tolist()
+
+    @property
+    def x(self):
+        return self._x.copy() if self._is_sparse else self._x.tolist()
+
+    @property
+    def _is_sparse(self):
+        return spsparse.issparse(self._x)
+
+    def s_id_to_ind(self, selected_sids):
+        sid_list = self.sids
+        return [sid_list.index(i) for i in selected_sids]
+
+    def f_id_to_ind(self, selected_fids):
+        fid_list = self.fids
+        return [fid_list.index(i) for i in selected_fids]
+
+    def ind_x(self, selected_s_inds=None, selected_f_inds=None):
+        """sdm.py:662-699 -- subsetting slices the cached D, no recompute."""
+        if selected_s_inds is None:
+            selected_s_inds = slice(None, None)
+        if selected_f_inds is None:
+            selected_f_inds = slice(None, None)
+        sub_d = None
+        if self._use_pdist:
+            sub_d = self._d[selected_s_inds, :][:, selected_s_inds].copy()
+        return SampleDistanceMatrix(
+            x=self._x[selected_s_inds, :][:, selected_f_inds].copy(),
+            d=sub_d, metric=self._metric, use_pdist=self._use_pdist,
+            sids=self._sids[selected_s_inds].tolist(),
+            fids=self._fids[selected_f_inds].tolist(), nprocs=self._nprocs)
+
+    def id_x(self, selected_sids=None, selected_fids=None):
+        s = None if selected_sids is None else self.s_id_to_ind(selected_sids)
+        f = None if selected_fids is None else self.f_id_to_ind(selected_fids)
+        return self.ind_x(s, f)
+
+    # ------------------------------------------------------- device helpers
+    def _check_metric(self, metric):
+        if not isinstance(metric, str) or metric not in METRIC_IDS:
+            raise ValueError(
+                "metric {!r} is not on the B200 path; supported: {}".format(
+                    metric, sorted(METRIC_IDS)))
+        if self._is_sparse and metric == "correlation":
+            raise ValueError("Only the following metrics are supportted for "
+                             "sparse matrices, ['cosine', 'euclidean']")
+
+    def _cells(self, metric):
+        """Prepared cells in HBM for ``metric`` (cached per metric)."""
+        self._check_metric(metric)
+        if metric not in self._cells_lut:
+            if self._is_sparse:
+                x = self._x
+                if not x.has_canonical_format:
+                    x = x.copy()
+                    x.sum_duplicates()
+                ip = x.indptr.astype(np.int64, copy=False)
+                cells = dev.Cells.from_csr(
+                    dev.to_device(ip),
+                    dev.to_device(x.indices.astype(np.int32, copy=False)),
+                    dev.to_device(x.data.astype(np.float64, copy=False)),
+                    x.shape, metric)
+            else:
+                cells = dev.Cells.from_dense(dev.to_device(self._x), metric)
+            self._cells_lut[metric] = cells
+        return self._cells_lut[metric]
+
+    def _device_d(self):
+        """D resident in HBM, or None when it is too large to keep."""
+        n = self._x.shape[0]
+        if self._d_dev is None and n * n * 8 <= DEVICE_D_CACHE_BYTES:
+            if self._lazy_load_d is not None:
+                self._d_dev = dev.to_device(self._lazy_load_d)
+            else:
+                self._d_dev = self._cells(self._metric).pdist_symmetric()
+        return self._d_dev
+
+    def _d_stripes(self):
+        """Yield (row_begin, row_end, device stripe of D) covering all rows."""
+        n = self._x.shape[0]
+        whole = self._device_d()
+        if whole is not None:
+            yield 0, n, whole
+            return
+        rows = max(128, (STRIPE_BYTES // (8 * n)) // 128 * 128)
+        if self._lazy_load_d is not None:
+            for r0 in range(0, n, rows):
+                r1 = min(n, r0 + rows)
+                yield r0, r1, dev.to_device(self._lazy_load_d[r0:r1])
+            return
+        cells = self._cells(self._metric)
+        for r0 in range(0, n, rows):
+            r1 = min(n, r0 + rows)
+            yield r0, r1, cells.pdist_stripe(r0, r1)
+
+    # ----------------------------------------------------- distance matrix
+    @staticmethod
+    def num_correct_dist_mat(dmat, upper_bound=None):
+        """sdm.py:187-222, in place on the caller's array (round trip through
+        HBM); emits the reference's two ``UserWarning``s."""
+        if (not isinstance(dmat, np.ndarray) or dmat.ndim != 2
+                or dmat.shape[0] != dmat.shape[1]):
+            raise ValueError("dmat must be a 2D (n_samples, n_samples)"
+                             " np array")
+        if dmat.shape[0] == 0:
+            return dmat
+        t = dev.to_device(dmat.astype(np.float64, copy=False))
+        flags = dev.num_correct_dist_mat_(t, upper_bound)
+        if flags & NCDM_BAD_DIAG:
+            warnings.warn("distance matrix might not be numerically "
+                          "correct. diag vals should be close to 0.")
+        if flags & NCDM_ASYMMETRIC:
+            warnings.warn("distance matrix might not be numerically "
+                          "correct. should be approximately symmetric.")
+        dmat[...] = t.cpu().numpy()
+        return dmat
+
+    @staticmethod
+    def _static_pdist(x, metric):
+        if spsparse.issparse(x):
+            return SampleDistanceMatrix(x, metric=metric)._d
+        x = np.asarray(x, dtype="float64")
+        if x.ndim != 2:
+            raise ValueError("x has shape (n_samples, n_features)")
+        return SampleDistanceMatrix(x, metric=metric)._d
+
+    @staticmethod
+    def cosine_pdist(x):
+        """sdm.py:1223-1266.  The result already carries the clean-up of
+        ``num_correct_dist_mat`` (it is fused into the kernel epilogue)."""
+        return SampleDistanceMatrix._static_pdist(x, "cosine")
+
+    @staticmethod
+    def correlation_pdist(x):
+        """sdm.py:1268-1287."""
+        return SampleDistanceMatrix._static_pdist(x, "correlation")
+
+    @property
+    def d(self):
+        return self._d.tolist()
+
+    def _validate_pdist(self):
+        """The checks the reference's ``_d`` makes before computing
+        (sdm.py:1194-1209, 1219-1220)."""
+        if not self._use_pdist:
+            raise ValueError("This SDM instance does not use pdist.")
+        if self._is_sparse and self._metric not in (
+                "cityblock", "cosine", "euclidean", "l1", "l2", "manhattan"):
+            raise ValueError("Only the following metrics are supportted for "
+                             "sparse matrices, ['cityblock', 'cosine', "
+                             "'euclidean', 'l1', 'l2', 'manhattan']")
+        if self._lazy_load_d is None:
+            n = self._x.shape[0]
+            if self._x.shape[0] * self._x.shape[1] == 0:
+                self._lazy_load_d = np.zeros((n, n))
+            else:
+                self._check_metric(self._metric)
+
+    @property
+    def _d(self):
+        """sdm.py:1193-1221: lazy, memoised in ``_lazy_load_d``.  D may
+        already be resident in HBM (an earlier kNN accessor); the host copy is
+        made on first access."""
+        self._validate_pdist()
+        if self._lazy_load_d is None:
+            n = self._x.shape[0]
+            out = np.empty((n, n), dtype=np.float64)
+            for r0, r1, stripe in self._d_stripes():
+                out[r0:r1] = stripe.cpu().numpy()
+            self._lazy_load_d = out
+        return self._lazy_load_d
+
+    # ------------------------------------------------------ sorted columns
+    def _col_sort(self, want_sorted, want_arg):
+        self._validate_pdist()
+        n = self._x.shape[0]
+        srt = np.empty((n, n), dtype=np.float64) if want_sorted else None
+        arg = np.empty((n, n), dtype=np.int64) if want_arg else None
+        if n:
+            for r0, r1, stripe in self._d_stripes():
+                s, a = dev.col_sort(stripe, want_sorted, want_arg)
+                if want_sorted:
+                    srt[r0:r1] = s.cpu().numpy()
+                if want_arg:
+                    arg[r0:r1] = a.cpu().numpy()
+        # cell-major -> the reference's (rank, cell) orientation (a view)
+        return (srt.T if want_sorted else None, arg.T if want_arg else None)
+
+    @property
+    def _col_sorted_d(self):
+        """sdm.py:1289-1296."""
+        if self._lazy_load_col_sorted_d is None:
+            self._lazy_load_col_sorted_d = self._col_sort(True, False)[0]
+        return self._lazy_load_col_sorted_d
+
+    @property
+    def _col_argsorted_d(self):
+        """sdm.py:1298-1305."""
+        if self._lazy_load_col_argsorted_d is None:
+            self._lazy_load_col_argsorted_d = self._col_sort(False, True)[1]
+        return self._lazy_load_col_argsorted_d
+
+    def s_ith_nn_d(self, i):
+        return self._col_sorted_d[i, :]
+
+    def s_ith_nn_ind(self, i):
+        return self._col_argsorted_d[i, :]
+
+    # ------------------------------------------------------------------ kNN
+    def _knn_from_pdist(self, k, exclude):
+        """Top-k of every column of D (== row, D is symmetric)."""
+        self._validate_pdist()
+        n = self._x.shape[0]
+        idx = np.empty((n, k), dtype=np.int64)
+        dist = np.empty((n, k), dtype=np.float64)
+        if (self._lazy_load_d is None and self._d_dev is None
+                and k <= 31 and n * n * 8 > DEVICE_D_CACHE_BYTES):
+            # D is not needed by anyone yet and would not fit: fused path
+            i, dd = self._cells(self._metric).knn_stripe(k, exclude)
+            return i.cpu().numpy(), dd.cpu().numpy()
+        for r0, r1, stripe in self._d_stripes():
+            i, dd = dev.knn_from_d(stripe, k, exclude, row_begin=r0)
+            idx[r0:r1] = i.cpu().numpy()
+            dist[r0:r1] = dd.cpu().numpy()
+        return idx, dist
+
+    def s_knn_ind_lut(self, k, metric=None, use_pca=False, use_hnsw=False,
+                      index_params=None, query_params=None, verbose=False):
+        """sdm.py:751-790: ``{i: [1st_NN_ind, ..., kth_NN_ind]}``."""
+        n = self._x.shape[0]
+        if k < 0 or k > n - 1:
+            raise ValueError("k ({}) should >= 0 and <= n_samples-1".format(k))
+        k = int(k)
+        if self._use_pdist:
+            if k == 0:
+                return dict(zip(range(n), [[] for _ in range(n)]))
+            if self._lazy_load_col_argsorted_d is not None or k > MAX_TOPK:
+                arr = self._col_argsorted_d[1:k + 1, :].T
+            else:
+                # ranks 1..k of the stable column argsort, without sorting
+                # the other n-k-1 ranks
+                arr = self._knn_from_pdist(k, EXCLUDE_FIRST)[0]
+            return dict(zip(range(n), arr.tolist()))
+        if self._last_k is None or self._last_k < k:
+            compute_k = min(10, max(n - 1, 0)) if k < 10 else k
+            targets, distances = self.s_knns(
+                compute_k, metric=metric, use_pca=use_pca, use_hnsw=use_hnsw,
+                index_params=index_params, query_params=query_params,
+                verbose=verbose)
+        else:
+            targets, distances = self._last_knns
+        lut = defaultdict(list)
+        for i in range(len(targets)):
+            lut[i]
+            lut[i].extend(int(t) for t in targets[i][:k])
+        return lut
+
+    def s_knns(self, k, metric=None, use_pca=False, use_hnsw=False,
+               index_params=None, query_params=None, verbose=False):
+        """sdm.py:792-870: exact kNN, ``(list of index arrays, list of
+        distance arrays)``, self excluded, ascending distance."""
+        if k < 1:
+            raise ValueError("k should >= 1")
+        if use_hnsw:
+            raise NotImplementedError(
+                "approximate HNSW search (nmslib) is outside the B200 path; "
+                "the exact brute-force path is use_hnsw=False")
+        if index_params is not None:
+            raise ValueError("index_params are not used with use_hnsw=False.")
+        if query_params is not None:
+            raise ValueError("query_params are not used with use_hnsw=False.")
+        targets, distances = self._s_knns_skl(k, metric=metric,
+                                              use_pca=use_pca, verbose=verbose)
+        self._last_k = k
+        self._last_knns = (targets, distances)
+        return targets, distances
+
+    def _s_knns_skl(self, k, metric=None, use_pca=False, verbose=False):
+        """sdm.py:1053-1083 (the slot sklearn's NearestNeighbors filled)."""
+        if metric is None:
+            metric = self._metric
+        if use_pca:
+            raise NotImplementedError(
+                "PCA-space kNN needs scedar's PCA (sdm.py:1313-1334), which "
+                "is outside the B200 path; pass the PCs as x instead")
+        n = self._x.shape[0]
+        k = int(k)
+        if k + 1 > n:
+            raise ValueError("Expected n_neighbors < n_samples_fit, but "
+                             "n_neighbors = {}, n_samples_fit = {}".format(
+                                 k, n))
+        if verbose:
+            print("Construct {} distance KNN graph on raw data.".format(
+                metric))
+        if self._use_pdist:
+            if k > MAX_TOPK:
+                arg = self._col_argsorted_d[:k + 1, :].T
+                srt = self._col_sorted_d[:k + 1, :].T
+                keep = arg != np.arange(n)[:, None]
+                keep[keep.all(axis=1), 0] = False
+                idx = arg[keep].reshape(n, k)
+                dist = srt[keep].reshape(n, k)
+            else:
+                idx, dist = self._knn_from_pdist(k, EXCLUDE_SELF)
+        else:
+            if k > MAX_TOPK:
+                raise NotImplementedError("k > {} without pdist".format(
+                    MAX_TOPK))
+            i, dd = self._cells(metric).knn_stripe(k, EXCLUDE_SELF)
+            idx, dist = i.cpu().numpy(), dd.cpu().numpy()
+        return list(idx), list(dist)
+
+    def s_knn_connectivity_matrix(self, k, metric=None, use_pca=False,
+                                  use_hnsw=False, index_params=None,
+                                  query_params=None, verbose=False):
+        """sdm.py:872-947: CSR, entry (i, j) = distance when j is one of i's
+        kNN; exact-zero distances stored as -inf."""
+        targets, distances = self.s_knns(
+            k=k, metric=metric, use_pca=use_pca, use_hnsw=use_hnsw,
+            index_params=index_params, query_params=query_params,
+            verbose=verbose)
+        n = self._x.shape[0]
+        sources_1d = np.repeat(np.arange(n), [len(t) for t in targets])
+        targets_1d = np.concatenate(targets, axis=0)
+        distances_1d = np.concatenate(distances, axis=0)
+        distances_1d[distances_1d == 0] = -np.inf
+        return spsparse.coo_matrix((distances_1d, (sources_1d, targets_1d)),
+                                   shape=(n, n)).tocsr()
+
+    # ------------------------------------------------------------- read-only
+    @property
+    def metric(self):
+        return self._metric
+
+    def release_device(self):
+        """Drop every HBM-resident cache (prepared cells, D)."""
+        for c in self._cells_lut.values():
+            c.close()
+        self._cells_lut = {}
+        self._d_dev = None
+        torch.cuda.empty_cache()
