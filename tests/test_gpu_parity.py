@@ -37,14 +37,15 @@ def assert_d_close(got, want):
     assert (got >= 0).all()
 
 
-def near_tie_rows(idx, ref_idx, d_ref, ulps=4):
-    """Rows where indices differ; each must be a sub-ulp near tie in the
-    reference distances, returned as a count."""
+def near_tie_rows(idx, ref_idx, d_ref, rel=1e-13):
+    """Rows where indices differ; each must be a near tie in the reference
+    distances (the two candidates within `rel`, three orders below the 1e-10
+    distance tolerance -- SURVEY.md section 8d).  Returns the count."""
     bad = np.where((idx != ref_idx).any(axis=1))[0]
     for r in bad:
         a = d_ref[r, idx[r]]
         b = d_ref[r, ref_idx[r]]
-        assert np.all(np.abs(a - b) <= ulps * np.spacing(np.maximum(a, b))), r
+        assert np.all(np.abs(a - b) <= rel * np.maximum(a, b)), r
     return len(bad)
 
 
@@ -96,6 +97,10 @@ def test_knn_lut_golden(b200, golden, name, full):
             lut2 = sdm2.s_knn_ind_lut(k)
             assert np.array_equal(
                 np.array([lut2[i] for i in range(x.shape[0])]), want), m
+        elif name == "counts_ties":
+            # centred integer counts: mathematically exact ties whose order
+            # is decided by rounding noise; every mismatch must be such a tie
+            near_tie_rows(got, want, orc.pdist(x, m))
         else:
             assert near_tie_rows(got, want, orc.pdist(x, m)) == 0, m
 
