@@ -77,6 +77,9 @@ const char* scedar_last_error(void);
  * per row in registers); larger k is served by scedar_col_sort. */
 int scedar_max_k(void);
 
+/* Number of kernels this library has launched in this process (monotonic). */
+long long scedar_launch_count(void);
+
 /* ------------------------------------------------------------------------
  * Prepared cells: the device-resident working copy of x that the Gram kernels
  * read (rows padded to a multiple of 128 cells, genes to a multiple of 16,

@@ -23,6 +23,7 @@ SIGNATURES = {
     "scedar_abi_version": (c_int, []),
     "scedar_last_error": (c_char_p, []),
     "scedar_max_k": (c_int, []),
+    "scedar_launch_count": (ctypes.c_longlong, []),
     "scedar_cells_from_dense": (c_int, [c_void_p, c_int64, c_int64, c_int64,
                                         c_int, c_void_p, POINTER(c_void_p)]),
     "scedar_cells_from_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p,

@@ -2,6 +2,7 @@
 // checking, scratch management and the sequencing of the kernels.  No compute
 // happens on the host and there is no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <new>
 
 #include "common.cuh"
@@ -29,6 +30,9 @@ int Scratch::alloc(size_t bytes, cudaStream_t s) {
   }
   return SCEDAR_OK;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
 
 int num_sms() {
   static int sms = 0;
@@ -100,6 +104,7 @@ extern "C" {
 int scedar_abi_version(void) { return SCEDAR_ABI_VERSION; }
 const char* scedar_last_error(void) { return g_last_error.c_str(); }
 int scedar_max_k(void) { return 127; }
+long long scedar_launch_count(void) { return g_launches.load(); }
 
 int scedar_cells_from_dense(const double* x, int64_t n, int64_t p, int64_t ldx, int metric,
                             void* stream, scedar_cells_t** out) {

@@ -51,6 +51,7 @@ struct Scratch {
 };
 
 int num_sms();
+void count_launch(int n = 1);  // kernels launched by this library (bench evidence)
 
 }  // namespace scedar
 

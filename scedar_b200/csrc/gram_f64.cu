@@ -42,16 +42,18 @@ constexpr int KFUSED = 32;  // entries kept per row by the fused top-k
 constexpr int LIST_BYTES = BM * KFUSED * (8 + 4);
 constexpr int GROUP_ROWS = 16;  // row tiles per L2 swizzle group
 
-enum Mode { MODE_STORE = 0, MODE_SYM = 1, MODE_DIAG = 2, MODE_TOPK = 3 };
+enum Mode { MODE_STORE = 0, MODE_DIAG = 2, MODE_TOPK = 3 };
 
 struct GramArgs {
   const double* xw;
   const double* stat;
   int64_t n, n_pad, p_pad;
   int64_t row_begin, row_end;  // rows of D this launch owns
-  double* out;                 // D stripe (STORE/SYM) or stat (DIAG)
+  double* out;                 // D stripe (STORE) or stat (DIAG)
   int64_t ldd;
   int euclid;
+  int mirror;  // STORE: tiles above the diagonal of the stripe's own square
+               // block are not computed but written as transposes
   // TOPK
   int K, splits;
   double* part_d;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
 
   // ---- tile coordinates --------------------------------------------------
   int64_t I, J;
+  bool mirrored = false;
   if (MODE == MODE_DIAG) {
     I = J = blockIdx.x;
   } else {
@@ -290,7 +293,15 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
     const int64_t rows_here = left < GROUP_ROWS ? left : GROUP_ROWS;
     I = rt0 + grp * GROUP_ROWS + rem % rows_here;
     J = rem / rows_here;
-    if (MODE == MODE_SYM && J > I) return;  // upper tiles come from the mirror
+    if (a.mirror && I != J) {
+      // both tiles lie wholly inside this stripe's rows: D[I,J] == D[J,I]^T is
+      // produced once, by the lower tile
+      const int64_t ie = (I + 1) * BM < a.n ? (I + 1) * BM : a.n;
+      const int64_t je = (J + 1) * BN < a.n ? (J + 1) * BN : a.n;
+      mirrored = I * BM >= a.row_begin && ie <= a.row_end &&
+                 J * BN >= a.row_begin && je <= a.row_end;
+      if (mirrored && J > I) return;
+    }
   }
   const int64_t i0 = I * BM, j0 = J * BN;
 
@@ -327,12 +338,12 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
       if (j0 + c < a.n) dst[c] = smem[r * LDT + c];
     }
   }
-  if (MODE == MODE_SYM && I != J) {
+  if (MODE == MODE_STORE && mirrored) {
     // mirrored tile: column c of T is row j0+c of D
     for (int c = warp; c < BN; c += NT / 32) {
       const int64_t gj = j0 + c;
       if (gj >= a.n) continue;
-      double* __restrict__ dst = a.out + gj * a.ldd + i0;
+      double* __restrict__ dst = a.out + (gj - a.row_begin) * a.ldd + i0;
 #pragma unroll
       for (int q = 0; q < BM / 32; ++q) {
         const int r = lane + 32 * q;
@@ -344,15 +355,12 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
 
 template <int MODE>
 int launch(const GramArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    SCEDAR_CUDA(cudaFuncSetAttribute(gram_f64_kernel<MODE>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     MAIN_BYTES + LIST_BYTES));
-    configured = true;
-  }
+  SCEDAR_CUDA(cudaFuncSetAttribute(gram_f64_kernel<MODE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   MAIN_BYTES + LIST_BYTES));
   gram_f64_kernel<MODE><<<grid, NT, smem_bytes, s>>>(a);
   SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
   return SCEDAR_OK;
 }
 
@@ -385,6 +393,7 @@ int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   a.row_end = row_end;
   a.out = d_out;
   a.ldd = ldd;
+  a.mirror = 1;
   const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
   const int64_t tiles = RT * (c->n_pad / BN);
   if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");
@@ -393,16 +402,8 @@ int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
 
 int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
                           cudaStream_t s) {
-  if (c->n == 0) return SCEDAR_OK;
-  GramArgs a = base_args(c);
-  a.row_begin = 0;
-  a.row_end = c->n;
-  a.out = d_out;
-  a.ldd = ldd;
-  const int64_t RT = (c->n + BM - 1) / BM;
-  const int64_t tiles = RT * (c->n_pad / BN);
-  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "matrix too large for one launch");
-  return launch<MODE_SYM>(a, dim3((unsigned)tiles), MAIN_BYTES, s);
+  // the stripe [0, n) is the whole matrix: every upper tile is a mirror
+  return launch_gram_stripe(c, 0, c->n, d_out, ldd, s);
 }
 
 int gram_topk_splits(const scedar_cells* c, int64_t rows) {

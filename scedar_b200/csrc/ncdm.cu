@@ -82,6 +82,7 @@ int launch_ncdm(double* d, int64_t ldd, int64_t n, int has_ub, double ub, int32_
   if (pairs > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "matrix too large");
   ncdm_kernel<<<(unsigned)pairs, 256, 0, s>>>(d, ldd, n, has_ub, ub, flags);
   SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
   return SCEDAR_OK;
 }
 

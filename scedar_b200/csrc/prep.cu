@@ -124,6 +124,7 @@ int launch_prep_dense(const double* x, int64_t n, int64_t p, int64_t ldx,
       prep_dense_kernel<256, false><<<grid, 256, 0, s>>>(x, n, p, ldx, centre, xw, n_pad, p_pad);
   }
   SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
   return SCEDAR_OK;
 }
 
@@ -141,6 +142,7 @@ int launch_prep_csr(const void* indptr, int indptr_is_64,
     prep_csr_scatter_kernel<int32_t><<<grid, 256, 0, s>>>(
         static_cast<const int32_t*>(indptr), indices, data, n, p, xw, p_pad);
   SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
   return SCEDAR_OK;
 }
 

@@ -299,6 +299,7 @@ int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row
   else
     return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
   SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
   return SCEDAR_OK;
 }
 
@@ -312,6 +313,7 @@ int launch_topk_merge(const double* part_d, const int32_t* part_i, int splits, i
   else
     return fail(SCEDAR_ERR_UNSUPPORTED, "merge of more than 32 entries per row");
   SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
   return SCEDAR_OK;
 }
 

@@ -1,0 +1,131 @@
+"""Row-stripe sharding of the distance matrix / kNN path over several GPUs.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink).  Row i of D and
+the kNN list of cell i depend on x[i] and all of x and on nothing else, so the
+path shards by contiguous, tile-aligned row stripes:
+
+* x is broadcast once from rank 0 (<= 1.6 GB at 100k x 2000);
+* every rank prepares the cells (the K1 pass is cheaper than shipping its
+  output) and owns rows [row_begin, row_end) of D and of the kNN lists;
+* only the (index, distance) lists are all-gathered -- D stripes stay in the
+  HBM of their owner.
+
+The compute operators are injected (``ops``) so the sharding logic can be
+tested on CPU with the ``gloo`` backend; the default is the CUDA library.
+"""
+import torch
+import torch.distributed as dist
+
+TILE = 128
+
+
+def partition(n, world):
+    """Tile-aligned contiguous row stripes: list of (row_begin, row_end)."""
+    tiles = (n + TILE - 1) // TILE
+    base, extra = divmod(tiles, world)
+    out, t0 = [], 0
+    for r in range(world):
+        t1 = t0 + base + (1 if r < extra else 0)
+        out.append((min(t0 * TILE, n), min(t1 * TILE, n)))
+        t0 = t1
+    return out
+
+
+class _DeviceOps(object):
+    """The CUDA library (default operators)."""
+
+    def prepare(self, x, metric):
+        from . import device
+        return device.Cells.from_dense(x, metric)
+
+    def pdist_stripe(self, cells, r0, r1, out=None):
+        return cells.pdist_stripe(r0, r1, out=out)
+
+    def knn_from_d(self, d, k, exclude, row_begin):
+        from . import device
+        return device.knn_from_d(d, k, exclude, row_begin=row_begin)
+
+    def knn_stripe(self, cells, k, exclude, r0, r1):
+        return cells.knn_stripe(k, exclude, r0, r1)
+
+
+class StripedDistanceMatrix(object):
+    """Distance matrix + kNN of a cells x genes matrix, row-striped over the
+    ranks of a process group (or a single process when torch.distributed is
+    not initialised).
+
+    Parameters
+    ----------
+    x : float64 tensor [n, p] on this rank's device, or None on ranks != src
+        (it is then received by broadcast).
+    shape : (n, p), needed on ranks that pass x=None.
+    broadcast : False when every rank already holds x.
+    """
+
+    def __init__(self, x, metric="correlation", shape=None, group=None,
+                 src=0, device=None, ops=None, broadcast=True):
+        self.ops = ops or _DeviceOps()
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        if x is None:
+            if shape is None or device is None:
+                raise ValueError("ranks without x need shape and device")
+            x = torch.empty(shape, dtype=torch.float64, device=device)
+        if x.dim() != 2 or x.dtype != torch.float64:
+            raise ValueError("x has shape (n_samples, n_features), float64")
+        if self.world > 1 and broadcast:
+            dist.broadcast(x, src=src, group=group)
+        self.n, self.p = x.shape
+        self.metric = metric
+        self.stripes = partition(self.n, self.world)
+        self.row_begin, self.row_end = self.stripes[self.rank]
+        self.cells = self.ops.prepare(x, metric)
+        self.d_stripe = None
+
+    @property
+    def rows(self):
+        return self.row_end - self.row_begin
+
+    def compute_d(self, out=None):
+        """This rank's rows of D, kept in HBM: tensor [rows, n]."""
+        self.d_stripe = self.ops.pdist_stripe(self.cells, self.row_begin,
+                                              self.row_end, out=out)
+        return self.d_stripe
+
+    def knn_local(self, k, exclude, from_d=True):
+        """(idx[rows, k] int64, dist[rows, k]) of this rank's rows."""
+        if from_d:
+            if self.d_stripe is None:
+                self.compute_d()
+            return self.ops.knn_from_d(self.d_stripe, k, exclude,
+                                       self.row_begin)
+        return self.ops.knn_stripe(self.cells, k, exclude, self.row_begin,
+                                   self.row_end)
+
+    def knn(self, k, exclude, from_d=True):
+        """kNN lists of ALL cells on every rank: the all-gather of the
+        per-stripe lists (the only data-path collective)."""
+        idx, dd = self.knn_local(k, exclude, from_d=from_d)
+        if self.world == 1:
+            return idx, dd
+        return self._gather(idx), self._gather(dd)
+
+    def _gather(self, t):
+        """all-gather of ragged stripes: pad to the widest stripe, trim."""
+        widest = max(e - b for b, e in self.stripes)
+        pad = torch.zeros((widest,) + tuple(t.shape[1:]), dtype=t.dtype,
+                          device=t.device)
+        pad[:t.shape[0]] = t
+        out = torch.empty((self.world * widest,) + tuple(t.shape[1:]),
+                          dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        parts = [out[r * widest:r * widest + (e - b)]
+                 for r, (b, e) in enumerate(self.stripes)]
+        return torch.cat(parts, dim=0)
+
+    def close(self):
+        if hasattr(self.cells, "close"):
+            self.cells.close()
+        self.d_stripe = None

@@ -1,0 +1,92 @@
+"""CPU, world_size 2, gloo: the row-stripe sharding logic (broadcast of x,
+stripe ownership, ragged all-gather of the kNN lists) with the compute
+operators replaced by the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleOps(object):
+    """Stand-in operators (CPU tensors) with the device operators' contract."""
+
+    def prepare(self, x, metric):
+        from oracle import sdm_oracle as orc
+        return {"d": orc.pdist(x.numpy(), metric)}
+
+    def pdist_stripe(self, cells, r0, r1, out=None):
+        return torch.from_numpy(np.ascontiguousarray(cells["d"][r0:r1]))
+
+    def knn_from_d(self, d, k, exclude, row_begin):
+        d = d.numpy()
+        order = np.argsort(d, kind="mergesort", axis=1)[:, :k + 1]
+        rows = np.arange(d.shape[0])[:, None]
+        if exclude == 0:
+            idx = order[:, 1:]
+        else:
+            keep = order != (rows + row_begin)
+            keep[keep.all(axis=1), 0] = False
+            idx = order[keep].reshape(d.shape[0], k)
+        return (torch.from_numpy(idx.astype(np.int64)),
+                torch.from_numpy(np.take_along_axis(d, idx, axis=1)))
+
+    def knn_stripe(self, cells, k, exclude, r0, r1):
+        return self.knn_from_d(self.pdist_stripe(cells, r0, r1), k, exclude,
+                               r0)
+
+
+def _worker(rank, world, port, n, p, k, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import sdm_oracle as orc
+        from scedar_b200.stripes import StripedDistanceMatrix
+        x = None
+        if rank == 0:
+            x = torch.from_numpy(
+                np.random.default_rng(1).poisson(1.0, (n, p)).astype(float))
+        sdm = StripedDistanceMatrix(x, "euclidean", shape=(n, p),
+                                    device="cpu", ops=OracleOps())
+        stripe = sdm.compute_d()
+        assert stripe.shape == (sdm.row_end - sdm.row_begin, n)
+        idx, dd = sdm.knn(k, exclude=1)
+        idx2, dd2 = sdm.knn(k, exclude=0, from_d=False)
+        ok = None
+        if rank == 0:
+            d = orc.pdist(x.numpy(), "euclidean")
+            ridx, rdist = orc.knns_precomputed(d, k)
+            fidx, _ = orc.knn_drop_first(d, k)
+            ok = (np.array_equal(idx.numpy(), ridx)
+                  and np.array_equal(dd.numpy(), rdist)
+                  and np.array_equal(idx2.numpy(), fidx))
+        q.put((rank, sdm.stripes, tuple(idx.shape), ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [300, 129])
+def test_two_rank_stripes(n):
+    world, p, k = 2, 12, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, p, k, q))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    got.sort()
+    assert got[0][1] == got[1][1]                    # same partition
+    assert got[0][2] == got[1][2] == (n, k)          # every rank: all lists
+    assert got[0][3] is True
