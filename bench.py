@@ -29,6 +29,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+TRACE = bool(os.environ.get("SCEDAR_BENCH_TRACE"))
 METRIC = "cell_pair_distances_per_s"
 UNIT = "pairs/s"
 
@@ -228,20 +229,32 @@ def run_b200(a):
         the phases on the launching stream (read after the region ends)."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] \
             if timed_kernel else None
+        trace = [time.perf_counter()] if TRACE else None
         if ev:
             ev[0].record()
         sdm = StripedDistanceMatrix(x, a.metric, shape=(n, p), device=dev,
                                     broadcast=broadcast)   # K1 + Gram diagonal
         if ev:
             ev[1].record()
+        if trace:
+            trace.append(time.perf_counter())
         sdm.compute_d(out=d_buf)                           # K2
         if ev:
             ev[2].record()
+        if trace:
+            trace.append(time.perf_counter())
         idx, dd = sdm.knn(k, EXCLUDE_FIRST)   # K3, s_knn_ind_lut semantics
         if ev:
             ev[3].record()
             phase_events.append(ev)
+        if trace:
+            trace.append(time.perf_counter())
         sdm.close()
+        if trace:
+            trace.append(time.perf_counter())
+            print("rank{} host ms: {}".format(rank, [
+                round((b - a_) * 1e3, 2) for a_, b in zip(trace, trace[1:])]),
+                file=sys.stderr, flush=True)
         return idx, dd
 
     def sync_all():
@@ -261,7 +274,8 @@ def run_b200(a):
     for _ in range(a.warmup):
         step(x_dev, False)
     sync_all()
-    clocks = ClockSampler(local) if rank == 0 else None
+    clocks = ClockSampler(local) if (
+        rank == 0 and not os.environ.get("SCEDAR_BENCH_NO_CLOCKS")) else None
     launches0 = lib.scedar_launch_count()
     t_host0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True)

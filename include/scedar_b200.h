@@ -102,6 +102,8 @@ int scedar_cells_from_csr(const void* indptr, int indptr_is_64,
                           int64_t n, int64_t p, int metric, void* stream,
                           scedar_cells_t** out);
 
+/* Stream-ordered on the stream the cells were created on (work that reads the
+ * cells on another stream must have been synchronised with it). */
 int scedar_cells_free(scedar_cells_t* cells);
 int64_t scedar_cells_n(const scedar_cells_t* cells);
 int64_t scedar_cells_p(const scedar_cells_t* cells);
@@ -117,6 +119,31 @@ int scedar_cells_metric(const scedar_cells_t* cells);
 int scedar_pdist_stripe(const scedar_cells_t* cells, int precision,
                         int64_t row_begin, int64_t row_end, double* d_out,
                         int64_t ldd, void* stream);
+
+/* Multi-GPU form over peer memory: rank r of `world` (one process per GPU)
+ * owns rows [stripe_begin[r], stripe_begin[r+1]) (128-aligned, covering [0,n))
+ * in stripe_ptr[r], all [rows_r, n] with row stride ldd and all mapped on THIS
+ * device (own stripe + peers opened with scedar_stripe_open).  Every
+ * off-diagonal 128 x 128 tile pair of the whole matrix is computed once -- by
+ * the owner of the higher row tile when the tile indices sum to an even number,
+ * the lower otherwise -- and the epilogue stores the tile into the local stripe
+ * and its transpose straight into the other owner's stripe over NVLink, so N
+ * GPUs do n(n+1)p flops in total instead of 2n^2p.  stripe_begin / stripe_ptr
+ * are HOST arrays.  The caller must barrier all ranks on their streams before
+ * anyone reads a stripe and before the next call writes it. */
+int scedar_pdist_stripe_p2p(const scedar_cells_t* cells, int precision, int rank,
+                            int world, const int64_t* stripe_begin,
+                            double* const* stripe_ptr, int64_t ldd,
+                            void* stream);
+
+/* Stripe buffers that can be mapped by the peer processes of one node
+ * (cudaMalloc + CUDA IPC).  handle64 is a 64-byte opaque blob to ship to the
+ * peers (e.g. torch.distributed.all_gather_object). */
+int scedar_stripe_alloc(size_t bytes, void** dev_ptr);
+int scedar_stripe_free(void* dev_ptr);
+int scedar_stripe_export(void* dev_ptr, void* handle64);
+int scedar_stripe_open(const void* handle64, void** peer_ptr);
+int scedar_stripe_close(void* peer_ptr);
 
 /* Whole matrix at once, computing only the lower-triangle tiles and writing
  * each tile and its transpose (half the contraction work). */

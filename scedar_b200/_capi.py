@@ -35,6 +35,14 @@ SIGNATURES = {
     "scedar_cells_metric": (c_int, [c_void_p]),
     "scedar_pdist_stripe": (c_int, [c_void_p, c_int, c_int64, c_int64,
                                     c_void_p, c_int64, c_void_p]),
+    "scedar_pdist_stripe_p2p": (c_int, [c_void_p, c_int, c_int, c_int,
+                                        POINTER(c_int64), POINTER(c_void_p),
+                                        c_int64, c_void_p]),
+    "scedar_stripe_alloc": (c_int, [ctypes.c_size_t, POINTER(c_void_p)]),
+    "scedar_stripe_free": (c_int, [c_void_p]),
+    "scedar_stripe_export": (c_int, [c_void_p, c_void_p]),
+    "scedar_stripe_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "scedar_stripe_close": (c_int, [c_void_p]),
     "scedar_pdist_symmetric": (c_int, [c_void_p, c_int, c_void_p, c_int64,
                                        c_void_p]),
     "scedar_knn_stripe": (c_int, [c_void_p, c_int, c_int, c_int, c_int64,

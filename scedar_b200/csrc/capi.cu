@@ -3,6 +3,7 @@
 // happens on the host and there is no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 #include <new>
 
 #include "common.cuh"
@@ -17,7 +18,22 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
+// Keep freed scratch in the device's default memory pool instead of returning
+// it to the driver at every synchronisation (the default threshold is 0).
+static void keep_pool_warm() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for = dev;
+}
+
 int Scratch::alloc(size_t bytes, cudaStream_t s) {
+  keep_pool_warm();
   stream = s;
   if (bytes == 0) bytes = 16;
   cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
@@ -68,7 +84,7 @@ int check_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end) {
   return SCEDAR_OK;
 }
 
-int new_cells(int64_t n, int64_t p, int metric, scedar_cells** out) {
+int new_cells(int64_t n, int64_t p, int metric, cudaStream_t s, scedar_cells** out) {
   if (!out) return fail(SCEDAR_ERR_ARG, "out is NULL");
   *out = nullptr;
   SCEDAR_CHECK(check_metric(metric));
@@ -82,8 +98,12 @@ int new_cells(int64_t n, int64_t p, int metric, scedar_cells** out) {
   c->n_pad = std::max<int64_t>(round_up(n, kRowPad), kRowPad);
   c->p_pad = std::max<int64_t>(round_up(p, kColPad), kColPad);
   cudaGetDevice(&c->device);
-  cudaError_t e = cudaMalloc(&c->xw, sizeof(double) * c->n_pad * c->p_pad);
-  if (e == cudaSuccess) e = cudaMalloc(&c->stat, sizeof(double) * c->n_pad);
+  // stream-ordered pool allocation: no device-wide sync, and re-preparing
+  // cells of the same size reuses the pooled block
+  c->stream = s;
+  keep_pool_warm();
+  cudaError_t e = cudaMallocAsync(&c->xw, sizeof(double) * c->n_pad * c->p_pad, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&c->stat, sizeof(double) * c->n_pad, s);
   if (e != cudaSuccess) {
     cudaGetLastError();
     scedar_cells_free(c);
@@ -111,7 +131,7 @@ int scedar_cells_from_dense(const double* x, int64_t n, int64_t p, int64_t ldx, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n > 0 && p > 0 && !x) return fail(SCEDAR_ERR_ARG, "x is NULL");
   if (ldx < p) return fail(SCEDAR_ERR_ARG, "ldx must be >= p");
-  SCEDAR_CHECK(new_cells(n, p, metric, out));
+  SCEDAR_CHECK(new_cells(n, p, metric, s, out));
   scedar_cells* c = *out;
   int rc = launch_prep_dense(x, n, p, ldx, metric, c->xw, c->n_pad, c->p_pad, s);
   if (rc == SCEDAR_OK) rc = launch_gram_diag(c, s);
@@ -129,7 +149,7 @@ int scedar_cells_from_csr(const void* indptr, int indptr_is_64, const int32_t* i
   if (metric == SCEDAR_METRIC_CORRELATION)
     return fail(SCEDAR_ERR_ARG, "correlation is not defined for sparse cells (sdm.py:1196-1204)");
   if (!indptr) return fail(SCEDAR_ERR_ARG, "indptr is NULL");
-  SCEDAR_CHECK(new_cells(n, p, metric, out));
+  SCEDAR_CHECK(new_cells(n, p, metric, s, out));
   scedar_cells* c = *out;
   int rc = launch_prep_csr(indptr, indptr_is_64, indices, data, n, p, c->xw, c->n_pad, c->p_pad, s);
   if (rc == SCEDAR_OK) rc = launch_gram_diag(c, s);
@@ -142,8 +162,8 @@ int scedar_cells_from_csr(const void* indptr, int indptr_is_64, const int32_t* i
 
 int scedar_cells_free(scedar_cells_t* c) {
   if (!c) return SCEDAR_OK;
-  if (c->xw) cudaFree(c->xw);
-  if (c->stat) cudaFree(c->stat);
+  if (c->xw) cudaFreeAsync(c->xw, c->stream);
+  if (c->stat) cudaFreeAsync(c->stat, c->stream);
   delete c;
   return SCEDAR_OK;
 }
@@ -170,6 +190,47 @@ int scedar_pdist_symmetric(const scedar_cells_t* c, int precision, double* d_out
   if (!d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
   return launch_gram_symmetric(c, d_out, ldd, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_pdist_stripe_p2p(const scedar_cells_t* c, int precision, int rank, int world,
+                            const int64_t* stripe_begin, double* const* stripe_ptr,
+                            int64_t ldd, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  SCEDAR_CHECK(check_precision(precision));
+  if (!stripe_begin || !stripe_ptr) return fail(SCEDAR_ERR_ARG, "NULL stripe table");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  return launch_gram_stripe_p2p(c, rank, world, stripe_begin, stripe_ptr, ldd,
+                                static_cast<cudaStream_t>(stream));
+}
+
+// ---- peer-mapped stripes (one process per GPU, same node) ------------------
+int scedar_stripe_alloc(size_t bytes, void** dev_ptr) {
+  if (!dev_ptr) return fail(SCEDAR_ERR_ARG, "dev_ptr is NULL");
+  SCEDAR_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 16));
+  return SCEDAR_OK;
+}
+int scedar_stripe_free(void* dev_ptr) {
+  if (dev_ptr) SCEDAR_CUDA(cudaFree(dev_ptr));
+  return SCEDAR_OK;
+}
+int scedar_stripe_export(void* dev_ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  if (!dev_ptr || !handle64) return fail(SCEDAR_ERR_ARG, "NULL argument");
+  cudaIpcMemHandle_t h;
+  SCEDAR_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return SCEDAR_OK;
+}
+int scedar_stripe_open(const void* handle64, void** peer_ptr) {
+  if (!peer_ptr || !handle64) return fail(SCEDAR_ERR_ARG, "NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  SCEDAR_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SCEDAR_OK;
+}
+int scedar_stripe_close(void* peer_ptr) {
+  if (peer_ptr) SCEDAR_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return SCEDAR_OK;
 }
 
 int scedar_knn_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row_begin,

@@ -63,6 +63,7 @@ struct scedar_cells {
   int device = 0;
   double* xw = nullptr;    // [n_pad, p_pad] working copy (centred if correlation)
   double* stat = nullptr;  // [n_pad] sqrt(1/|x|^2) (0 for zero rows) or |x|^2
+  cudaStream_t stream = nullptr;  // creation stream: the frees are ordered on it
 };
 
 namespace scedar {
@@ -82,6 +83,9 @@ int launch_gram_diag(const scedar_cells* c, cudaStream_t s);
 int launch_gram_stripe(const scedar_cells* c, int64_t row_begin,
                        int64_t row_end, double* d_out, int64_t ldd,
                        cudaStream_t s);
+int launch_gram_stripe_p2p(const scedar_cells* c, int rank, int world,
+                           const int64_t* stripe_begin, double* const* stripe_ptr,
+                           int64_t ldd, cudaStream_t s);
 int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
                           cudaStream_t s);
 // fused Gram -> top-K; part_d/part_i: [splits, rows, K] partial lists

@@ -41,6 +41,7 @@ constexpr int MAIN_BYTES = PIPE_BYTES > TILE_BYTES ? PIPE_BYTES : TILE_BYTES;
 constexpr int KFUSED = 32;  // entries kept per row by the fused top-k
 constexpr int LIST_BYTES = BM * KFUSED * (8 + 4);
 constexpr int GROUP_ROWS = 16;  // row tiles per L2 swizzle group
+constexpr int kMaxPeers = 16;
 
 enum Mode { MODE_STORE = 0, MODE_DIAG = 2, MODE_TOPK = 3 };
 
@@ -54,6 +55,12 @@ struct GramArgs {
   int euclid;
   int mirror;  // STORE: tiles above the diagonal of the stripe's own square
                // block are not computed but written as transposes
+  // STORE over peer memory (world > 1): every off-diagonal tile pair of the
+  // WHOLE matrix is computed once, by the owner of one of its two row tiles,
+  // and its transpose is stored straight into the other owner's stripe
+  int world;
+  int64_t stripe_begin[kMaxPeers + 1];  // tile-aligned row ranges of the ranks
+  double* stripe_ptr[kMaxPeers];        // their D stripes, mapped on this GPU
   // TOPK
   int K, splits;
   double* part_d;
@@ -282,6 +289,8 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
   // ---- tile coordinates --------------------------------------------------
   int64_t I, J;
   bool mirrored = false;
+  double* mirror_out = a.out;       // stripe that receives the transposed tile
+  int64_t mirror_begin = a.row_begin;
   if (MODE == MODE_DIAG) {
     I = J = blockIdx.x;
   } else {
@@ -293,7 +302,18 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
     const int64_t rows_here = left < GROUP_ROWS ? left : GROUP_ROWS;
     I = rt0 + grp * GROUP_ROWS + rem % rows_here;
     J = rem / rows_here;
-    if (a.mirror && I != J) {
+    if (a.world > 1 && I != J) {
+      // balanced ownership of the pair {I, J}: the higher row tile computes it
+      // when I+J is even, the lower one when odd
+      const int64_t lo = I < J ? I : J, hi = I < J ? J : I;
+      const int64_t row_tile = ((lo + hi) & 1) == 0 ? hi : lo;
+      if (I != row_tile) return;
+      mirrored = true;
+      int o = 0;
+      while (o + 1 < a.world && J * BN >= a.stripe_begin[o + 1]) ++o;
+      mirror_out = a.stripe_ptr[o];
+      mirror_begin = a.stripe_begin[o];
+    } else if (a.mirror && I != J) {
       // both tiles lie wholly inside this stripe's rows: D[I,J] == D[J,I]^T is
       // produced once, by the lower tile
       const int64_t ie = (I + 1) * BM < a.n ? (I + 1) * BM : a.n;
@@ -343,7 +363,7 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
     for (int c = warp; c < BN; c += NT / 32) {
       const int64_t gj = j0 + c;
       if (gj >= a.n) continue;
-      double* __restrict__ dst = a.out + (gj - a.row_begin) * a.ldd + i0;
+      double* __restrict__ dst = mirror_out + (gj - mirror_begin) * a.ldd + i0;
 #pragma unroll
       for (int q = 0; q < BM / 32; ++q) {
         const int r = lane + 32 * q;
@@ -394,6 +414,39 @@ int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   a.out = d_out;
   a.ldd = ldd;
   a.mirror = 1;
+  const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
+  const int64_t tiles = RT * (c->n_pad / BN);
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");
+  return launch<MODE_STORE>(a, dim3((unsigned)tiles), MAIN_BYTES, s);
+}
+
+int launch_gram_stripe_p2p(const scedar_cells* c, int rank, int world,
+                           const int64_t* stripe_begin, double* const* stripe_ptr,
+                           int64_t ldd, cudaStream_t s) {
+  if (world < 1 || world > kMaxPeers) return fail(SCEDAR_ERR_ARG, "world must be in 1..16");
+  if (rank < 0 || rank >= world) return fail(SCEDAR_ERR_ARG, "rank out of range");
+  for (int r = 0; r <= world; ++r) {
+    const int64_t b = stripe_begin[r];
+    const bool aligned = b % BM == 0 || b == c->n;
+    if (!aligned || (r > 0 && b < stripe_begin[r - 1]))
+      return fail(SCEDAR_ERR_ARG, "stripes must be ascending and 128-row aligned");
+  }
+  if (stripe_begin[0] != 0 || stripe_begin[world] != c->n)
+    return fail(SCEDAR_ERR_ARG, "stripes must cover [0, n)");
+  const int64_t row_begin = stripe_begin[rank], row_end = stripe_begin[rank + 1];
+  if (row_end <= row_begin) return SCEDAR_OK;
+  GramArgs a = base_args(c);
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.out = stripe_ptr[rank];
+  a.ldd = ldd;
+  a.mirror = 1;  // world == 1 degenerates to the local mirror
+  a.world = world;
+  for (int r = 0; r < world; ++r) {
+    a.stripe_begin[r] = stripe_begin[r];
+    a.stripe_ptr[r] = stripe_ptr[r];
+  }
+  a.stripe_begin[world] = stripe_begin[world];
   const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
   const int64_t tiles = RT * (c->n_pad / BN);
   if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");

@@ -183,3 +183,95 @@ def to_device(a):
     """Host ndarray -> CUDA tensor through pinned memory."""
     t = torch.from_numpy(np.ascontiguousarray(a))
     return t.pin_memory().cuda(non_blocking=True) if t.numel() else t.cuda()
+
+
+class _RawCuda(object):
+    """Exposes a raw device allocation through __cuda_array_interface__ so
+    torch can view it without a copy."""
+
+    def __init__(self, ptr, shape, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+            "version": 3, "strides": None}
+
+
+class PeerStripes(object):
+    """The D stripes of all ranks of one node, each allocated by its owner with
+    ``scedar_stripe_alloc`` and mapped into every peer process through CUDA
+    IPC, so a Gram epilogue can store a mirrored tile straight into the
+    owner's HBM over NVLink (``Cells.pdist_stripe_p2p``).
+
+    ``stripes``: list of (row_begin, row_end) per rank (stripes.partition).
+    With ``group=None`` and ``rank=None`` all stripes are allocated locally
+    (single-process emulation of the N ranks on one GPU, used by the tests).
+    """
+
+    def __init__(self, stripes, n, rank=None, group=None):
+        _guard()
+        import torch.distributed as dist
+        self.lib = _capi.load()
+        self.stripes, self.n, self.rank = list(stripes), int(n), rank
+        self.world = len(self.stripes)
+        self.ptrs = [None] * self.world
+        self._own, self._opened = [], []
+        mine = range(self.world) if rank is None else [rank]
+        for r in mine:
+            b, e = self.stripes[r]
+            p = ctypes.c_void_p()
+            _capi.check(self.lib.scedar_stripe_alloc(
+                max(e - b, 0) * self.n * 8, ctypes.byref(p)))
+            self.ptrs[r] = p.value
+            self._own.append(p.value)
+        if rank is not None and self.world > 1:
+            blob = ctypes.create_string_buffer(64)
+            _capi.check(self.lib.scedar_stripe_export(
+                ctypes.c_void_p(self.ptrs[rank]), blob))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, blob.raw, group=group)
+            for r, h in enumerate(handles):
+                if r == rank:
+                    continue
+                p = ctypes.c_void_p()
+                buf = ctypes.create_string_buffer(h, 64)
+                _capi.check(self.lib.scedar_stripe_open(buf, ctypes.byref(p)))
+                self.ptrs[r] = p.value
+                self._opened.append(p.value)
+
+    def tensor(self, r=None):
+        """Zero-copy torch view [rows, n] of stripe r (default: own)."""
+        r = self.rank if r is None else r
+        b, e = self.stripes[r]
+        if e - b == 0:
+            return torch.empty((0, self.n), dtype=torch.float64, device="cuda")
+        return torch.as_tensor(_RawCuda(self.ptrs[r], (e - b, self.n), self),
+                               device="cuda")
+
+    def tables(self):
+        begins = [b for b, _ in self.stripes] + [self.stripes[-1][1]]
+        return ((ctypes.c_int64 * len(begins))(*begins),
+                (ctypes.c_void_p * self.world)(*self.ptrs))
+
+    def close(self):
+        torch.cuda.synchronize()
+        for p in self._opened:
+            self.lib.scedar_stripe_close(ctypes.c_void_p(p))
+        for p in self._own:
+            self.lib.scedar_stripe_free(ctypes.c_void_p(p))
+        self._opened, self._own = [], []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pdist_stripe_p2p(cells, peers, rank, precision="fp64"):
+    """Rank ``rank``'s share of the balanced symmetric contraction: its tiles
+    go to its own stripe, their transposes to the peers' stripes.  All ranks
+    must barrier before reading (stripes.StripedDistanceMatrix does)."""
+    begins, ptrs = peers.tables()
+    _capi.check(_capi.load().scedar_pdist_stripe_p2p(
+        cells._h, PRECISION_IDS[precision], rank, peers.world, begins, ptrs,
+        peers.n, _stream()))

@@ -45,6 +45,14 @@ class _DeviceOps(object):
         from . import device
         return device.knn_from_d(d, k, exclude, row_begin=row_begin)
 
+    def peer_stripes(self, stripes, n, rank, group):
+        from . import device
+        return device.PeerStripes(stripes, n, rank=rank, group=group)
+
+    def pdist_stripe_p2p(self, cells, peers, rank):
+        from . import device
+        device.pdist_stripe_p2p(cells, peers, rank)
+
     def knn_stripe(self, cells, k, exclude, r0, r1):
         return cells.knn_stripe(k, exclude, r0, r1)
 
@@ -78,6 +86,7 @@ class StripedDistanceMatrix(object):
         if self.world > 1 and broadcast:
             dist.broadcast(x, src=src, group=group)
         self.n, self.p = x.shape
+        self.d_device = x.device
         self.metric = metric
         self.stripes = partition(self.n, self.world)
         self.row_begin, self.row_end = self.stripes[self.rank]
@@ -88,11 +97,37 @@ class StripedDistanceMatrix(object):
     def rows(self):
         return self.row_end - self.row_begin
 
-    def compute_d(self, out=None):
-        """This rank's rows of D, kept in HBM: tensor [rows, n]."""
+    def compute_d(self, out=None, peers=None):
+        """This rank's rows of D, kept in HBM: tensor [rows, n].
+
+        With ``peers`` (a ``device.PeerStripes`` shared by all ranks) the
+        contraction is the balanced symmetric one: every tile pair of the
+        whole matrix is computed by one rank and mirrored into the other
+        owner's stripe over NVLink.  The two barriers fence the peer writes:
+        nobody may still be reading a stripe when the stores start, and every
+        store must have landed before anyone reads."""
+        if peers is not None and self.world > 1:
+            self._fence()
+            self.ops.pdist_stripe_p2p(self.cells, peers, self.rank)
+            self._fence()
+            self.d_stripe = peers.tensor(self.rank)
+            return self.d_stripe
         self.d_stripe = self.ops.pdist_stripe(self.cells, self.row_begin,
                                               self.row_end, out=out)
         return self.d_stripe
+
+    def _fence(self):
+        """Stream-ordered cross-rank barrier (a one-element all-reduce): no
+        host synchronisation, later kernels on this stream wait for it."""
+        if getattr(self, "_flag", None) is None:
+            self._flag = torch.zeros(1, dtype=torch.int32,
+                                     device=self.d_device)
+        dist.all_reduce(self._flag, group=self.group)
+
+    def make_peer_stripes(self):
+        """Allocate this rank's peer-mappable D stripe and map the others."""
+        return self.ops.peer_stripes(self.stripes, self.n, self.rank,
+                                     self.group)
 
     def knn_local(self, k, exclude, from_d=True):
         """(idx[rows, k] int64, dist[rows, k]) of this rank's rows."""

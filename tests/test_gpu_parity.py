@@ -403,3 +403,29 @@ def test_host_abi(b200):
             x.ctypes.data_as(ctypes.c_void_p), 700, 130, 1, 0, 700, 1,
             idx.ctypes.data_as(ctypes.c_void_p),
             dist.ctypes.data_as(ctypes.c_void_p), 0))
+
+
+def test_p2p_balanced_symmetric_single_gpu_emulation(b200):
+    """The multi-GPU peer-store kernel, with the N ranks emulated one after
+    the other on one GPU (all stripes local): every stripe must equal the
+    rows of the whole-matrix result bit for bit."""
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200.stripes import partition
+    x = torch.from_numpy(np.random.default_rng(8).gamma(
+        0.5, 1.0, size=(1100, 70))).cuda()
+    for m in ("correlation", "euclidean"):
+        cells = dev.Cells.from_dense(x, m)
+        full = cells.pdist_symmetric()
+        for world in (1, 2, 3, 8, 11):
+            parts = partition(1100, world)
+            peers = dev.PeerStripes(parts, 1100)
+            for r in range(world):
+                peers.tensor(r).fill_(-7.0)
+            for r in range(world):
+                dev.pdist_stripe_p2p(cells, peers, r)
+            torch.cuda.synchronize()
+            for r, (b, e) in enumerate(parts):
+                assert torch.equal(peers.tensor(r), full[b:e]), (m, world, r)
+            peers.close()
+        cells.close()
