@@ -203,6 +203,10 @@ def run_b200(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != a.gpus:
         raise SystemExit("--gpus {} but WORLD_SIZE={}".format(a.gpus, world))
+    # NCCL prints its version banner on stdout: keep fd 1 clean for the one
+    # JSON line the driver reads
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -219,7 +223,15 @@ def run_b200(a):
     if world > 1:
         dist.broadcast(x_dev, src=0)
     r0, r1 = partition(n, world)[rank]
-    d_buf = torch.empty((r1 - r0, n), dtype=torch.float64, device=dev)
+    # D stripe: with several GPUs it is a peer-mapped buffer so the symmetric
+    # contraction can mirror tiles into the owner's HBM over NVLink
+    peers = None
+    if world > 1:
+        from scedar_b200.device import PeerStripes
+        peers = PeerStripes(partition(n, world), n, rank=rank)
+        d_buf = peers.tensor(rank)
+    else:
+        d_buf = torch.empty((r1 - r0, n), dtype=torch.float64, device=dev)
     idx_host = torch.empty((n, k), dtype=torch.int64).pin_memory()
     dist_host = torch.empty((n, k), dtype=torch.float64).pin_memory()
     phase_events = []
@@ -238,7 +250,7 @@ def run_b200(a):
             ev[1].record()
         if trace:
             trace.append(time.perf_counter())
-        sdm.compute_d(out=d_buf)                           # K2
+        sdm.compute_d(out=d_buf, peers=peers)              # K2
         if ev:
             ev[2].record()
         if trace:
@@ -313,6 +325,11 @@ def run_b200(a):
     sync_all()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / a.steps)
     e2e_value = float(n) * n / e2e_s
+    if peers is not None:        # unmap before anyone frees its stripe
+        sync_all()
+        del d_buf
+        peers.close()
+        peers = None
 
     # ---- self-check of the last step's result on 64 rows (not timed) -------
     if rank == 0 and a.metric == "correlation":
@@ -335,8 +352,10 @@ def run_b200(a):
         return
 
     rows_here = r1 - r0
-    entries = rows_here * float(n) - rows_here * (rows_here - 1) / 2.0
-    alg_flops = 2.0 * p * entries          # n(n+1)p at N=1 (symmetric)
+    # entries of D this rank computes: the symmetric contraction is split
+    # evenly over the ranks (every tile pair once), n(n+1)/2 in total
+    entries = (n * (n + 1.0) / 2.0) * rows_here / n
+    alg_flops = 2.0 * p * entries          # n(n+1)p/N
     fp64_peak = fp64_peak_tflops()
     achieved = alg_flops / (gram_avg_ms * 1e-3) * 1e-12
     peaks = measured_peaks()
@@ -347,7 +366,10 @@ def run_b200(a):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "n_cells": n, "n_genes": p,
                    "k": k, "metric": a.metric,
-                   "sharding": "row stripes x{}".format(world),
+                   "sharding": "row stripes x{}{}".format(
+                       world, ", symmetric tile pairs mirrored into the "
+                       "owner's stripe by peer stores over NVLink"
+                       if world > 1 else ", lower tiles mirrored"),
                    "l2": "inputs larger than L2 (x {:.1f} GB, D stripe "
                          "{:.1f} GB per GPU)".format(
                              n * p * 8e-9, rows_here * n * 8e-9),
@@ -377,7 +399,7 @@ def run_b200(a):
     }
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(a)
-    print(json.dumps(out), flush=True)
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
