@@ -71,9 +71,7 @@ int check_metric(int metric) {
 }
 
 int check_precision(int precision) {
-  if (precision == SCEDAR_PRECISION_FP64) return SCEDAR_OK;
-  if (precision == SCEDAR_PRECISION_FAST)
-    return fail(SCEDAR_ERR_UNSUPPORTED, "fast precision is not built in this version");
+  if (precision == SCEDAR_PRECISION_FP64 || precision == SCEDAR_PRECISION_FAST) return SCEDAR_OK;
   return fail(SCEDAR_ERR_ARG, "precision must be 0 (fp64) or 1 (fast)");
 }
 
@@ -115,6 +113,40 @@ int new_cells(int64_t n, int64_t p, int metric, cudaStream_t s, scedar_cells** o
 }
 
 }  // namespace
+int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin,
+                    int64_t row_end, int64_t* idx_out, double* dist_out, cudaStream_t s) {
+  const int64_t rows = row_end - row_begin;
+  if (k == 0 || rows <= 0) return SCEDAR_OK;
+  const int K = k + 1;
+  if (K <= 32) {
+    // fused: Gram tile -> epilogue -> per-row lists in shared memory, D never
+    // reaches HBM; column splits give every SM work, then one merge pass
+    const int splits = gram_topk_splits(c, rows);
+    Scratch pd, pi;
+    SCEDAR_CHECK(pd.alloc(sizeof(double) * splits * rows * K, s));
+    SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * splits * rows * K, s));
+    SCEDAR_CHECK(launch_gram_topk(c, row_begin, row_end, K, splits, pd.as<double>(),
+                                  pi.as<int32_t>(), s));
+    return launch_topk_merge(pd.as<double>(), pi.as<int32_t>(), splits, rows, K, row_begin, k,
+                             exclude, idx_out, dist_out, s);
+  }
+  if (K > 128) return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
+  // wider lists: materialise D in row chunks that stay L2-sized, select per chunk
+  int64_t chunk = (int64_t(256) << 20) / (8 * std::max<int64_t>(c->n, 1));
+  chunk = std::max<int64_t>(128, chunk / 128 * 128);
+  chunk = std::min(chunk, round_up(rows, 128));
+  Scratch dbuf;
+  SCEDAR_CHECK(dbuf.alloc(sizeof(double) * chunk * c->n, s));
+  for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk) {
+    const int64_t r1 = std::min(row_end, r0 + chunk);
+    SCEDAR_CHECK(launch_gram_stripe(c, r0, r1, dbuf.as<double>(), c->n, s));
+    SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), c->n, c->n, r0, r1, k, exclude,
+                                    idx_out + (r0 - row_begin) * k,
+                                    dist_out + (r0 - row_begin) * k, s));
+  }
+  return SCEDAR_OK;
+}
+
 }  // namespace scedar
 
 using namespace scedar;
@@ -162,6 +194,7 @@ int scedar_cells_from_csr(const void* indptr, int indptr_is_64, const int32_t* i
 
 int scedar_cells_free(scedar_cells_t* c) {
   if (!c) return SCEDAR_OK;
+  if (c->fast) fast_state_free(c->fast, c->stream);
   if (c->xw) cudaFreeAsync(c->xw, c->stream);
   if (c->stat) cudaFreeAsync(c->stat, c->stream);
   delete c;
@@ -179,6 +212,8 @@ int scedar_pdist_stripe(const scedar_cells_t* c, int precision, int64_t row_begi
   if (row_end == row_begin) return SCEDAR_OK;
   if (!d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (precision == SCEDAR_PRECISION_FAST)
+    return launch_fast_stripe(c, row_begin, row_end, d_out, ldd, static_cast<cudaStream_t>(stream));
   return launch_gram_stripe(c, row_begin, row_end, d_out, ldd, static_cast<cudaStream_t>(stream));
 }
 
@@ -189,6 +224,8 @@ int scedar_pdist_symmetric(const scedar_cells_t* c, int precision, double* d_out
   if (c->n == 0) return SCEDAR_OK;
   if (!d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (precision == SCEDAR_PRECISION_FAST)
+    return launch_fast_stripe(c, 0, c->n, d_out, ldd, static_cast<cudaStream_t>(stream));
   return launch_gram_symmetric(c, d_out, ldd, static_cast<cudaStream_t>(stream));
 }
 
@@ -197,6 +234,8 @@ int scedar_pdist_stripe_p2p(const scedar_cells_t* c, int precision, int rank, in
                             int64_t ldd, void* stream) {
   if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
   SCEDAR_CHECK(check_precision(precision));
+  if (precision != SCEDAR_PRECISION_FP64)
+    return fail(SCEDAR_ERR_UNSUPPORTED, "peer-store stripes are FP64 only");
   if (!stripe_begin || !stripe_ptr) return fail(SCEDAR_ERR_ARG, "NULL stripe table");
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
   return launch_gram_stripe_p2p(c, rank, world, stripe_begin, stripe_ptr, ldd,
@@ -257,37 +296,12 @@ int scedar_knn_stripe(const scedar_cells_t* c, int precision, int k, int exclude
   if (k < 0 || k > c->n - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
   if (exclude != SCEDAR_EXCLUDE_FIRST && exclude != SCEDAR_EXCLUDE_SELF)
     return fail(SCEDAR_ERR_ARG, "exclude must be 0 (first) or 1 (self)");
-  const int64_t rows = row_end - row_begin;
-  if (k == 0 || rows == 0) return SCEDAR_OK;
+  if (k == 0 || row_end == row_begin) return SCEDAR_OK;
   if (!idx_out || !dist_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
-  const int K = k + 1;
-  if (K <= 32) {
-    // fused: Gram tile -> epilogue -> per-row lists in shared memory, D never
-    // reaches HBM; column splits give every SM work, then one merge pass
-    const int splits = gram_topk_splits(c, rows);
-    Scratch pd, pi;
-    SCEDAR_CHECK(pd.alloc(sizeof(double) * splits * rows * K, s));
-    SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * splits * rows * K, s));
-    SCEDAR_CHECK(launch_gram_topk(c, row_begin, row_end, K, splits, pd.as<double>(),
-                                  pi.as<int32_t>(), s));
-    return launch_topk_merge(pd.as<double>(), pi.as<int32_t>(), splits, rows, K, row_begin, k,
-                             exclude, idx_out, dist_out, s);
-  }
-  if (K > 128) return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
-  // wider lists: materialise D in row chunks that stay L2-sized, select per chunk
-  int64_t chunk = (int64_t(256) << 20) / (8 * std::max<int64_t>(c->n, 1));
-  chunk = std::max<int64_t>(128, chunk / 128 * 128);
-  chunk = std::min(chunk, round_up(rows, 128));
-  Scratch dbuf;
-  SCEDAR_CHECK(dbuf.alloc(sizeof(double) * chunk * c->n, s));
-  for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk) {
-    const int64_t r1 = std::min(row_end, r0 + chunk);
-    SCEDAR_CHECK(launch_gram_stripe(c, r0, r1, dbuf.as<double>(), c->n, s));
-    SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), c->n, c->n, r0, r1, k, exclude,
-                                    idx_out + (r0 - row_begin) * k,
-                                    dist_out + (r0 - row_begin) * k, s));
-  }
-  return SCEDAR_OK;
+  // the tensor-core pass proposes 32 candidates per cell; larger k runs FP64
+  if (precision == SCEDAR_PRECISION_FAST && k <= fast_knn_max_k())
+    return launch_fast_knn(c, k, exclude, row_begin, row_end, idx_out, dist_out, s);
+  return knn_stripe_fp64(c, k, exclude, row_begin, row_end, idx_out, dist_out, s);
 }
 
 int scedar_col_sort(const double* d, int64_t ldd, int64_t rows, int64_t n_cols,

@@ -64,6 +64,7 @@ struct scedar_cells {
   double* xw = nullptr;    // [n_pad, p_pad] working copy (centred if correlation)
   double* stat = nullptr;  // [n_pad] sqrt(1/|x|^2) (0 for zero rows) or |x|^2
   cudaStream_t stream = nullptr;  // creation stream: the frees are ordered on it
+  void* fast = nullptr;  // FastState of the tensor-core path (gram_tc.cu), lazy
 };
 
 namespace scedar {
@@ -93,6 +94,19 @@ int gram_topk_splits(const scedar_cells* c, int64_t rows);
 int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,
                      int K, int splits, double* part_d, int32_t* part_i,
                      cudaStream_t s);
+
+// gram_tc.cu (tcgen05 fast path)
+void fast_state_free(void* fast, cudaStream_t s);
+int fast_knn_max_k();
+int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                       double* d_out, int64_t ldd, cudaStream_t s);
+int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin,
+                    int64_t row_end, int64_t* idx_out, double* dist_out,
+                    cudaStream_t s);
+// capi.cu: the FP64 kNN of a row range (fused when k+1 <= 32)
+int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin,
+                    int64_t row_end, int64_t* idx_out, double* dist_out,
+                    cudaStream_t s);
 
 // topk.cu
 int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols,

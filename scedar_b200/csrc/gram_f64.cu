@@ -25,6 +25,7 @@
 // (n(n+1)p for the symmetric variant).  HBM traffic is bounded by the tile
 // swizzle (16 row panels stay in L2 while the column panels stream once).
 #include "common.cuh"
+#include "topk_list.cuh"
 
 namespace scedar {
 namespace {
@@ -142,20 +143,6 @@ __device__ __forceinline__ void gram_mainloop(double (&acc)[8][4][2], double* sm
   __syncthreads();  // pipeline buffers are free: the epilogue tile aliases them
 }
 
-__device__ __forceinline__ double finish_entry(double P, double s_hi, double s_lo,
-                                               bool diag, int euclid) {
-  double d;
-  if (euclid) {
-    double t2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, P), s_hi), s_lo);
-    t2 = t2 < 0.0 ? 0.0 : t2;
-    d = __dsqrt_rn(t2);
-  } else {
-    d = __dsub_rn(1.0, __dmul_rn(__dmul_rn(P, s_hi), s_lo));
-    d = d < 0.0 ? 0.0 : d;
-  }
-  return diag ? 0.0 : d;
-}
-
 // accumulators -> metric epilogue -> smem tile T[r][c] (stride LDT)
 template <bool RAW>
 __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], double* T,
@@ -196,9 +183,6 @@ __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], doubl
 }
 
 // ---- warp-resident sorted list (one entry per lane), order (d, idx) --------
-__device__ __forceinline__ bool before(double d, int j, double td, int tj) {
-  return d < td || (d == td && j < tj);
-}
 __device__ __forceinline__ void warp_insert(double& ld, int& li, double d, int j, int lane) {
   const unsigned less = __ballot_sync(0xffffffffu, before(ld, li, d, j));
   const int pos = __popc(less);

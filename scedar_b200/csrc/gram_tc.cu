@@ -1,0 +1,662 @@
+// K2 (fast path) -- Gram contraction on the 5th-generation tensor cores:
+// tcgen05.mma (kind::f16, FP32 accumulators in TMEM) fed by TMA into
+// 128B-swizzled shared memory, with the metric epilogue and the streaming
+// top-k fused.  Selected by SCEDAR_PRECISION_FAST.
+//
+// Precision scheme ("3xFP16"): every cell is scaled to unit length in float64
+// and split into two halves x = hi + lo (|x - hi - lo| <= 2^-22 |x|); the
+// contraction accumulates hi.hi + hi.lo + lo.hi in FP32, i.e. a product of
+// FP32 quality from three tensor-core passes over the same K slab (the
+// north star's split-precision fast path; FP16 halves rather than BF16 because
+// unit-length rows need mantissa, not range).  Stated tolerance of the fast
+// distance matrix: |D_fast - D_fp64| <= 2e-5 * max(D) (tests assert it; typical
+// 1e-6).  The fast kNN is EXACT: the tensor-core pass only proposes 32
+// candidates per cell, which are re-ranked with float64 distances computed
+// like the FP64 path and verified against the candidate threshold; cells
+// whose margin is too small are recomputed by the FP64 kernel.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0   TMA producer: per K slab 4 boxes (A_hi, A_lo: 128 x 64 halves;
+//            B_hi, B_lo: 256 x 64) -> 96 KB stage, 2 stages, mbarrier full/empty
+//   warp 1   MMA issuer (one elected lane): per slab 4 k-steps x 3 products of
+//            UMMA 128 x 256 x 16 into one of two 256-column TMEM accumulators;
+//            tcgen05.commit frees the stage / publishes the accumulator
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp quarter),
+//            metric formula, then either a coalesced float64 store of the D
+//            tile through shared memory, or threshold-gated insertion into
+//            the thread-private candidate list of that row
+// The CTA owns a 128-row tile and a range of 256-column tiles, so per-row
+// candidate lists never leave the SM.
+//
+// Replaces the same reference arithmetic as gram_f64.cu (np.dot, cosine /
+// correlation scaling, sklearn euclidean, scedar/eda/sdm.py:1216, 1245-1266).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "topk_list.cuh"
+
+namespace scedar {
+namespace {
+
+constexpr int TM = 128, TN = 256, TK = 64;
+constexpr int TSTAGES = 2;
+constexpr int A_BYTES = TM * TK * 2, B_BYTES = TN * TK * 2;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304
+constexpr int KC = 32;       // candidates kept per row
+constexpr int STG_LD = 33;   // staging / list row stride (conflict-free)
+constexpr int EPI_BYTES = TM * STG_LD * 8;
+constexpr int BAR_BYTES = 128;
+constexpr int TC_SMEM = 1024 + TSTAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t IDESC = (1u << 4)                   // accumulator FP32
+                           | ((uint32_t)(TN >> 3) << 17)  // N
+                           | ((uint32_t)(TM >> 4) << 24); // M; A,B = F16 K-major
+
+struct TcArgs {
+  const double* stat;   // sqrt(1/|x|^2) or |x|^2 (euclid), float64
+  const float* nrm2f;   // euclid: |x|^2 as float
+  const float* nrmf;    // euclid: |x| as float
+  int64_t n;
+  int kblocks;
+  int64_t row_begin, row_end;
+  int euclid;
+  int splits;
+  double* out;          // STORE: D stripe
+  int64_t ldd;
+  float* part_key;      // TOPK: [splits, rows, KC]
+  int32_t* part_idx;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a descriptor or protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  const long long t0 = clock64();
+  do {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("scedar gram_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x);
+      __trap();
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// K-major operand tile in 128B-swizzled shared memory: rows of 128 bytes,
+// 8-row swizzle atoms 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(IDESC), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool beforef(float k, int j, float tk, int tj) {
+  return k < tk || (k == tk && j < tj);
+}
+
+template <bool TOPK>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+               const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi,
+               const __grid_constant__ CUtensorMap map_b_lo, const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  uint8_t* epi = gbase + TSTAGES * STAGE_BYTES;
+  const uint32_t bars = base + TSTAGES * STAGE_BYTES + EPI_BYTES;
+  // barrier slots (8 bytes each): full[2], empty[2], tfull[2], tempty[2]
+  const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(epi + EPI_BYTES + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(tfull0 + 8 * s, 1);
+      mbar_init(tempty0 + 8 * s, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_slot))),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t I = a.row_begin / TM + blockIdx.x;
+  const int64_t i0 = I * TM;
+  const int64_t CT = (a.n + TN - 1) / TN;
+  const int64_t J0 = CT * blockIdx.y / a.splits, J1 = CT * (blockIdx.y + 1) / a.splits;
+  const int KB = a.kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t J = J0; J < J1; ++J) {
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+          const uint32_t st = base + s * STAGE_BYTES;
+          tma_load_2d(st, &map_a_hi, kb * TK, (int)i0, full0 + 8 * s);
+          tma_load_2d(st + A_BYTES, &map_a_lo, kb * TK, (int)i0, full0 + 8 * s);
+          tma_load_2d(st + 2 * A_BYTES, &map_b_hi, kb * TK, (int)(J * TN), full0 + 8 * s);
+          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * TK, (int)(J * TN),
+                      full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, t = 0;
+      for (int64_t J = J0; J < J1; ++J, ++t) {
+        const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+        mbar_wait(tempty0 + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < TK / 16; ++kk) {
+            const uint64_t ah = umma_desc(st + kk * 32);
+            const uint64_t al = umma_desc(st + A_BYTES + kk * 32);
+            const uint64_t bh = umma_desc(st + 2 * A_BYTES + kk * 32);
+            const uint64_t bl = umma_desc(st + 2 * A_BYTES + B_BYTES + kk * 32);
+            umma_f16(d_tmem, ah, bh, (kb | kk) != 0);
+            umma_f16(d_tmem, ah, bl, 1);
+            umma_f16(d_tmem, al, bh, 1);
+          }
+          umma_commit(empty0 + 8 * s);   // stage reusable once these MMAs retire
+        }
+        umma_commit(tfull0 + 8 * acc);   // accumulator complete
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quarter q, one thread per tile row --
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int e = (warp - 2) * 32 + lane;   // 0..127 inside the epilogue group
+    const int64_t gi = i0 + r;
+    const bool row_ok = gi >= a.row_begin && gi < a.row_end;
+    double s_row = 0.0;
+    float n2_row = 0.f, n_row = 0.f;
+    if (gi < a.n) {
+      s_row = a.stat[gi];
+      if (a.euclid) {
+        n2_row = a.nrm2f[gi];
+        n_row = a.nrmf[gi];
+      }
+    }
+    float* lkey = reinterpret_cast<float*>(epi);
+    int* lidx = reinterpret_cast<int*>(epi + TM * STG_LD * 4);
+    double* stg = reinterpret_cast<double*>(epi);
+    float tau = __int_as_float(0x7f800000);
+    int tauj = 0x7fffffff;
+    if (TOPK) {
+      for (int c = 0; c < KC; ++c) {
+        lkey[r * STG_LD + c] = __int_as_float(0x7f800000);
+        lidx[r * STG_LD + c] = 0x7fffffff;
+      }
+    }
+    uint32_t t = 0;
+    for (int64_t J = J0; J < J1; ++J, ++t) {
+      const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+      mbar_wait(tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const int64_t j0 = J * TN;
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c0, v);
+        if (TOPK) {
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int64_t gj = j0 + c0 + c;
+              if (gj >= a.n) break;
+              const float pv = __uint_as_float(v[c]);
+              float key;
+              if (a.euclid)
+                key = fmaf(-2.f * n_row * __ldg(a.nrmf + gj), pv, n2_row + __ldg(a.nrm2f + gj));
+              else
+                key = -pv;
+              if (beforef(key, (int)gj, tau, tauj)) {
+                int pos = KC - 1;
+                while (pos > 0 && beforef(key, (int)gj, lkey[r * STG_LD + pos - 1],
+                                          lidx[r * STG_LD + pos - 1])) {
+                  lkey[r * STG_LD + pos] = lkey[r * STG_LD + pos - 1];
+                  lidx[r * STG_LD + pos] = lidx[r * STG_LD + pos - 1];
+                  --pos;
+                }
+                lkey[r * STG_LD + pos] = key;
+                lidx[r * STG_LD + pos] = (int)gj;
+                tau = lkey[r * STG_LD + KC - 1];
+                tauj = lidx[r * STG_LD + KC - 1];
+              }
+            }
+          }
+        } else {
+          // metric in float64 from the FP32 similarity, staged for coalescing
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int64_t gj = j0 + c0 + c;
+            const double pv = (double)__uint_as_float(v[c]);
+            double d;
+            if (a.euclid) {
+              const double s_col = gj < a.n ? a.stat[gj] : 0.0;
+              double t2 = s_row + s_col - 2.0 * sqrt(s_row * s_col) * pv;
+              t2 = t2 < 0.0 ? 0.0 : t2;
+              d = sqrt(t2);
+            } else {
+              d = 1.0 - pv;
+              d = d < 0.0 ? 0.0 : d;
+            }
+            stg[r * STG_LD + c] = gi == gj ? 0.0 : d;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rr * 4 + (e >> 5), col = e & 31;
+            const int64_t gi2 = i0 + row, gj = j0 + c0 + col;
+            if (gi2 >= a.row_begin && gi2 < a.row_end && gj < a.n)
+              a.out[(gi2 - a.row_begin) * a.ldd + gj] = stg[row * STG_LD + col];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+    }
+    if (TOPK && row_ok) {
+      const int64_t rows = a.row_end - a.row_begin;
+      const int64_t o = ((int64_t)blockIdx.y * rows + (gi - a.row_begin)) * KC;
+      for (int c = 0; c < KC; ++c) {
+        a.part_key[o + c] = lkey[r * STG_LD + c];
+        a.part_idx[o + c] = lidx[r * STG_LD + c];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
+// unit-length rows split into FP16 hi/lo: xh, xl [n256, p64]
+__global__ void __launch_bounds__(256)
+split_kernel(const double* __restrict__ xw, const double* __restrict__ stat, int64_t n_pad,
+             int64_t p_pad, int64_t n256, int64_t p64, int euclid, __half* __restrict__ xh,
+             __half* __restrict__ xl, float* __restrict__ nrm2f, float* __restrict__ nrmf) {
+  const int64_t row = blockIdx.x;
+  double scale = 0.0;
+  if (row < n_pad) {
+    const double s = stat[row];
+    scale = euclid ? (s > 0.0 ? 1.0 / sqrt(s) : 0.0) : s;
+    if (threadIdx.x == 0 && euclid) {
+      nrm2f[row] = (float)s;
+      nrmf[row] = (float)sqrt(s);
+    }
+  } else if (threadIdx.x == 0 && euclid) {
+    nrm2f[row] = 0.f;
+    nrmf[row] = 0.f;
+  }
+  for (int64_t c = threadIdx.x; c < p64; c += blockDim.x) {
+    double v = 0.0;
+    if (row < n_pad && c < p_pad) v = xw[row * p_pad + c] * scale;
+    const __half h = __double2half(v);
+    const __half l = __double2half(v - (double)__half2float(h));
+    xh[row * p64 + c] = h;
+    xl[row * p64 + c] = l;
+  }
+}
+
+// merge the per-split candidate lists of a row, recompute the candidates'
+// distances in float64 (same accumulation order and epilogue as the FP64
+// Gram kernel), sort, emit k, and record what the margin check needs
+__global__ void __launch_bounds__(256)
+rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat, int64_t n,
+              int64_t p_pad, int euclid, const float* __restrict__ part_key,
+              const int32_t* __restrict__ part_idx, int splits, int64_t rows, int64_t row_begin,
+              int k, int exclude, int64_t* __restrict__ idx_out, double* __restrict__ dist_out,
+              unsigned int* __restrict__ err_bits, double* __restrict__ tau_out,
+              double* __restrict__ dk_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int K = k + 1;
+  const int64_t gi = row_begin + row;
+  // top-KC approximate candidates over all splits (order: key, index)
+  WarpList<1> L;
+  L.init();
+  for (int s = 0; s < splits; ++s) {
+    const int64_t o = ((int64_t)s * rows + row) * KC;
+    const float kf = part_key[o + lane];
+    const int j = part_idx[o + lane];
+    L.offer((double)kf, j, j != 0x7fffffff, KC, lane);
+  }
+  const int j = L.i[0];
+  const bool valid = j != 0x7fffffff;
+  const double approx = euclid ? sqrt(L.d[0] < 0.0 ? 0.0 : L.d[0]) : 1.0 + L.d[0];
+  // exact distance of my candidate
+  double dist = pos_inf();
+  if (valid) {
+    const double* __restrict__ xi = xw + gi * p_pad;
+    const double* __restrict__ xj = xw + (int64_t)j * p_pad;
+    double acc = 0.0;
+    for (int64_t c = 0; c < p_pad; c += 2) {
+      const double2 u = *reinterpret_cast<const double2*>(xi + c);
+      const double2 w = *reinterpret_cast<const double2*>(xj + c);
+      acc = fma(u.x, w.x, acc);
+      acc = fma(u.y, w.y, acc);
+    }
+    const bool lower = gi >= j;
+    const double si = stat[gi], sj = stat[j];
+    dist = finish_entry(acc, lower ? si : sj, lower ? sj : si, gi == j, euclid);
+  }
+  // observed approximation error (feeds the global margin)
+  float err = valid ? (float)fabs(approx - dist) : 0.f;
+  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+  if (lane == 0) atomicMax(err_bits, __float_as_uint(err));
+  // threshold of the candidate set: the largest approximate distance kept
+  const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+  const double tau = __shfl_sync(0xffffffffu, approx, n_valid > 0 ? n_valid - 1 : 0);
+  // rank by (exact distance, index)
+  int rank = 0;
+  for (int m = 0; m < 32; ++m) {
+    const double dm = __shfl_sync(0xffffffffu, dist, m);
+    const int jm = __shfl_sync(0xffffffffu, j, m);
+    if (m != lane && before(dm, jm, dist, j)) ++rank;
+  }
+  int src = 0;
+  for (int m = 0; m < 32; ++m) {
+    const int rm = __shfl_sync(0xffffffffu, rank, m);
+    if (rm == lane) src = m;
+  }
+  WarpList<1> S;
+  S.d[0] = __shfl_sync(0xffffffffu, dist, src);
+  S.i[0] = __shfl_sync(0xffffffffu, j, src);
+  S.emit(K, exclude, (int)gi, idx_out + row * k, dist_out + row * k, lane);
+  const double dk = __shfl_sync(0xffffffffu, S.d[0], K - 1);
+  if (lane == 0) {
+    // all cells were candidates -> nothing can be missing
+    tau_out[row] = n_valid >= n ? pos_inf() : tau;
+    dk_out[row] = dk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
+              const unsigned int* __restrict__ err_bits, int64_t rows, int64_t row_begin,
+              unsigned char* __restrict__ tile_flag, int* __restrict__ n_flagged) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  // a cell outside the candidate set has approximate distance >= tau, hence
+  // exact distance >= tau - eps; it cannot enter the top k+1 if dk < tau - eps
+  const double eps = 8.0 * (double)__uint_as_float(*err_bits) + 1e-12;
+  if (!(dk[row] + eps < tau[row])) {
+    tile_flag[(row_begin + row) / 128 - row_begin / 128] = 1;
+    atomicAdd(n_flagged, 1);
+  }
+}
+
+int encode_map(CUtensorMap* m, const __half* ptr, int64_t rows, int64_t cols, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(
+      m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    const char* msg = nullptr;
+    cuGetErrorString(r, &msg);
+    return fail(SCEDAR_ERR_CUDA, std::string("cuTensorMapEncodeTiled: ") + (msg ? msg : "?"));
+  }
+  return SCEDAR_OK;
+}
+
+struct FastMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+int tc_splits(int64_t rows, int64_t n) {
+  const int64_t row_tiles = (rows + TM - 1) / TM + 1;
+  const int64_t CT = (n + TN - 1) / TN;
+  int64_t s = (2 * (int64_t)num_sms() + row_tiles - 1) / row_tiles;
+  if (s < 1) s = 1;
+  if (s > CT) s = CT;
+  if (s > 32) s = 32;
+  return (int)s;
+}
+
+}  // namespace
+
+// fast-path working set of a cells handle (created on first use)
+struct FastState {
+  __half* xh = nullptr;
+  __half* xl = nullptr;
+  float* nrm2f = nullptr;
+  float* nrmf = nullptr;
+  int64_t n256 = 0, p64 = 0;
+  FastMaps maps;
+};
+
+void fast_state_free(void* p, cudaStream_t s) {
+  FastState* f = static_cast<FastState*>(p);
+  if (!f) return;
+  if (f->xh) cudaFreeAsync(f->xh, s);
+  if (f->xl) cudaFreeAsync(f->xl, s);
+  if (f->nrm2f) cudaFreeAsync(f->nrm2f, s);
+  if (f->nrmf) cudaFreeAsync(f->nrmf, s);
+  delete f;
+}
+
+static int ensure_fast(const scedar_cells* c, cudaStream_t s, FastState** out) {
+  scedar_cells* mc = const_cast<scedar_cells*>(c);
+  if (mc->fast) {
+    *out = static_cast<FastState*>(mc->fast);
+    return SCEDAR_OK;
+  }
+  FastState* f = new FastState();
+  f->n256 = round_up(c->n_pad, 256);
+  f->p64 = round_up(c->p_pad, TK);
+  const size_t hb = sizeof(__half) * f->n256 * f->p64;
+  cudaError_t e = cudaMallocAsync(&f->xh, hb, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->xl, hb, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->nrm2f, sizeof(float) * f->n256, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->nrmf, sizeof(float) * f->n256, s);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fast_state_free(f, s);
+    return fail(SCEDAR_ERR_NOMEM, std::string("fast-path buffers: ") + cudaGetErrorString(e));
+  }
+  const int euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
+  split_kernel<<<(unsigned)f->n256, 256, 0, s>>>(c->xw, c->stat, c->n_pad, c->p_pad, f->n256,
+                                                 f->p64, euclid, f->xh, f->xl, f->nrm2f, f->nrmf);
+  count_launch();
+  int rc = SCEDAR_OK;
+  if (cudaGetLastError() != cudaSuccess) rc = fail(SCEDAR_ERR_CUDA, "split kernel launch failed");
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_hi, f->xh, f->n256, f->p64, TM);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_lo, f->xl, f->n256, f->p64, TM);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_hi, f->xh, f->n256, f->p64, TN);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_lo, f->xl, f->n256, f->p64, TN);
+  if (rc != SCEDAR_OK) {
+    fast_state_free(f, s);
+    return rc;
+  }
+  mc->fast = f;
+  *out = f;
+  return SCEDAR_OK;
+}
+
+static TcArgs tc_args(const scedar_cells* c, const FastState* f, int64_t row_begin,
+                      int64_t row_end) {
+  TcArgs a{};
+  a.stat = c->stat;
+  a.nrm2f = f->nrm2f;
+  a.nrmf = f->nrmf;
+  a.n = c->n;
+  a.kblocks = (int)(f->p64 / TK);
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
+  return a;
+}
+
+int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end, double* d_out,
+                       int64_t ldd, cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  FastState* f = nullptr;
+  SCEDAR_CHECK(ensure_fast(c, s, &f));
+  TcArgs a = tc_args(c, f, row_begin, row_end);
+  a.out = d_out;
+  a.ldd = ldd;
+  const int64_t rows = row_end - row_begin;
+  a.splits = tc_splits(rows, c->n);
+  const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
+  SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  gram_tc_kernel<false><<<dim3((unsigned)RT, (unsigned)a.splits), TC_THREADS, TC_SMEM, s>>>(
+      f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
+int fast_knn_max_k() { return KC - 9; }  // k + 1 + 8 spare candidates <= 32
+
+int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin,
+                    int64_t row_end, int64_t* idx_out, double* dist_out, cudaStream_t s) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0 || k == 0) return SCEDAR_OK;
+  FastState* f = nullptr;
+  SCEDAR_CHECK(ensure_fast(c, s, &f));
+  TcArgs a = tc_args(c, f, row_begin, row_end);
+  a.splits = tc_splits(rows, c->n);
+  const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
+  Scratch pk, pi, tau, dk, misc, flags;
+  SCEDAR_CHECK(pk.alloc(sizeof(float) * a.splits * rows * KC, s));
+  SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * a.splits * rows * KC, s));
+  SCEDAR_CHECK(tau.alloc(sizeof(double) * rows, s));
+  SCEDAR_CHECK(dk.alloc(sizeof(double) * rows, s));
+  SCEDAR_CHECK(misc.alloc(16, s));
+  SCEDAR_CHECK(flags.alloc(RT + 16, s));
+  SCEDAR_CUDA(cudaMemsetAsync(misc.ptr, 0, 16, s));
+  SCEDAR_CUDA(cudaMemsetAsync(flags.ptr, 0, RT + 16, s));
+  a.part_key = pk.as<float>();
+  a.part_idx = pi.as<int32_t>();
+  SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  gram_tc_kernel<true><<<dim3((unsigned)RT, (unsigned)a.splits), TC_THREADS, TC_SMEM, s>>>(
+      f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
+  SCEDAR_CUDA(cudaGetLastError());
+  unsigned int* err_bits = misc.as<unsigned int>();
+  int* n_flagged = reinterpret_cast<int*>(misc.as<unsigned int>() + 1);
+  rerank_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+      c->xw, c->stat, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits, rows, row_begin,
+      k, exclude, idx_out, dist_out, err_bits, tau.as<double>(), dk.as<double>());
+  margin_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+      tau.as<double>(), dk.as<double>(), err_bits, rows, row_begin, flags.as<unsigned char>(),
+      n_flagged);
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch(3);
+  // rows whose candidate margin is too thin are recomputed by the FP64 kernel
+  int h_flagged = 0;
+  SCEDAR_CUDA(cudaMemcpyAsync(&h_flagged, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SCEDAR_CUDA(cudaStreamSynchronize(s));
+  if (h_flagged == 0) return SCEDAR_OK;
+  std::vector<unsigned char> hf((size_t)RT);
+  SCEDAR_CUDA(cudaMemcpyAsync(hf.data(), flags.ptr, (size_t)RT, cudaMemcpyDeviceToHost, s));
+  SCEDAR_CUDA(cudaStreamSynchronize(s));
+  const int64_t t0 = row_begin / TM;
+  for (int64_t t = 0; t < RT; ++t) {
+    if (!hf[(size_t)t]) continue;
+    int64_t t1 = t;
+    while (t1 + 1 < RT && hf[(size_t)(t1 + 1)]) ++t1;
+    const int64_t r0 = std::max<int64_t>(row_begin, (t0 + t) * TM);
+    const int64_t r1 = std::min<int64_t>(row_end, (t0 + t1 + 1) * TM);
+    SCEDAR_CHECK(knn_stripe_fp64(c, k, exclude, r0, r1, idx_out + (r0 - row_begin) * k,
+                                 dist_out + (r0 - row_begin) * k, s));
+    t = t1;
+  }
+  return SCEDAR_OK;
+}
+
+}  // namespace scedar

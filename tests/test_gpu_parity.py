@@ -429,3 +429,50 @@ def test_p2p_balanced_symmetric_single_gpu_emulation(b200):
                 assert torch.equal(peers.tensor(r), full[b:e]), (m, world, r)
             peers.close()
         cells.close()
+
+
+@pytest.mark.parametrize("metric", ["correlation", "cosine", "euclidean"])
+def test_fast_path_tcgen05(b200, metric):
+    """precision='fast' (tcgen05 + TMA, 3xFP16 split): the distance matrix is
+    within the stated tolerance 2e-5 * max(D) of the FP64 path, and the kNN is
+    EXACT (same indices, same float64 distances) after the FP64 re-rank."""
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200._capi import EXCLUDE_FIRST, EXCLUDE_SELF
+    from scedar_b200 import synth
+    for n, p in ((700, 300), (1500, 130), (2100, 2000)):
+        x = torch.from_numpy(synth.log_counts(n, p, seed=n + p)).cuda()
+        cells = dev.Cells.from_dense(x, metric)
+        d64 = cells.pdist_symmetric()
+        dfast = cells.pdist_stripe(0, n, precision="fast")
+        err = (dfast - d64).abs().max().item() / d64.max().item()
+        assert err <= 2e-5, (metric, n, p, err)
+        assert torch.equal(dfast.diagonal(), torch.zeros_like(dfast.diagonal()))
+        part = cells.pdist_stripe(200, 555, precision="fast")
+        assert torch.equal(part, dfast[200:555])
+        for k, ex in ((15, EXCLUDE_FIRST), (15, EXCLUDE_SELF), (1, EXCLUDE_SELF),
+                      (23, EXCLUDE_FIRST)):
+            i64, v64 = cells.knn_stripe(k, ex)
+            ifa, vfa = cells.knn_stripe(k, ex, precision="fast")
+            assert torch.equal(i64, ifa), (metric, n, p, k, ex)
+            assert torch.allclose(v64, vfa, rtol=1e-12, atol=1e-14)
+        ifa, vfa = cells.knn_stripe(15, EXCLUDE_SELF, 300, 650, precision="fast")
+        i64, v64 = cells.knn_stripe(15, EXCLUDE_SELF, 300, 650)
+        assert torch.equal(i64, ifa)
+        cells.close()
+
+
+def test_fast_path_ties_and_fallback(b200):
+    """Integer counts: thousands of exact ties defeat any margin, so the fast
+    kNN must fall back to the FP64 kernel for those rows and still be exact."""
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200._capi import EXCLUDE_FIRST
+    from scedar_b200 import synth
+    x = torch.from_numpy(synth.raw_counts(900, 60, seed=4)).cuda()
+    for metric in ("euclidean", "cosine"):
+        cells = dev.Cells.from_dense(x, metric)
+        i64, v64 = cells.knn_stripe(10, EXCLUDE_FIRST)
+        ifa, vfa = cells.knn_stripe(10, EXCLUDE_FIRST, precision="fast")
+        assert torch.equal(i64, ifa) and torch.equal(v64, vfa)
+        cells.close()
