@@ -51,6 +51,9 @@ constexpr int EPI_BYTES = TM * STG_LD * 8;
 constexpr int BAR_BYTES = 128;
 constexpr int TC_SMEM = 1024 + TSTAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
 constexpr int TC_THREADS = 192;
+constexpr int RR_CH = 64, RR_LD = 65;   // re-rank: genes per chunk, padded row stride
+constexpr int RR_WARPS = 4;
+constexpr int RR_SMEM = RR_WARPS * (32 * RR_LD + RR_CH) * 8;
 constexpr uint32_t IDESC = (1u << 4)                   // accumulator FP32
                            | ((uint32_t)(TN >> 3) << 17)  // N
                            | ((uint32_t)(TM >> 4) << 24); // M; A,B = F16 K-major
@@ -389,7 +392,7 @@ split_kernel(const double* __restrict__ xw, const double* __restrict__ stat, int
 // merge the per-split candidate lists of a row, recompute the candidates'
 // distances in float64 (same accumulation order and epilogue as the FP64
 // Gram kernel), sort, emit k, and record what the margin check needs
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * RR_WARPS)
 rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat, int64_t n,
               int64_t p_pad, int euclid, const float* __restrict__ part_key,
               const int32_t* __restrict__ part_idx, int splits, int64_t rows, int64_t row_begin,
@@ -413,18 +416,40 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat, in
   const int j = L.i[0];
   const bool valid = j != 0x7fffffff;
   const double approx = euclid ? sqrt(L.d[0] < 0.0 ? 0.0 : L.d[0]) : 1.0 + L.d[0];
-  // exact distance of my candidate
+  // exact distance of my candidate: the warp streams the 32 candidate rows
+  // through shared memory in 64-gene chunks (coalesced 512-byte row segments),
+  // then every lane walks its own row in gene order with one FMA chain -- the
+  // accumulation order of the FP64 Gram kernel
+  extern __shared__ double rr_smem[];
+  double* buf = rr_smem + (threadIdx.x >> 5) * (32 * RR_LD + RR_CH);
+  double* xs = buf + 32 * RR_LD;
+  const double* __restrict__ xi = xw + gi * p_pad;
+  double acc = 0.0;
+  for (int64_t c0 = 0; c0 < p_pad; c0 += RR_CH) {
+    const int64_t left = p_pad - c0;
+    const bool in = 2 * lane < left;          // p_pad is a multiple of 16
+#pragma unroll 8
+    for (int m = 0; m < 32; ++m) {
+      const int jm = __shfl_sync(0xffffffffu, j, m);
+      double2 w = make_double2(0.0, 0.0);
+      if (jm != 0x7fffffff && in)
+        w = *reinterpret_cast<const double2*>(xw + (int64_t)jm * p_pad + c0 + 2 * lane);
+      buf[m * RR_LD + 2 * lane] = w.x;
+      buf[m * RR_LD + 2 * lane + 1] = w.y;
+    }
+    {
+      double2 u = make_double2(0.0, 0.0);
+      if (in) u = *reinterpret_cast<const double2*>(xi + c0 + 2 * lane);
+      xs[2 * lane] = u.x;
+      xs[2 * lane + 1] = u.y;
+    }
+    __syncwarp();
+    const int lim = left < RR_CH ? (int)left : RR_CH;
+    for (int c = 0; c < lim; ++c) acc = fma(xs[c], buf[lane * RR_LD + c], acc);
+    __syncwarp();
+  }
   double dist = pos_inf();
   if (valid) {
-    const double* __restrict__ xi = xw + gi * p_pad;
-    const double* __restrict__ xj = xw + (int64_t)j * p_pad;
-    double acc = 0.0;
-    for (int64_t c = 0; c < p_pad; c += 2) {
-      const double2 u = *reinterpret_cast<const double2*>(xi + c);
-      const double2 w = *reinterpret_cast<const double2*>(xj + c);
-      acc = fma(u.x, w.x, acc);
-      acc = fma(u.y, w.y, acc);
-    }
     const bool lower = gi >= j;
     const double si = stat[gi], sj = stat[j];
     dist = finish_entry(acc, lower ? si : sj, lower ? sj : si, gi == j, euclid);
@@ -480,15 +505,28 @@ int encode_map(CUtensorMap* m, const __half* ptr, int64_t rows, int64_t cols, in
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
   cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(
+  // resolved through the runtime: the library must load (and be inspected) on
+  // machines without a driver, so it cannot link against libcuda
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) !=
+            cudaSuccess || !fn)
+      return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  CUresult r = encode(
       m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    const char* msg = nullptr;
-    cuGetErrorString(r, &msg);
-    return fail(SCEDAR_ERR_CUDA, std::string("cuTensorMapEncodeTiled: ") + (msg ? msg : "?"));
-  }
+  if (r != CUDA_SUCCESS)
+    return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " +
+                                     std::to_string((int)r));
   return SCEDAR_OK;
 }
 
@@ -629,7 +667,9 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   SCEDAR_CUDA(cudaGetLastError());
   unsigned int* err_bits = misc.as<unsigned int>();
   int* n_flagged = reinterpret_cast<int*>(misc.as<unsigned int>() + 1);
-  rerank_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+  SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   RR_SMEM));
+  rerank_kernel<<<(unsigned)((rows + RR_WARPS - 1) / RR_WARPS), 32 * RR_WARPS, RR_SMEM, s>>>(
       c->xw, c->stat, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits, rows, row_begin,
       k, exclude, idx_out, dist_out, err_bits, tau.as<double>(), dk.as<double>());
   margin_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(

@@ -12,6 +12,7 @@ Plotting, t-SNE / UMAP / PCA, HNSW and the classified-sample subclasses are
 not part of this path and are not provided here; see
 INTEGRATION.md for patching these hooks into an installed scedar instead.
 """
+import os
 import warnings
 from collections import defaultdict
 
@@ -28,6 +29,7 @@ DEVICE_D_CACHE_BYTES = 48 << 30
 # stripe size used when D is streamed to the host in pieces
 STRIPE_BYTES = 2 << 30
 MAX_TOPK = 127
+FAST_MAX_K = 23     # tensor-core candidate lists hold 32 entries
 
 
 def _check_is_valid_sfids(sfids):
@@ -51,7 +53,15 @@ class SampleDistanceMatrix(object):
 
     Parameters are the reference's (sdm.py:93-94).  ``nprocs`` is accepted and
     stored for compatibility; the device is the current CUDA device.
+
+    ``precision`` (class or instance attribute, default from the environment
+    variable ``SCEDAR_B200_PRECISION``, else ``"fp64"``) selects the Gram
+    kernel: ``"fp64"`` matches the reference's float64 to 1e-10;
+    ``"fast"`` runs the contraction on the tcgen05 tensor cores -- the
+    distance matrix is then within 1e-4 * max(D), while kNN results stay
+    exact (float64 re-rank of the tensor-core candidates).
     """
+    precision = os.environ.get("SCEDAR_B200_PRECISION", "fp64")
 
     def __init__(self, x, d=None, metric="cosine", use_pdist=True,
                  sids=None, fids=None, nprocs=None):
@@ -114,6 +124,7 @@ class SampleDistanceMatrix(object):
         # device-side caches (not part of the reference's state)
         self._cells_lut = {}
         self._d_dev = None
+        self._d_user = d is not None
 
     # ------------------------------------------------------------------ ids
     @property
@@ -197,7 +208,8 @@ class SampleDistanceMatrix(object):
             if self._lazy_load_d is not None:
                 self._d_dev = dev.to_device(self._lazy_load_d)
             else:
-                self._d_dev = self._cells(self._metric).pdist_symmetric()
+                self._d_dev = self._cells(self._metric).pdist_symmetric(
+                    precision=self.precision)
         return self._d_dev
 
     def _d_stripes(self):
@@ -216,7 +228,8 @@ class SampleDistanceMatrix(object):
         cells = self._cells(self._metric)
         for r0 in range(0, n, rows):
             r1 = min(n, r0 + rows)
-            yield r0, r1, cells.pdist_stripe(r0, r1)
+            yield r0, r1, cells.pdist_stripe(r0, r1,
+                                             precision=self.precision)
 
     # ----------------------------------------------------- distance matrix
     @staticmethod
@@ -338,10 +351,16 @@ class SampleDistanceMatrix(object):
         n = self._x.shape[0]
         idx = np.empty((n, k), dtype=np.int64)
         dist = np.empty((n, k), dtype=np.float64)
-        if (self._lazy_load_d is None and self._d_dev is None
-                and k <= 31 and n * n * 8 > DEVICE_D_CACHE_BYTES):
-            # D is not needed by anyone yet and would not fit: fused path
-            i, dd = self._cells(self._metric).knn_stripe(k, exclude)
+        fused = (self._lazy_load_d is None and self._d_dev is None
+                 and k <= 31 and n * n * 8 > DEVICE_D_CACHE_BYTES)
+        # a tensor-core D is approximate: exact neighbours come from the
+        # candidate + float64 re-rank kernel, never from that matrix
+        exact_fast = (self.precision == "fast" and not self._d_user
+                      and k <= FAST_MAX_K)
+        if fused or exact_fast:
+            # D is not needed (or would not fit): fused Gram -> top-k
+            i, dd = self._cells(self._metric).knn_stripe(
+                k, exclude, precision=self.precision)
             return i.cpu().numpy(), dd.cpu().numpy()
         for r0, r1, stripe in self._d_stripes():
             i, dd = dev.knn_from_d(stripe, k, exclude, row_begin=r0)
@@ -431,7 +450,8 @@ class SampleDistanceMatrix(object):
             if k > MAX_TOPK:
                 raise NotImplementedError("k > {} without pdist".format(
                     MAX_TOPK))
-            i, dd = self._cells(metric).knn_stripe(k, EXCLUDE_SELF)
+            i, dd = self._cells(metric).knn_stripe(k, EXCLUDE_SELF,
+                                                   precision=self.precision)
             idx, dist = i.cpu().numpy(), dd.cpu().numpy()
         return list(idx), list(dist)
 

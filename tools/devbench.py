@@ -42,6 +42,13 @@ def main():
             del d
         t = timed(lambda: cells.knn_stripe(15, EXCLUDE_SELF))
         out["fused_knn_ms"] = round(t, 3); out["fused_tflops"] = round(2.0 * n * n * p / t * 1e-9, 2)
+        t = timed(lambda: cells.knn_stripe(15, EXCLUDE_SELF, precision="fast"))
+        out["fast_knn_ms"] = round(t, 3); out["fast_knn_tflops_alg"] = round(2.0 * n * n * p / t * 1e-9, 2)
+        if n * n * 8 < 60e9:
+            d = torch.empty((n, n), dtype=torch.float64, device="cuda")
+            t = timed(lambda: cells.pdist_stripe(0, n, out=d, precision="fast"))
+            out["fast_d_ms"] = round(t, 3); out["fast_d_tflops_alg"] = round(2.0 * n * n * p / t * 1e-9, 2)
+            del d
         cells.close(); del x
         torch.cuda.empty_cache()
         print(json.dumps(out), flush=True)
