@@ -92,8 +92,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   do {
     if (clock64() - t0 > 8000000000LL) {
-      printf("scedar gram_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x,
-             blockIdx.y, threadIdx.x);
+      printf("scedar gram_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x,
+             threadIdx.x);
       __trap();
     }
     asm volatile(
@@ -199,10 +199,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t I = a.row_begin / TM + blockIdx.x;
+  // 1-D grid, column splits fastest: the CTAs resident at one time cover few
+  // row tiles, so their A panels (and the B tiles they sweep) stay in L2
+  const int split = (int)(blockIdx.x % a.splits);
+  const int64_t I = a.row_begin / TM + blockIdx.x / a.splits;
   const int64_t i0 = I * TM;
   const int64_t CT = (a.n + TN - 1) / TN;
-  const int64_t J0 = CT * blockIdx.y / a.splits, J1 = CT * (blockIdx.y + 1) / a.splits;
+  const int64_t J0 = CT * split / a.splits, J1 = CT * (split + 1) / a.splits;
   const int KB = a.kblocks;
 
   if (warp == 0) {
@@ -346,7 +349,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     if (TOPK && row_ok) {
       const int64_t rows = a.row_end - a.row_begin;
-      const int64_t o = ((int64_t)blockIdx.y * rows + (gi - a.row_begin)) * KC;
+      const int64_t o = ((int64_t)split * rows + (gi - a.row_begin)) * KC;
       for (int c = 0; c < KC; ++c) {
         a.part_key[o + c] = lkey[r * STG_LD + c];
         a.part_idx[o + c] = lidx[r * STG_LD + c];
@@ -534,11 +537,13 @@ struct FastMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-int tc_splits(int64_t rows, int64_t n) {
+int tc_splits(int64_t rows, int64_t n, int64_t min_splits) {
+  // STORE: at least 8 column splits (L2 locality, see the kernel); TOPK: as few
+  // as fill the SMs twice, every split warms up its own candidate lists
   const int64_t row_tiles = (rows + TM - 1) / TM + 1;
   const int64_t CT = (n + TN - 1) / TN;
   int64_t s = (2 * (int64_t)num_sms() + row_tiles - 1) / row_tiles;
-  if (s < 1) s = 1;
+  if (s < min_splits) s = min_splits;
   if (s > CT) s = CT;
   if (s > 32) s = 32;
   return (int)s;
@@ -627,11 +632,11 @@ int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   a.out = d_out;
   a.ldd = ldd;
   const int64_t rows = row_end - row_begin;
-  a.splits = tc_splits(rows, c->n);
+  a.splits = tc_splits(rows, c->n, 8);
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  gram_tc_kernel<false><<<dim3((unsigned)RT, (unsigned)a.splits), TC_THREADS, TC_SMEM, s>>>(
+  gram_tc_kernel<false><<<(unsigned)(RT * a.splits), TC_THREADS, TC_SMEM, s>>>(
       f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
@@ -647,7 +652,7 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   FastState* f = nullptr;
   SCEDAR_CHECK(ensure_fast(c, s, &f));
   TcArgs a = tc_args(c, f, row_begin, row_end);
-  a.splits = tc_splits(rows, c->n);
+  a.splits = tc_splits(rows, c->n, 1);
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   Scratch pk, pi, tau, dk, misc, flags;
   SCEDAR_CHECK(pk.alloc(sizeof(float) * a.splits * rows * KC, s));
@@ -662,7 +667,7 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   a.part_idx = pi.as<int32_t>();
   SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  gram_tc_kernel<true><<<dim3((unsigned)RT, (unsigned)a.splits), TC_THREADS, TC_SMEM, s>>>(
+  gram_tc_kernel<true><<<(unsigned)(RT * a.splits), TC_THREADS, TC_SMEM, s>>>(
       f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
   SCEDAR_CUDA(cudaGetLastError());
   unsigned int* err_bits = misc.as<unsigned int>();
