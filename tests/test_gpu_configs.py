@@ -1,0 +1,149 @@
+"""BASELINE.json configs 2, 3 and 5 at their full sizes on the B200, checked
+through size-independent properties and exact row subsamples (the reference
+cannot hold these matrices on the host).  Config 1 is in
+test_gpu_parity.py::test_c1_scale_properties, config 4 is bench.py (which
+self-checks 64 rows against NumPy)."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests")
+    import scedar_b200
+    from scedar_b200 import _capi
+    _capi.load()
+    return scedar_b200
+
+
+def stable_topk(d_rows, self_rows, k, drop_self):
+    """Reference order on a few rows: (distance, index) ascending."""
+    order = np.argsort(d_rows, kind="mergesort", axis=1)[:, :k + 1]
+    if not drop_self:
+        return order[:, 1:]
+    keep = order != self_rows[:, None]
+    keep[keep.all(axis=1), 0] = False
+    return order[keep].reshape(len(self_rows), k)
+
+
+def test_config2_sparse_cosine_20000(b200):
+    """cosine distance + kNN graph inputs on CSR 20,000 x 20,000, ~10 % nnz."""
+    from scedar_b200 import synth
+    n = p = 20000
+    xs = synth.sparse_lognormal(n, p, seed=20000, density=0.10)
+    sdm = b200.SampleDistanceMatrix(xs, metric="cosine")
+    targets, distances = sdm.s_knns(15)
+    idx, dist = np.array(targets), np.array(distances)
+    assert idx.shape == (n, 15) and (np.diff(dist, axis=1) >= 0).all()
+    assert (idx != np.arange(n)[:, None]).all()
+    # exact rows against SciPy/NumPy float64
+    rows = np.arange(0, n, 331)
+    nrm = np.sqrt(np.asarray(xs.multiply(xs).sum(axis=1)).ravel())
+    dref = 1.0 - (xs[rows] @ xs.T).toarray() / nrm[rows, None] / nrm[None, :]
+    dref[np.arange(len(rows)), rows] = 0.0
+    want = stable_topk(dref, rows, 15, drop_self=True)
+    assert np.array_equal(idx[rows], want)
+    np.testing.assert_allclose(dist[rows],
+                               np.take_along_axis(dref, want, axis=1),
+                               rtol=1e-10, atol=1e-13)
+    d = sdm._d                                   # 3.2 GB, already in HBM
+    assert d.shape == (n, n) and np.array_equal(d[:2000], d[:, :2000].T)
+    assert not d.diagonal().any() and d.min() >= 0
+    assert np.abs(d[rows] - dref).max() <= 1e-10
+    conn = sdm.s_knn_connectivity_matrix(15)
+    assert conn.shape == (n, n) and conn.nnz == 15 * n
+    assert np.array_equal(conn.indptr, 15 * np.arange(n + 1))
+    # CSR path == densified path (same kernels after the scatter)
+    sub = xs[:3000]
+    a = b200.SampleDistanceMatrix(sub, metric="cosine")._d
+    b = b200.SampleDistanceMatrix(sub.toarray(), metric="cosine")._d
+    assert np.array_equal(a, b)
+    sdm.release_device()
+
+
+def test_config3_pbmc68k_euclidean_knn(b200):
+    """68,579 x 2,000 euclidean: the kNN stage of the RareSampleDetection /
+    FeatureImputation pipeline, with and without a materialised D (37.6 GB,
+    kept in HBM)."""
+    import torch
+    from scedar_b200 import device as dev, synth
+    from scedar_b200._capi import EXCLUDE_FIRST, EXCLUDE_SELF
+    n, p, k = 68579, 2000, 15
+    x = synth.blobs(n, p, seed=68579)
+    xt = dev.to_device(x)
+    cells = dev.Cells.from_dense(xt, "euclidean")
+    fi, fd = cells.knn_stripe(k, EXCLUDE_SELF)              # fused, no D
+    d = cells.pdist_symmetric()                             # D in HBM
+    di, dd = dev.knn_from_d(d, k, EXCLUDE_SELF)
+    assert torch.equal(fi, di) and torch.equal(fd, dd)
+    li, ld = dev.knn_from_d(d, k, EXCLUDE_FIRST)            # s_knn_ind_lut
+    assert torch.equal(li, di)            # no duplicates: both rules agree
+    assert torch.equal(d[:4096, :4096], d[:4096, :4096].T)
+    assert float(d.diagonal().abs().max()) == 0.0
+    # tensor-core candidates + FP64 re-rank: identical
+    qi, qd = cells.knn_stripe(k, EXCLUDE_SELF, precision="fast")
+    assert torch.equal(qi, fi) and torch.equal(qd, fd)
+    rows = np.arange(0, n, 1117)
+    sq = np.einsum("ij,ij->i", x, x)
+    d2 = -2.0 * (x[rows] @ x.T)
+    d2 += sq[rows, None]
+    d2 += sq[None, :]
+    dref = np.sqrt(np.maximum(d2, 0))
+    dref[np.arange(len(rows)), rows] = 0.0
+    want = stable_topk(dref, rows, k, drop_self=True)
+    assert np.array_equal(fi.cpu().numpy()[rows], want)
+    got = d[torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert np.abs(got - dref).max() / dref.max() <= 1e-10
+    # rare cells (uniform outliers) have the largest k-th neighbour distance
+    kth = fd[:, -1].cpu().numpy()
+    assert kth.max() > 2 * np.median(kth)
+    cells.close()
+    del d
+    torch.cuda.empty_cache()
+
+
+def test_config5_streaming_topk_1m_x_50(b200):
+    """1,000,000 cells x 50 PCs, k=30, no materialised D.  The full run is
+    checked on sampled rows against brute-force NumPy over all 10^6 cells and
+    through self-consistency; a 20,000-cell subsample is compared with the
+    oracle (the reference's own path) as BASELINE.json states."""
+    import torch
+    from oracle import sdm_oracle as orc
+    from scedar_b200 import device as dev, synth
+    from scedar_b200._capi import EXCLUDE_SELF
+    n, p, k = 1000000, 50, 30
+    x = synth.pcs(n, p, seed=1000000)
+    cells = dev.Cells.from_dense(dev.to_device(x), "euclidean")
+    idx_t, dist_t = cells.knn_stripe(k, EXCLUDE_SELF)
+    idx, dist = idx_t.cpu().numpy(), dist_t.cpu().numpy()
+    cells.close()
+    assert idx.shape == (n, k) and idx.min() >= 0 and idx.max() < n
+    assert (np.diff(dist, axis=1) >= 0).all()
+    assert (idx != np.arange(n)[:, None]).all()
+    rows = np.arange(0, n, 15631)
+    sq = np.einsum("ij,ij->i", x, x)
+    d2 = -2.0 * (x[rows] @ x.T)
+    d2 += sq[rows, None]
+    d2 += sq[None, :]
+    dref = np.sqrt(np.maximum(d2, 0))
+    dref[np.arange(len(rows)), rows] = 0.0
+    want = stable_topk(dref, rows, k, drop_self=True)
+    assert np.array_equal(idx[rows], want)
+    np.testing.assert_allclose(dist[rows],
+                               np.take_along_axis(dref, want, axis=1),
+                               rtol=1e-10, atol=1e-12)
+    # 20k-cell subsample against the oracle
+    sub = x[:20000]
+    cells = dev.Cells.from_dense(dev.to_device(sub), "euclidean")
+    si, sd = cells.knn_stripe(k, EXCLUDE_SELF)
+    cells.close()
+    ridx, rdist = orc.knns_precomputed(orc.pdist(sub, "euclidean"), k)
+    assert np.array_equal(si.cpu().numpy(), ridx)
+    np.testing.assert_allclose(sd.cpu().numpy(), rdist, rtol=1e-10,
+                               atol=1e-12)
+    torch.cuda.empty_cache()
