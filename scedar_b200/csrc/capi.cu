@@ -7,6 +7,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace scedar {
 
@@ -107,6 +108,12 @@ int new_cells(int64_t n, int64_t p, int metric, cudaStream_t s, scedar_cells** o
     scedar_cells_free(c);
     return fail(e == cudaErrorMemoryAllocation ? SCEDAR_ERR_NOMEM : SCEDAR_ERR_CUDA,
                 std::string("allocating the working copy: ") + cudaGetErrorString(e));
+  }
+  int rc = encode_tensor_map(&c->xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->xw, c->n_pad,
+                             c->p_pad, 128, 16);
+  if (rc != SCEDAR_OK) {
+    scedar_cells_free(c);
+    return rc;
   }
   *out = c;
   return SCEDAR_OK;

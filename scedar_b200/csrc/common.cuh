@@ -1,6 +1,7 @@
 // Shared declarations of the scedar_b200 CUDA library (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -65,6 +66,7 @@ struct scedar_cells {
   double* stat = nullptr;  // [n_pad] sqrt(1/|x|^2) (0 for zero rows) or |x|^2
   cudaStream_t stream = nullptr;  // creation stream: the frees are ordered on it
   void* fast = nullptr;  // FastState of the tensor-core path (gram_tc.cu), lazy
+  CUtensorMap xmap;      // TMA view of xw: boxes of 128 rows x 16 doubles, 128B swizzle
 };
 
 namespace scedar {

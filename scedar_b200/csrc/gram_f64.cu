@@ -17,30 +17,42 @@
 // diagonal by construction.  Products are kept out of FMA contraction with
 // __dmul_rn/__dadd_rn so exact ties in integer data stay exact ties.
 //
-// Tiling: CTA 128x128, 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA fragments,
-// K slab 16 doubles (one 128-byte line per row), 3-stage cp.async pipeline.
-// smem rows are padded to 20 doubles so the 64-bit fragment loads of a
-// half-warp (4 rows x 4 k) hit 16 distinct 8-byte banks.
+// Tiling: CTA 128x128; 8 consumer warps (2 x 4), warp tile 64x32 = 8x4 DMMA
+// fragments, plus one producer warp whose elected lane streams K slabs of 16
+// doubles (one 128-byte line per row) with TMA (cp.async.bulk.tensor, 128B
+// swizzle) through a 4-stage ring of full/empty mbarriers -- no CTA-wide
+// barrier and no per-thread copy instructions in the main loop.  Fragment rows
+// are mapped to tile rows by perm8() so the swizzled 64-bit fragment loads of
+// a half-warp (4 rows x 4 k) hit 16 distinct 8-byte banks without padding.
 // Roofline: FP64 tensor pipe; algorithmic flops 2*rows*n*p per stripe
 // (n(n+1)p for the symmetric variant).  HBM traffic is bounded by the tile
 // swizzle (16 row panels stay in L2 while the column panels stream once).
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 #include "topk_list.cuh"
 
 namespace scedar {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3;
-constexpr int LDK = 20;   // padded K stride of a smem row (doubles)
-constexpr int NT = 256;
-constexpr int STAGE_DOUBLES = (BM + BN) * LDK;
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int WARPS_M = 2, WARPS_N = 4;       // consumer warp grid
+constexpr int NCONS = WARPS_M * WARPS_N * 32; // 256 threads issue LDS + DMMA
+constexpr int NT = NCONS + 32;                // + one TMA producer warp
+constexpr int MF = 8, NF = 4;                 // 8x8 fragments per warp tile
+constexpr int WTM = MF * 8, WTN = NF * 8;     // warp tile 64 x 32
+constexpr int PANEL_DOUBLES = BM * BK;        // one TMA box: 128 rows x 16 doubles
+constexpr int STAGE_DOUBLES = 2 * PANEL_DOUBLES;
+constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;  // 32 KB: A panel + B panel
+constexpr int STAGES = 4;
+constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
 constexpr int LDT = 129;  // odd stride: conflict-free row and column sweeps
 constexpr int TILE_DOUBLES = BM * LDT;
-constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;
 constexpr int TILE_BYTES = TILE_DOUBLES * 8;
 constexpr int MAIN_BYTES = PIPE_BYTES > TILE_BYTES ? PIPE_BYTES : TILE_BYTES;
+constexpr int BAR_BYTES = 128;
 constexpr int KFUSED = 32;  // entries kept per row by the fused top-k
 constexpr int LIST_BYTES = BM * KFUSED * (8 + 4);
+constexpr int SMEM_BASE = 1024 + MAIN_BYTES + BAR_BYTES;  // + LIST_BYTES for TOPK
 constexpr int GROUP_ROWS = 16;  // row tiles per L2 swizzle group
 constexpr int kMaxPeers = 16;
 
@@ -68,18 +80,6 @@ struct GramArgs {
   int32_t* part_i;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;\n" ::);
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile(
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -87,60 +87,68 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-// one K slab (16 doubles) of the A and B row panels -> stage buffer
-__device__ __forceinline__ void load_stage(double* stage, const double* __restrict__ xw,
-                                           int64_t p_pad, int64_t i0, int64_t j0,
-                                           int64_t k0, int tid) {
+// Fragment row g of an 8-row group lives in tile row perm8(g): with the
+// 128-byte TMA swizzle (16-byte chunk index XOR row%8) the 16 lanes of a
+// half-warp (4 fragment rows x 4 k) then read 16 distinct 8-byte banks.
+__device__ __forceinline__ int perm8(int g) { return ((g & 3) << 1) | (g >> 2); }
+
+// Consumer side of the pipeline: acc += A(i0.., :) . B(j0.., :)^T over the whole
+// padded K range.  `it` counts K slabs across tiles (stage = it % STAGES).
+__device__ __forceinline__ void gram_consume(double (&acc)[MF][NF][2], const double* pipe,
+                                             uint32_t full0, uint32_t empty0, int KT,
+                                             uint32_t& it) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N, g = lane >> 2, t = lane & 3;
+  const int pa = perm8(g);
+  int off[BK / 4];  // swizzled position of k = 4*kk + t inside a 16-double row
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int idx = tid + it * NT;
-    const int r = idx >> 3, c = idx & 7;
-    cp_async16(stage + r * LDK + c * 2, xw + (i0 + r) * p_pad + k0 + c * 2);
-    cp_async16(stage + (BM + r) * LDK + c * 2, xw + (j0 + r) * p_pad + k0 + c * 2);
+  for (int kk = 0; kk < BK / 4; ++kk) off[kk] = (((2 * kk + (t >> 1)) ^ pa) << 1) | (t & 1);
+  const double* Arow = pipe + (wm * WTM + pa) * BK;
+  const double* Brow = pipe + PANEL_DOUBLES + (wn * WTN + pa) * BK;
+#pragma unroll
+  for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+
+  for (int kt = 0; kt < KT; ++kt, ++it) {
+    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+    mbar_wait(full0 + 8 * s, ph);   // the TMA boxes of this slab have landed
+    const double* As = Arow + s * STAGE_DOUBLES;
+    const double* Bs = Brow + s * STAGE_DOUBLES;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[MF], b[NF];
+#pragma unroll
+      for (int mf = 0; mf < MF; ++mf) a[mf] = As[mf * 8 * BK + off[kk]];
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) b[nf] = Bs[nf * 8 * BK + off[kk]];
+#pragma unroll
+      for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) dmma(acc[mf][nf], a[mf], b[nf]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);   // this warp is done with the slab
   }
 }
 
-// acc[mf][nf][2] += A(i0.., :) . B(j0.., :)^T over the whole padded K range
-__device__ __forceinline__ void gram_mainloop(double (&acc)[8][4][2], double* smem,
-                                              const double* __restrict__ xw,
-                                              int64_t p_pad, int64_t i0, int64_t j0) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int mf = 0; mf < 8; ++mf)
-#pragma unroll
-    for (int nf = 0; nf < 4; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+// Producer side (one lane of the producer warp): stream the K slabs of row
+// panels i0 and j0 through the stage ring.
+__device__ __forceinline__ void gram_produce(const CUtensorMap* map, uint32_t pipe_u32,
+                                             uint32_t full0, uint32_t empty0, int KT,
+                                             int64_t i0, int64_t j0, uint32_t& it) {
+  for (int kt = 0; kt < KT; ++kt, ++it) {
+    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+    mbar_wait(empty0 + 8 * s, ph ^ 1);
+    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+    const uint32_t st = pipe_u32 + s * STAGE_BYTES;
+    tma_load_2d(st, map, kt * BK, (int)i0, full0 + 8 * s);
+    tma_load_2d(st + PANEL_DOUBLES * 8, map, kt * BK, (int)j0, full0 + 8 * s);
+  }
+}
 
-  const int KT = (int)(p_pad / BK);
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_stage(smem + s * STAGE_DOUBLES, xw, p_pad, i0, j0, (int64_t)s * BK, tid);
-    cp_async_commit();
-  }
-  for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    const int nxt = kt + STAGES - 1;
-    if (nxt < KT)
-      load_stage(smem + (nxt % STAGES) * STAGE_DOUBLES, xw, p_pad, i0, j0, (int64_t)nxt * BK, tid);
-    cp_async_commit();
-    const double* As = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 64 + g) * LDK + t;
-    const double* Bs = smem + (kt % STAGES) * STAGE_DOUBLES + (BM + wn * 32 + g) * LDK + t;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
-#pragma unroll
-      for (int mf = 0; mf < 8; ++mf) a[mf] = As[mf * 8 * LDK + kk * 4];
-#pragma unroll
-      for (int nf = 0; nf < 4; ++nf) b[nf] = Bs[nf * 8 * LDK + kk * 4];
-#pragma unroll
-      for (int mf = 0; mf < 8; ++mf)
-#pragma unroll
-        for (int nf = 0; nf < 4; ++nf) dmma(acc[mf][nf], a[mf], b[nf]);
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();  // pipeline buffers are free: the epilogue tile aliases them
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
 }
 
 // accumulators -> metric epilogue -> smem tile T[r][c] (stride LDT)
@@ -149,26 +157,26 @@ __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], doubl
                                              const double* __restrict__ stat,
                                              int64_t i0, int64_t j0, int euclid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N, g = lane >> 2, t = lane & 3;
   double sr[8], sc[4][2];
   if (!RAW) {
 #pragma unroll
-    for (int mf = 0; mf < 8; ++mf) sr[mf] = __ldg(stat + i0 + wm * 64 + mf * 8 + g);
+    for (int mf = 0; mf < 8; ++mf) sr[mf] = __ldg(stat + i0 + wm * 64 + mf * 8 + perm8(g));
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
-      sc[nf][0] = __ldg(stat + j0 + wn * 32 + nf * 8 + 2 * t);
-      sc[nf][1] = __ldg(stat + j0 + wn * 32 + nf * 8 + 2 * t + 1);
+      sc[nf][0] = __ldg(stat + j0 + wn * 32 + nf * 8 + perm8(2 * t));
+      sc[nf][1] = __ldg(stat + j0 + wn * 32 + nf * 8 + perm8(2 * t + 1));
     }
   }
 #pragma unroll
   for (int mf = 0; mf < 8; ++mf) {
-    const int r = wm * 64 + mf * 8 + g;
+    const int r = wm * 64 + mf * 8 + perm8(g);   // fragment row -> tile row
     const int64_t gi = i0 + r;
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int c = wn * 32 + nf * 8 + 2 * t + e;
+        const int c = wn * 32 + nf * 8 + perm8(2 * t + e);
         double v = acc[mf][nf][e];
         if (!RAW) {
           const int64_t gj = j0 + c;
@@ -198,85 +206,31 @@ __device__ __forceinline__ void warp_insert(double& ld, int& li, double d, int j
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
-  extern __shared__ __align__(16) double smem[];
+__global__ void __launch_bounds__(NT, 1)
+gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // the TMA swizzle needs 1 KB alignment
+  double* smem = reinterpret_cast<double*>(smem_raw + (base - raw));  // pipeline / epilogue tile
+  const uint32_t full0 = base + MAIN_BYTES, empty0 = full0 + 8 * STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp == NCONS / 32;
   const int64_t CT = a.n_pad / BN;
+  const int KT = (int)(a.p_pad / BK);
 
-  if (MODE == MODE_TOPK) {
-    // this CTA owns row tile I and the column tiles [J0, J1)
-    double* Ld = smem + MAIN_BYTES / 8;
-    int* Li = reinterpret_cast<int*>(Ld + BM * KFUSED);
-    const int64_t I = a.row_begin / BM + blockIdx.x;
-    const int64_t i0 = I * BM;
-    const int64_t J0 = CT * blockIdx.y / a.splits, J1 = CT * (blockIdx.y + 1) / a.splits;
-    for (int e = tid; e < BM * KFUSED; e += NT) {
-      Ld[e] = __longlong_as_double(0x7ff0000000000000LL);  // +inf
-      Li[e] = 0x7fffffff;
-    }
-    __syncthreads();
-    const int K = a.K;
-    for (int64_t J = J0; J < J1; ++J) {
-      const int64_t j0 = J * BN;
-      double acc[8][4][2];
-      gram_mainloop(acc, smem, a.xw, a.p_pad, i0, j0);
-      tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid);
-      __syncthreads();
-      // warp w scans rows w, w+8, ...; lane l holds entry l of the row's list
-      for (int r = warp; r < BM; r += NT / 32) {
-        const int64_t gi = i0 + r;
-        if (gi < a.row_begin || gi >= a.row_end) continue;
-        double ld = Ld[r * KFUSED + lane];
-        int li = Li[r * KFUSED + lane];
-        double td = __shfl_sync(0xffffffffu, ld, K - 1);
-        int tj = __shfl_sync(0xffffffffu, li, K - 1);
-        bool dirty = false;
-#pragma unroll
-        for (int q = 0; q < BN / 32; ++q) {
-          const int c = lane + 32 * q;
-          const int64_t gj = j0 + c;
-          const double v = smem[r * LDT + c];
-          unsigned m = __ballot_sync(0xffffffffu, gj < a.n && before(v, (int)gj, td, tj));
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const double d = __shfl_sync(0xffffffffu, v, src);
-            const int j = (int)(j0 + src + 32 * q);
-            if (before(d, j, td, tj)) {
-              warp_insert(ld, li, d, j, lane);
-              td = __shfl_sync(0xffffffffu, ld, K - 1);
-              tj = __shfl_sync(0xffffffffu, li, K - 1);
-              dirty = true;
-            }
-          }
-        }
-        if (dirty) {
-          Ld[r * KFUSED + lane] = ld;
-          Li[r * KFUSED + lane] = li;
-        }
-      }
-      __syncthreads();
-    }
-    // partial lists out: part[split][row - row_begin][K]
-    const int64_t rows = a.row_end - a.row_begin;
-    for (int e = tid; e < BM * K; e += NT) {
-      const int r = e / K, l = e % K;
-      const int64_t gi = i0 + r;
-      if (gi < a.row_begin || gi >= a.row_end) continue;
-      const int64_t o = ((int64_t)blockIdx.y * rows + (gi - a.row_begin)) * K + l;
-      a.part_d[o] = Ld[r * KFUSED + l];
-      a.part_i[o] = Li[r * KFUSED + l];
-    }
-    return;
-  }
-
-  // ---- tile coordinates --------------------------------------------------
-  int64_t I, J;
+  // ---- tile coordinates (uniform over the CTA) -----------------------------
+  int64_t I, J = 0, J0 = 0, J1 = 1;
   bool mirrored = false;
   double* mirror_out = a.out;       // stripe that receives the transposed tile
   int64_t mirror_begin = a.row_begin;
-  if (MODE == MODE_DIAG) {
-    I = J = blockIdx.x;
+  if (MODE == MODE_TOPK) {
+    // this CTA owns row tile I and the column tiles [J0, J1)
+    I = a.row_begin / BM + blockIdx.x;
+    J0 = CT * blockIdx.y / a.splits;
+    J1 = CT * (blockIdx.y + 1) / a.splits;
+  } else if (MODE == MODE_DIAG) {
+    I = J0 = blockIdx.x;
+    J1 = J0 + 1;
   } else {
     const int64_t rt0 = a.row_begin / BM;
     const int64_t RT = (a.row_end + BM - 1) / BM - rt0;
@@ -306,63 +260,144 @@ __global__ void __launch_bounds__(NT, 1) gram_f64_kernel(GramArgs a) {
                  J * BN >= a.row_begin && je <= a.row_end;
       if (mirrored && J > I) return;
     }
+    J0 = J;
+    J1 = J + 1;
   }
-  const int64_t i0 = I * BM, j0 = J * BN;
+  const int64_t i0 = I * BM;
 
-  double acc[8][4][2];
-  gram_mainloop(acc, smem, a.xw, a.p_pad, i0, j0);
-
-  if (MODE == MODE_DIAG) {
-    tile_to_smem<true>(acc, smem, nullptr, i0, j0, 0);
-    __syncthreads();
-    if (tid < BM) {
-      const double ss = smem[tid * LDT + tid];
-      double s;
-      if (a.euclid) {
-        s = ss;  // |x|^2
-      } else {
-        // sqrt(1/ss), 0 for a zero vector (sdm.py:1259-1261)
-        s = __dsqrt_rn(ss != 0.0 ? __ddiv_rn(1.0, ss) : 0.0);
-      }
-      a.out[i0 + tid] = s;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);                // the producer's expect_tx arrive
+      mbar_init(empty0 + 8 * s, NCONS / 32);      // one arrive per consumer warp
     }
-    return;
+    mbar_fence_init();
   }
-
-  tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid);
+  double* Ld = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(smem) + MAIN_BYTES + BAR_BYTES);
+  int* Li = reinterpret_cast<int*>(Ld + BM * KFUSED);
+  if (MODE == MODE_TOPK) {
+    for (int e = tid; e < BM * KFUSED; e += NT) {
+      Ld[e] = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+      Li[e] = 0x7fffffff;
+    }
+  }
   __syncthreads();
-  // rows of the tile -> rows of D (256-byte coalesced warp stores)
-  for (int r = warp; r < BM; r += NT / 32) {
-    const int64_t gi = i0 + r;
-    if (gi < a.row_begin || gi >= a.row_end) continue;
-    double* __restrict__ dst = a.out + (gi - a.row_begin) * a.ldd + j0;
+
+  uint32_t it = 0;  // K slabs streamed so far (same count on both sides)
+  for (J = J0; J < J1; ++J) {
+    const int64_t j0 = J * BN;
+    if (producer) {
+      if (lane == 0) gram_produce(&xmap, base, full0, empty0, KT, i0, j0, it);
+      __syncwarp();
+    } else {
+      double acc[MF][NF][2];
+      gram_consume(acc, smem, full0, empty0, KT, it);
+      consumer_sync();  // every slab is consumed: the epilogue tile may alias the ring
+
+      if (MODE == MODE_DIAG) {
+        tile_to_smem<true>(acc, smem, nullptr, i0, j0, 0);
+        consumer_sync();
+        if (tid < BM) {
+          const double ss = smem[tid * LDT + tid];
+          double sv;
+          if (a.euclid) {
+            sv = ss;  // |x|^2
+          } else {
+            // sqrt(1/ss), 0 for a zero vector (sdm.py:1259-1261)
+            sv = __dsqrt_rn(ss != 0.0 ? __ddiv_rn(1.0, ss) : 0.0);
+          }
+          a.out[i0 + tid] = sv;
+        }
+      } else {
+        tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid);
+        consumer_sync();
+        if (MODE == MODE_TOPK) {
+          // warp w scans rows w, w+8, ...; lane l holds entry l of the row's list
+          const int K = a.K;
+          for (int r = warp; r < BM; r += NCONS / 32) {
+            const int64_t gi = i0 + r;
+            if (gi < a.row_begin || gi >= a.row_end) continue;
+            double ld = Ld[r * KFUSED + lane];
+            int li = Li[r * KFUSED + lane];
+            double td = __shfl_sync(0xffffffffu, ld, K - 1);
+            int tj = __shfl_sync(0xffffffffu, li, K - 1);
+            bool dirty = false;
 #pragma unroll
-    for (int q = 0; q < BN / 32; ++q) {
-      const int c = lane + 32 * q;
-      if (j0 + c < a.n) dst[c] = smem[r * LDT + c];
-    }
-  }
-  if (MODE == MODE_STORE && mirrored) {
-    // mirrored tile: column c of T is row j0+c of D
-    for (int c = warp; c < BN; c += NT / 32) {
-      const int64_t gj = j0 + c;
-      if (gj >= a.n) continue;
-      double* __restrict__ dst = mirror_out + (gj - mirror_begin) * a.ldd + i0;
+            for (int q = 0; q < BN / 32; ++q) {
+              const int c = lane + 32 * q;
+              const int64_t gj = j0 + c;
+              const double v = smem[r * LDT + c];
+              unsigned m = __ballot_sync(0xffffffffu, gj < a.n && before(v, (int)gj, td, tj));
+              while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const double d = __shfl_sync(0xffffffffu, v, src);
+                const int j = (int)(j0 + src + 32 * q);
+                if (before(d, j, td, tj)) {
+                  warp_insert(ld, li, d, j, lane);
+                  td = __shfl_sync(0xffffffffu, ld, K - 1);
+                  tj = __shfl_sync(0xffffffffu, li, K - 1);
+                  dirty = true;
+                }
+              }
+            }
+            if (dirty) {
+              Ld[r * KFUSED + lane] = ld;
+              Li[r * KFUSED + lane] = li;
+            }
+          }
+        } else {
+          // rows of the tile -> rows of D (256-byte coalesced warp stores)
+          for (int r = warp; r < BM; r += NCONS / 32) {
+            const int64_t gi = i0 + r;
+            if (gi < a.row_begin || gi >= a.row_end) continue;
+            double* __restrict__ dst = a.out + (gi - a.row_begin) * a.ldd + j0;
 #pragma unroll
-      for (int q = 0; q < BM / 32; ++q) {
-        const int r = lane + 32 * q;
-        if (i0 + r < a.n) dst[r] = smem[r * LDT + c];
+            for (int q = 0; q < BN / 32; ++q) {
+              const int c = lane + 32 * q;
+              if (j0 + c < a.n) dst[c] = smem[r * LDT + c];
+            }
+          }
+          if (mirrored) {
+            // mirrored tile: column c of T is row j0+c of D
+            for (int c = warp; c < BN; c += NCONS / 32) {
+              const int64_t gj = j0 + c;
+              if (gj >= a.n) continue;
+              double* __restrict__ dst = mirror_out + (gj - mirror_begin) * a.ldd + i0;
+#pragma unroll
+              for (int q = 0; q < BM / 32; ++q) {
+                const int r = lane + 32 * q;
+                if (i0 + r < a.n) dst[r] = smem[r * LDT + c];
+              }
+            }
+          }
+        }
       }
+    }
+    // the next tile's slabs overwrite the epilogue tile: everyone waits
+    if (MODE == MODE_TOPK) __syncthreads();
+  }
+
+  if (MODE == MODE_TOPK) {
+    // partial lists out: part[split][row - row_begin][K]
+    const int K = a.K;
+    const int64_t rows = a.row_end - a.row_begin;
+    for (int e = tid; e < BM * K; e += NT) {
+      const int r = e / K, l = e % K;
+      const int64_t gi = i0 + r;
+      if (gi < a.row_begin || gi >= a.row_end) continue;
+      const int64_t o = ((int64_t)blockIdx.y * rows + (gi - a.row_begin)) * K + l;
+      a.part_d[o] = Ld[r * KFUSED + l];
+      a.part_i[o] = Li[r * KFUSED + l];
     }
   }
 }
 
 template <int MODE>
-int launch(const GramArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
+int launch(const scedar_cells* c, const GramArgs& a, dim3 grid, cudaStream_t s) {
+  const int smem_bytes = SMEM_BASE + (MODE == MODE_TOPK ? LIST_BYTES : 0);
   SCEDAR_CUDA(cudaFuncSetAttribute(gram_f64_kernel<MODE>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   MAIN_BYTES + LIST_BYTES));
-  gram_f64_kernel<MODE><<<grid, NT, smem_bytes, s>>>(a);
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  gram_f64_kernel<MODE><<<grid, NT, smem_bytes, s>>>(c->xmap, a);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
   return SCEDAR_OK;
@@ -386,7 +421,7 @@ int launch_gram_diag(const scedar_cells* c, cudaStream_t s) {
   a.row_begin = 0;
   a.row_end = c->n_pad;
   a.out = c->stat;
-  return launch<MODE_DIAG>(a, dim3((unsigned)(c->n_pad / BM)), MAIN_BYTES, s);
+  return launch<MODE_DIAG>(c, a, dim3((unsigned)(c->n_pad / BM)), s);
 }
 
 int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end,
@@ -401,7 +436,7 @@ int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
   const int64_t tiles = RT * (c->n_pad / BN);
   if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");
-  return launch<MODE_STORE>(a, dim3((unsigned)tiles), MAIN_BYTES, s);
+  return launch<MODE_STORE>(c, a, dim3((unsigned)tiles), s);
 }
 
 int launch_gram_stripe_p2p(const scedar_cells* c, int rank, int world,
@@ -434,7 +469,7 @@ int launch_gram_stripe_p2p(const scedar_cells* c, int rank, int world,
   const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
   const int64_t tiles = RT * (c->n_pad / BN);
   if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");
-  return launch<MODE_STORE>(a, dim3((unsigned)tiles), MAIN_BYTES, s);
+  return launch<MODE_STORE>(c, a, dim3((unsigned)tiles), s);
 }
 
 int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
@@ -467,7 +502,7 @@ int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,
   a.part_d = part_d;
   a.part_i = part_i;
   const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
-  return launch<MODE_TOPK>(a, dim3((unsigned)RT, (unsigned)splits), MAIN_BYTES + LIST_BYTES, s);
+  return launch<MODE_TOPK>(c, a, dim3((unsigned)RT, (unsigned)splits), s);
 }
 
 }  // namespace scedar

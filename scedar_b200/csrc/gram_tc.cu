@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 #include "topk_list.cuh"
 
 namespace scedar {
@@ -73,46 +74,6 @@ struct TcArgs {
   int32_t* part_idx;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a descriptor or protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  const long long t0 = clock64();
-  do {
-    if (clock64() - t0 > 8000000000LL) {
-      printf("scedar gram_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x,
-             threadIdx.x);
-      __trap();
-    }
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
 // K-major operand tile in 128B-swizzled shared memory: rows of 128 bytes,
 // 8-row swizzle atoms 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -184,8 +145,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       mbar_init(tfull0 + 8 * s, 1);
       mbar_init(tempty0 + 8 * s, 128);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -504,33 +464,7 @@ margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
 }
 
 int encode_map(CUtensorMap* m, const __half* ptr, int64_t rows, int64_t cols, int box_rows) {
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  // resolved through the runtime: the library must load (and be inspected) on
-  // machines without a driver, so it cannot link against libcuda
-  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) !=
-            cudaSuccess || !fn)
-      return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-    encode = reinterpret_cast<encode_fn>(fn);
-  }
-  CUresult r = encode(
-      m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " +
-                                     std::to_string((int)r));
-  return SCEDAR_OK;
+  return encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, rows, cols, box_rows, TK);
 }
 
 struct FastMaps {
@@ -550,6 +484,36 @@ int tc_splits(int64_t rows, int64_t n, int64_t min_splits) {
 }
 
 }  // namespace
+
+int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes, const void* ptr,
+                      int64_t rows, int64_t cols, int box_rows, int box_cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  // resolved through the runtime: the library must load (and be inspected) on
+  // machines without a driver, so it cannot link against libcuda
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) !=
+            cudaSuccess || !fn)
+      return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  CUresult r = encode(m, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " +
+                                     std::to_string((int)r));
+  return SCEDAR_OK;
+}
 
 // fast-path working set of a cells handle (created on first use)
 struct FastState {
