@@ -190,6 +190,70 @@ int scedar_num_correct_dist_mat(double* d, int64_t ldd, int64_t n,
                                 int32_t* flags_out, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Consumers directly behind the path: everything below works
+ * on device buffers so the kNN lists / D never round-trip through the host.
+ * ---------------------------------------------------------------------- */
+
+/* kNN lists -> CSR connectivity matrix (s_knn_connectivity_matrix,
+ * sdm.py:934-947: coo_matrix((dist, (source, target))).tocsr()).  idx / dist
+ * are [n, k] (cell i's neighbours in row i); indptr_out [n+1] = i*k,
+ * indices_out / data_out [n*k] with the columns of a row ascending (what
+ * scipy's tocsr() + sum_duplicates() yields) and exact-zero distances stored
+ * as -inf (sdm.py:942).  k <= 128. */
+int scedar_knn_connectivity_csr(const int64_t* idx, const double* dist,
+                                int64_t n, int k, int64_t* indptr_out,
+                                int32_t* indices_out, double* data_out,
+                                void* stream);
+
+/* CSR data -> affinity edge weights of knn_conn_mat_to_aff_graph
+ * (sdm.py:1085-1093): -inf -> 0, then (max(w) - w) * aff_scale. */
+int scedar_knn_affinity(const double* data, int64_t nnz, double aff_scale,
+                        double* weights_out, void* stream);
+
+/* RareSampleDetection on a resident D (scedar/knn/detection.py:81-123).
+ * masked_kth: for rows [row_begin, row_end) of the stripe d (row r = cell
+ * row_begin + r; row stride ldd) that are alive, the value at 0-based `rank`
+ * of the row restricted to the alive columns -- np.sort(curr_dist_mat,
+ * axis=0)[i_k, s] of the shrinking sub-matrix (detection.py:100, 111, 119)
+ * without slicing or sorting; +inf for dead rows.  rank < 128.
+ * alive: uint8 [n_cols]. */
+int scedar_masked_kth(const double* d, int64_t ldd, int64_t n_cols,
+                      int64_t row_begin, int64_t row_end, const uint8_t* alive,
+                      int rank, double* kth_out, void* stream);
+/* One detection iteration (detection.py:63-66, 111-115): alive cells whose
+ * kth[i*ldk] <= cutoff stay alive and get last_kept[i] = iter, the others
+ * die.  *n_kept_out (device uint64) is incremented by the number kept. */
+int scedar_rare_update(const double* kth, int64_t ldk, int64_t n, double cutoff,
+                       int iter, uint8_t* alive, int32_t* last_kept,
+                       unsigned long long* n_kept_out, void* stream);
+/* max over the alive entries of a non-negative strided vector (d_max,
+ * detection.py:45, 101); alive may be NULL.  *max_out: device double,
+ * initialised to 0 by the caller. */
+int scedar_masked_max(const double* v, int64_t ldv, int64_t n,
+                      const uint8_t* alive, double* max_out, void* stream);
+/* ascending indices of the alive cells -> sel_out (capacity >= #alive) */
+int scedar_compact_alive(const uint8_t* alive, int64_t n, int64_t* sel_out,
+                         void* stream);
+/* out[r, :] = x[sel[r], :] (detection.py:71: curr_sdm._x[kept, :]) */
+int scedar_gather_rows(const double* x, int64_t ldx, int64_t p,
+                       const int64_t* sel, int64_t m, double* out, int64_t ldo,
+                       void* stream);
+
+/* One iteration of FeatureImputation._impute_features_runner
+ * (scedar/knn/imputation.py:56-101) with statistic_fun = np.median: for every
+ * cell s and gene f with x_curr[s,f] < min_present_val whose k neighbours
+ * knn[s, :] hold >= n_do_i values >= min_present_val, x_next[s,f] = median of
+ * the k neighbour values and idc[s,f] = iter; every other entry is copied.
+ * Reads x_curr only (the reference edits a copy).  stats_out (device
+ * uint64[2], may be NULL) receives the number of entries and of cells with
+ * idc > 0 after the iteration (imputation.py:105-109).  k <= 200. */
+int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
+                       const int64_t* knn, int k, int n_do_i,
+                       double min_present_val, int iter, double* x_next,
+                       int64_t ldn, int32_t* idc, int64_t ldi,
+                       unsigned long long* stats_out, void* stream);
+
+/* ------------------------------------------------------------------------
  * One-shot forms (prepare + run + free), the signatures SURVEY.md 8b lists.
  * ---------------------------------------------------------------------- */
 int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric,

@@ -53,6 +53,24 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "scedar_num_correct_dist_mat": (c_int, [c_void_p, c_int64, c_int64, c_int,
                                             c_double, c_void_p, c_void_p]),
+    "scedar_knn_connectivity_csr": (c_int, [c_void_p, c_void_p, c_int64, c_int,
+                                            c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
+    "scedar_knn_affinity": (c_int, [c_void_p, c_int64, c_double, c_void_p,
+                                    c_void_p]),
+    "scedar_masked_kth": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                  c_void_p, c_int, c_void_p, c_void_p]),
+    "scedar_rare_update": (c_int, [c_void_p, c_int64, c_int64, c_double, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scedar_masked_max": (c_int, [c_void_p, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p]),
+    "scedar_compact_alive": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "scedar_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p,
+                                   c_int64, c_void_p, c_int64, c_void_p]),
+    "scedar_impute_iter": (c_int, [c_void_p, c_int64, c_int64, c_int64,
+                                   c_void_p, c_int, c_int, c_double, c_int,
+                                   c_void_p, c_int64, c_void_p, c_int64,
+                                   c_void_p, c_void_p]),
     "scedar_pdist_dense": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_int64, c_int64, c_void_p, c_void_p]),
     "scedar_pdist_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64,

@@ -332,6 +332,87 @@ int scedar_num_correct_dist_mat(double* d, int64_t ldd, int64_t n, int has_upper
 }
 
 // ---- one-shot forms --------------------------------------------------------
+int scedar_knn_connectivity_csr(const int64_t* idx, const double* dist, int64_t n, int k,
+                                int64_t* indptr_out, int32_t* indices_out, double* data_out,
+                                void* stream) {
+  if (n < 0 || k < 0) return fail(SCEDAR_ERR_ARG, "n and k must be >= 0");
+  if (!indptr_out) return fail(SCEDAR_ERR_ARG, "indptr_out is NULL");
+  if (n * (int64_t)k > 0 && (!idx || !dist || !indices_out || !data_out))
+    return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_conn_csr(idx, dist, n, k, indptr_out, indices_out, data_out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int scedar_knn_affinity(const double* data, int64_t nnz, double aff_scale, double* weights_out,
+                        void* stream) {
+  if (nnz < 0) return fail(SCEDAR_ERR_ARG, "nnz must be >= 0");
+  if (nnz > 0 && (!data || !weights_out)) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_affinity(data, nnz, aff_scale, weights_out, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_masked_kth(const double* d, int64_t ldd, int64_t n_cols, int64_t row_begin,
+                      int64_t row_end, const uint8_t* alive, int rank, double* kth_out,
+                      void* stream) {
+  if (row_begin < 0 || row_end < row_begin || row_end > n_cols)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n_cols");
+  if (rank < 0) return fail(SCEDAR_ERR_ARG, "rank must be >= 0");
+  if (ldd < n_cols) return fail(SCEDAR_ERR_ARG, "ldd must be >= n_cols");
+  if (row_end == row_begin) return SCEDAR_OK;
+  if (!d || !alive || !kth_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_masked_kth(d, ldd, n_cols, row_begin, row_end, alive, rank, kth_out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int scedar_rare_update(const double* kth, int64_t ldk, int64_t n, double cutoff, int iter,
+                       uint8_t* alive, int32_t* last_kept, unsigned long long* n_kept_out,
+                       void* stream) {
+  if (n < 0 || ldk < 1) return fail(SCEDAR_ERR_ARG, "need n >= 0 and ldk >= 1");
+  if (n == 0) return SCEDAR_OK;
+  if (!kth || !alive || !last_kept || !n_kept_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_rare_update(kth, ldk, n, cutoff, iter, alive, last_kept, n_kept_out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int scedar_masked_max(const double* v, int64_t ldv, int64_t n, const uint8_t* alive,
+                      double* max_out, void* stream) {
+  if (n < 0 || ldv < 1) return fail(SCEDAR_ERR_ARG, "need n >= 0 and ldv >= 1");
+  if (n == 0) return SCEDAR_OK;
+  if (!v || !max_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_masked_max(v, ldv, n, alive, reinterpret_cast<unsigned long long*>(max_out),
+                           static_cast<cudaStream_t>(stream));
+}
+
+int scedar_compact_alive(const uint8_t* alive, int64_t n, int64_t* sel_out, void* stream) {
+  if (n < 0) return fail(SCEDAR_ERR_ARG, "n must be >= 0");
+  if (n == 0) return SCEDAR_OK;
+  if (!alive || !sel_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_compact_alive(alive, n, sel_out, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_gather_rows(const double* x, int64_t ldx, int64_t p, const int64_t* sel, int64_t m,
+                       double* out, int64_t ldo, void* stream) {
+  if (m < 0 || p < 0 || ldx < p || ldo < p)
+    return fail(SCEDAR_ERR_ARG, "need m >= 0, p >= 0, ldx >= p and ldo >= p");
+  if (m == 0 || p == 0) return SCEDAR_OK;
+  if (!x || !sel || !out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_gather_rows(x, ldx, p, sel, m, out, ldo, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
+                       const int64_t* knn, int k, int n_do_i, double min_present_val, int iter,
+                       double* x_next, int64_t ldn, int32_t* idc, int64_t ldi,
+                       unsigned long long* stats_out, void* stream) {
+  if (n < 0 || p < 0 || ldx < p || ldn < p || ldi < p)
+    return fail(SCEDAR_ERR_ARG, "need n >= 0, p >= 0 and row strides >= p");
+  if (k < 1 || k >= n) return fail(SCEDAR_ERR_ARG, "k should be >= 1 and < n_samples");
+  if (n_do_i > k || n_do_i < 1) return fail(SCEDAR_ERR_ARG, "n_do should be <= k and >= 1");
+  if (n == 0 || p == 0) return SCEDAR_OK;
+  if (!x_curr || !knn || !x_next || !idc) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  if (x_curr == x_next) return fail(SCEDAR_ERR_ARG, "x_next must not alias x_curr");
+  return launch_impute_iter(x_curr, ldx, n, p, knn, k, n_do_i, min_present_val, iter, x_next,
+                            ldn, idc, ldi, stats_out, static_cast<cudaStream_t>(stream));
+}
+
 int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric, int precision,
                        int64_t row_begin, int64_t row_end, double* d_out, void* stream) {
   scedar_cells_t* c = nullptr;

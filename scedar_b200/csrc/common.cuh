@@ -122,6 +122,32 @@ int launch_col_sort(const double* d, int64_t ldd, int64_t rows, int64_t n,
                     double* sorted_out, int64_t* argsorted_out,
                     cudaStream_t s);
 
+// consumers.cu (kNN graph, rare-sample detection, imputation)
+int launch_conn_csr(const int64_t* idx, const double* dist, int64_t n, int k,
+                    int64_t* indptr, int32_t* indices, double* data,
+                    cudaStream_t s);
+int launch_affinity(const double* w, int64_t nnz, double aff_scale, double* out,
+                    cudaStream_t s);
+int launch_masked_kth(const double* d, int64_t ldd, int64_t n_cols,
+                      int64_t row_begin, int64_t row_end, const uint8_t* alive,
+                      int rank, double* kth_out, cudaStream_t s);
+int launch_rare_update(const double* kth, int64_t ldk, int64_t n, double cutoff,
+                       int iter, uint8_t* alive, int32_t* last_kept,
+                       unsigned long long* counters, cudaStream_t s);
+int launch_masked_max(const double* v, int64_t ldv, int64_t n,
+                      const uint8_t* alive, unsigned long long* max_bits,
+                      cudaStream_t s);
+int launch_compact_alive(const uint8_t* alive, int64_t n, int64_t* sel,
+                         cudaStream_t s);
+int launch_gather_rows(const double* x, int64_t ldx, int64_t p,
+                       const int64_t* sel, int64_t m, double* out, int64_t ldo,
+                       cudaStream_t s);
+int launch_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
+                       const int64_t* knn, int k, int n_do_i, double min_present,
+                       int iter, double* x_next, int64_t ldn, int32_t* idc,
+                       int64_t ldi, unsigned long long* counters,
+                       cudaStream_t s);
+
 // ncdm.cu
 int launch_ncdm(double* d, int64_t ldd, int64_t n, int has_ub, double ub,
                 int32_t* flags, cudaStream_t s);

@@ -275,3 +275,106 @@ def pdist_stripe_p2p(cells, peers, rank, precision="fp64"):
     _capi.check(_capi.load().scedar_pdist_stripe_p2p(
         cells._h, PRECISION_IDS[precision], rank, peers.world, begins, ptrs,
         peers.n, _stream()))
+
+
+# ---------------------------------------------------------------------------
+# consumers behind the path: kNN graph, rare samples, imputation
+# ---------------------------------------------------------------------------
+def knn_connectivity_csr(idx, dist):
+    """kNN lists [n, k] (device) -> CSR (indptr int64, indices int32, data
+    float64) of ``s_knn_connectivity_matrix`` (sdm.py:934-947)."""
+    _guard()
+    dist = _f64(dist)
+    assert idx.is_cuda and idx.dtype == torch.int64 and idx.shape == dist.shape
+    idx, dist = idx.contiguous(), dist.contiguous()
+    n, k = idx.shape
+    indptr = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    indices = torch.empty(n * k, dtype=torch.int32, device="cuda")
+    data = torch.empty(n * k, dtype=torch.float64, device="cuda")
+    _capi.check(_capi.load().scedar_knn_connectivity_csr(
+        _ptr(idx), _ptr(dist), n, k, _ptr(indptr), _ptr(indices), _ptr(data),
+        _stream()))
+    return indptr, indices, data
+
+
+def knn_affinity(data, aff_scale=1.0):
+    """CSR data -> affinity weights (sdm.py:1085-1093)."""
+    _guard()
+    data = _f64(data).contiguous()
+    out = torch.empty_like(data)
+    _capi.check(_capi.load().scedar_knn_affinity(
+        _ptr(data), data.numel(), float(aff_scale), _ptr(out), _stream()))
+    return out
+
+
+def masked_kth(d, alive, rank, row_begin=0, out=None):
+    """Value at 0-based ``rank`` of every alive row of the stripe ``d``
+    [rows, n] restricted to the alive columns (+inf for dead rows)."""
+    _guard()
+    d = _f64(d)
+    rows, n = d.shape
+    assert alive.is_cuda and alive.dtype == torch.uint8 and alive.numel() == n
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float64, device="cuda")
+    _capi.check(_capi.load().scedar_masked_kth(
+        _ptr(d), d.stride(0) if rows > 1 else n, n, row_begin,
+        row_begin + rows, _ptr(alive), int(rank), _ptr(out), _stream()))
+    return out
+
+
+def rare_update(kth, cutoff, it, alive, last_kept, ldk=1):
+    """One keep / drop decision (detection.py:63-66, 111-115); returns the
+    number of cells kept (one 8-byte device -> host read)."""
+    _guard()
+    n = alive.numel()
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _capi.check(_capi.load().scedar_rare_update(
+        _ptr(kth), int(ldk), n, float(cutoff), int(it), _ptr(alive),
+        _ptr(last_kept), _ptr(counter), _stream()))
+    return int(counter.item())
+
+
+def masked_max(v, alive=None, ldv=1, n=None):
+    """max over the (alive) entries of a non-negative strided vector."""
+    _guard()
+    n = v.numel() // ldv if n is None else n
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _capi.check(_capi.load().scedar_masked_max(
+        _ptr(v), int(ldv), n, _ptr(alive), _ptr(out), _stream()))
+    return float(out.item())
+
+
+def compact_alive(alive, count):
+    """Ascending indices of the alive cells (int64 [count])."""
+    _guard()
+    sel = torch.empty(max(count, 1), dtype=torch.int64, device="cuda")
+    _capi.check(_capi.load().scedar_compact_alive(
+        _ptr(alive), alive.numel(), _ptr(sel), _stream()))
+    return sel[:count]
+
+
+def gather_rows(x, sel):
+    """x[sel, :] on the device."""
+    _guard()
+    x = _f64(x)
+    m, p = sel.numel(), x.shape[1]
+    out = torch.empty((m, p), dtype=torch.float64, device="cuda")
+    _capi.check(_capi.load().scedar_gather_rows(
+        _ptr(x), x.stride(0) if x.shape[0] > 1 else max(p, 1), p, _ptr(sel),
+        m, _ptr(out), max(p, 1), _stream()))
+    return out
+
+
+def impute_iter(x_curr, knn, n_do_i, min_present_val, it, x_next, idc,
+                stats=None):
+    """One imputation iteration (imputation.py:56-101), median statistic."""
+    _guard()
+    x_curr, x_next = _f64(x_curr), _f64(x_next)
+    n, p = x_curr.shape
+    assert knn.is_cuda and knn.dtype == torch.int64 and knn.is_contiguous()
+    assert idc.is_cuda and idc.dtype == torch.int32 and idc.is_contiguous()
+    assert x_curr.is_contiguous() and x_next.is_contiguous()
+    _capi.check(_capi.load().scedar_impute_iter(
+        _ptr(x_curr), max(p, 1), n, p, _ptr(knn), knn.shape[1], int(n_do_i),
+        float(min_present_val), int(it), _ptr(x_next), max(p, 1), _ptr(idc),
+        max(p, 1), _ptr(stats), _stream()))

@@ -125,6 +125,7 @@ class SampleDistanceMatrix(object):
         self._cells_lut = {}
         self._d_dev = None
         self._d_user = d is not None
+        self._knn_dev = None    # (k, exclude, metric, idx, dist) last lists in HBM
 
     # ------------------------------------------------------------------ ids
     @property
@@ -361,11 +362,18 @@ class SampleDistanceMatrix(object):
             # D is not needed (or would not fit): fused Gram -> top-k
             i, dd = self._cells(self._metric).knn_stripe(
                 k, exclude, precision=self.precision)
+            self._knn_dev = (k, exclude, self._metric, i, dd)
             return i.cpu().numpy(), dd.cpu().numpy()
+        parts = []
         for r0, r1, stripe in self._d_stripes():
             i, dd = dev.knn_from_d(stripe, k, exclude, row_begin=r0)
+            parts.append((i, dd))
             idx[r0:r1] = i.cpu().numpy()
             dist[r0:r1] = dd.cpu().numpy()
+        if parts:
+            self._knn_dev = (k, exclude, self._metric,
+                             torch.cat([q[0] for q in parts]),
+                             torch.cat([q[1] for q in parts]))
         return idx, dist
 
     def s_knn_ind_lut(self, k, metric=None, use_pca=False, use_hnsw=False,
@@ -452,6 +460,7 @@ class SampleDistanceMatrix(object):
                     MAX_TOPK))
             i, dd = self._cells(metric).knn_stripe(k, EXCLUDE_SELF,
                                                    precision=self.precision)
+            self._knn_dev = (k, EXCLUDE_SELF, metric, i, dd)
             idx, dist = i.cpu().numpy(), dd.cpu().numpy()
         return list(idx), list(dist)
 
@@ -460,17 +469,51 @@ class SampleDistanceMatrix(object):
                                   query_params=None, verbose=False):
         """sdm.py:872-947: CSR, entry (i, j) = distance when j is one of i's
         kNN; exact-zero distances stored as -inf."""
+        self._knn_dev = None
         targets, distances = self.s_knns(
             k=k, metric=metric, use_pca=use_pca, use_hnsw=use_hnsw,
             index_params=index_params, query_params=query_params,
             verbose=verbose)
         n = self._x.shape[0]
-        sources_1d = np.repeat(np.arange(n), [len(t) for t in targets])
-        targets_1d = np.concatenate(targets, axis=0)
-        distances_1d = np.concatenate(distances, axis=0)
-        distances_1d[distances_1d == 0] = -np.inf
-        return spsparse.coo_matrix((distances_1d, (sources_1d, targets_1d)),
-                                   shape=(n, n)).tocsr()
+        kd = self._knn_dev
+        if kd is not None and kd[0] == k and kd[1] == EXCLUDE_SELF:
+            idx_dev, dist_dev = kd[3], kd[4]       # still resident in HBM
+        else:
+            idx_dev = dev.to_device(np.asarray(targets, dtype=np.int64))
+            dist_dev = dev.to_device(np.asarray(distances, dtype=np.float64))
+        if k > 128:
+            raise NotImplementedError("connectivity matrix with k > 128")
+        indptr, indices, data = dev.knn_connectivity_csr(idx_dev, dist_dev)
+        return spsparse.csr_matrix(
+            (data.cpu().numpy(), indices.cpu().numpy(),
+             indptr.cpu().numpy().astype(np.int32 if n * k < 2 ** 31
+                                         else np.int64)), shape=(n, n))
+
+    @staticmethod
+    def knn_conn_mat_to_aff_edges(knn_conn_mat, aff_scale=1):
+        """The edge list of ``knn_conn_mat_to_aff_graph`` (sdm.py:1085-1093)
+        without igraph: ``(sources, targets, weights)`` with ``-inf -> 0`` and
+        ``weights = (max - weights) * aff_scale``, computed on the device."""
+        m = spsparse.csr_matrix(knn_conn_mat)
+        sources, targets = m.nonzero()
+        data = np.asarray(m[sources, targets]).ravel().astype(np.float64)
+        w = dev.knn_affinity(dev.to_device(data), aff_scale)
+        return sources, targets, w.cpu().numpy()
+
+    @staticmethod
+    def knn_conn_mat_to_aff_graph(knn_conn_mat, aff_scale=1):
+        """sdm.py:1085-1093; needs python-igraph for the Graph object (the
+        edge arithmetic itself is ``knn_conn_mat_to_aff_edges``)."""
+        try:
+            import igraph as ig
+        except ImportError:
+            raise ImportError("python-igraph is required for the Graph "
+                              "object; use knn_conn_mat_to_aff_edges for the "
+                              "edge list")
+        s_, t_, w = SampleDistanceMatrix.knn_conn_mat_to_aff_edges(
+            knn_conn_mat, aff_scale)
+        return ig.Graph(edges=list(zip(s_.tolist(), t_.tolist())),
+                        directed=False, edge_attrs={"weight": w})
 
     # ------------------------------------------------------------- read-only
     @property
@@ -483,4 +526,5 @@ class SampleDistanceMatrix(object):
             c.close()
         self._cells_lut = {}
         self._d_dev = None
+        self._knn_dev = None
         torch.cuda.empty_cache()
