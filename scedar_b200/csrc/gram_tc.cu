@@ -3,17 +3,30 @@
 // 128B-swizzled shared memory, with the metric epilogue and the streaming
 // top-k fused.  Selected by SCEDAR_PRECISION_FAST.
 //
-// Precision scheme ("3xFP16"): every cell is scaled to unit length in float64
-// and split into two halves x = hi + lo (|x - hi - lo| <= 2^-22 |x|); the
-// contraction accumulates hi.hi + hi.lo + lo.hi in FP32, i.e. a product of
-// FP32 quality from three tensor-core passes over the same K slab (the
-// north star's split-precision fast path; FP16 halves rather than BF16 because
-// unit-length rows need mantissa, not range).  Stated tolerance of the fast
-// distance matrix: |D_fast - D_fp64| <= 2e-5 * max(D) (tests assert it; typical
-// 1e-6).  The fast kNN is EXACT: the tensor-core pass only proposes 32
-// candidates per cell, which are re-ranked with float64 distances computed
-// like the FP64 path and verified against the candidate threshold; cells
-// whose margin is too small are recomputed by the FP64 kernel.
+// Precision scheme ("3xFP16"): every operand is split into two halves
+// x = hi + lo (|x - hi - lo| <= 2^-22 |x|); the contraction accumulates
+// hi.hi + hi.lo + lo.hi in FP32, i.e. a product of FP32 quality from three
+// tensor-core passes over the same K slab (the north star's split-precision
+// fast path; FP16 halves rather than BF16 because the operands are scaled into
+// FP16's range and need mantissa, not exponent).
+//
+// Operands.  The row tile (A) and the column tile (B) are different splits of
+// the same cells, so that the accumulator IS the ranking key / the metric:
+//   cosine, correlation   A = u,            B = -u            acc = -cos
+//   euclidean             A = [s x, 1],     B = [-2 s x, s^2|x|^2]
+//                                           acc = s^2 (|x_c|^2 - 2 x_r.x_c)
+// (u = unit-length row, s = a power of two that brings max |x|^2 under 2^15;
+// the extra K column is one of the padding columns of the 64-wide K slab).
+// The epilogue therefore needs no per-column loads: d^2 = acc / s^2 + |x_r|^2,
+// d = 1 + acc, and for the top-k a bare compare of the accumulator against
+// the row's threshold.
+//
+// Stated tolerance of the fast distance matrix: |D_fast - D_fp64| <= 1e-4 *
+// max(D) (tests assert it; typical 1e-6).  The fast kNN is EXACT: the
+// tensor-core pass only proposes candidates (32 per cell and column split),
+// which are re-ranked with float64 distances computed like the FP64 path and
+// verified against the candidate threshold; cells whose margin is too small
+// are recomputed by the FP64 kernel.
 //
 // Structure (one CTA per SM, 192 threads):
 //   warp 0   TMA producer: per K slab 4 boxes (A_hi, A_lo: 128 x 64 halves;
@@ -21,10 +34,15 @@
 //   warp 1   MMA issuer (one elected lane): per slab 4 k-steps x 3 products of
 //            UMMA 128 x 256 x 16 into one of two 256-column TMEM accumulators;
 //            tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp quarter),
-//            metric formula, then either a coalesced float64 store of the D
-//            tile through shared memory, or threshold-gated insertion into
-//            the thread-private candidate list of that row
+//   warps 2-5 epilogue, one thread per tile row, TMEM lane quarter = warp % 4:
+//            STORE  tcgen05.ld 32 columns -> metric in float64 -> coalesced
+//                   store of the D tile through shared memory
+//            TOPK   double-buffered tcgen05.ld of 32 columns; the hot loop is
+//                   one FSETP per candidate (accumulator < row threshold,
+//                   OR-reduced) and one vote per 32 x 32 block; a hit (rare
+//                   once the lists are warm) re-reads its column from TMEM and
+//                   is inserted warp-cooperatively (ballot + shuffle) into the
+//                   row's sorted 32-entry list in shared memory
 // The CTA owns a 128-row tile and a range of 256-column tiles, so per-row
 // candidate lists never leave the SM.
 //
@@ -46,9 +64,9 @@ constexpr int TM = 128, TN = 256, TK = 64;
 constexpr int TSTAGES = 2;
 constexpr int A_BYTES = TM * TK * 2, B_BYTES = TN * TK * 2;
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304
-constexpr int KC = 32;       // candidates kept per row
-constexpr int STG_LD = 33;   // staging / list row stride (conflict-free)
-constexpr int EPI_BYTES = TM * STG_LD * 8;
+constexpr int KC = 32;       // candidates kept per row and column split
+constexpr int STG_LD = 33;   // staging row stride of the STORE epilogue (conflict-free)
+constexpr int EPI_BYTES = TM * STG_LD * 8;   // >= TM * KC * 8 (the TOPK lists)
 constexpr int BAR_BYTES = 128;
 constexpr int TC_SMEM = 1024 + TSTAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
 constexpr int TC_THREADS = 192;
@@ -58,11 +76,11 @@ constexpr int RR_SMEM = RR_WARPS * (32 * RR_LD + RR_CH) * 8;
 constexpr uint32_t IDESC = (1u << 4)                   // accumulator FP32
                            | ((uint32_t)(TN >> 3) << 17)  // N
                            | ((uint32_t)(TM >> 4) << 24); // M; A,B = F16 K-major
+constexpr unsigned FULL = 0xffffffffu;
 
 struct TcArgs {
   const double* stat;   // sqrt(1/|x|^2) or |x|^2 (euclid), float64
-  const float* nrm2f;   // euclid: |x|^2 as float
-  const float* nrmf;    // euclid: |x| as float
+  const double* scale;  // device: [0] = s, [1] = 1/s^2 (both 1 unless euclid)
   int64_t n;
   int kblocks;
   int64_t row_begin, row_end;
@@ -103,7 +121,9 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// 32 lanes x 32 columns -> 32 registers per thread; NOT complete until
+// tmem_wait() has been executed on the same registers
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -115,10 +135,83 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ bool beforef(float k, int j, float tk, int tj) {
-  return k < tk || (k == tk && j < tj);
+// the registers are in/out operands so that no use of them can be scheduled
+// above the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]),
+                 "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]),
+                 "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]),
+                 "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld32_async(taddr, v);
+  tmem_wait(v);
+}
+// one column (dynamic address) of the warp's 32 lanes, complete on return
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(v)
+      : "r"(taddr)
+      : "memory");
+  return v;
+}
+
+// TOPK: one 32-row x 32-column block of accumulators against the per-row
+// thresholds.  Hot path: 32 compares OR-ed into one predicate + one vote.
+__device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t taddr, int64_t jbase,
+                                           int64_t n, float& tau, float* lkey, int* lidx,
+                                           int row0, int lane) {
+  bool any = false;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) any |= __uint_as_float(v[c]) < tau;
+  if (!__any_sync(FULL, any)) return;
+  unsigned hm = 0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) hm |= (__uint_as_float(v[c]) < tau) ? (1u << c) : 0u;
+  unsigned cm = __reduce_or_sync(FULL, hm);   // columns with a hit in some row
+  while (cm) {
+    const int c = __ffs(cm) - 1;
+    cm &= cm - 1;
+    const float key = __uint_as_float(tmem_ld1(taddr + c));
+    const int64_t gj = jbase + c;
+    unsigned m = __ballot_sync(FULL, key < tau && gj < n);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float nk = __shfl_sync(FULL, key, src);
+      const int nj = (int)gj;
+      // warp-cooperative insert into the sorted list of row row0 + src
+      float* lk_row = lkey + (row0 + src) * KC;
+      int* li_row = lidx + (row0 + src) * KC;
+      float lk = lk_row[lane];
+      int li = li_row[lane];
+      const int pos = __popc(__ballot_sync(FULL, lk < nk || (lk == nk && li < nj)));
+      const float pk = __shfl_up_sync(FULL, lk, 1);
+      const int pi = __shfl_up_sync(FULL, li, 1);
+      if (lane > pos) {
+        lk = pk;
+        li = pi;
+      } else if (lane == pos) {
+        lk = nk;
+        li = nj;
+      }
+      if (lane >= pos) {
+        lk_row[lane] = lk;
+        li_row[lane] = li;
+      }
+      const float worst = __shfl_sync(FULL, lk, KC - 1);
+      if (lane == src) tau = worst;
+    }
+  }
 }
 
 template <bool TOPK>
@@ -220,76 +313,72 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int e = (warp - 2) * 32 + lane;   // 0..127 inside the epilogue group
     const int64_t gi = i0 + r;
     const bool row_ok = gi >= a.row_begin && gi < a.row_end;
-    double s_row = 0.0;
-    float n2_row = 0.f, n_row = 0.f;
-    if (gi < a.n) {
-      s_row = a.stat[gi];
-      if (a.euclid) {
-        n2_row = a.nrm2f[gi];
-        n_row = a.nrmf[gi];
-      }
-    }
-    float* lkey = reinterpret_cast<float*>(epi);
-    int* lidx = reinterpret_cast<int*>(epi + TM * STG_LD * 4);
-    double* stg = reinterpret_cast<double*>(epi);
-    float tau = __int_as_float(0x7f800000);
-    int tauj = 0x7fffffff;
-    if (TOPK) {
-      for (int c = 0; c < KC; ++c) {
-        lkey[r * STG_LD + c] = __int_as_float(0x7f800000);
-        lidx[r * STG_LD + c] = 0x7fffffff;
-      }
-    }
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t t = 0;
-    for (int64_t J = J0; J < J1; ++J, ++t) {
-      const uint32_t acc = t & 1, aph = (t >> 1) & 1;
-      mbar_wait(tfull0 + 8 * acc, aph);
-      tc_fence_after();
-      const int64_t j0 = J * TN;
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TN + c0, v);
-        if (TOPK) {
-          if (row_ok) {
+    if (TOPK) {
+      float* lkey = reinterpret_cast<float*>(epi);           // [TM][KC]
+      int* lidx = reinterpret_cast<int*>(epi + TM * KC * 4);  // [TM][KC]
+      for (int rr = 0; rr < 32; ++rr) {
+        lkey[(q * 32 + rr) * KC + lane] = __int_as_float(0x7f800000);
+        lidx[(q * 32 + rr) * KC + lane] = 0x7fffffff;
+      }
+      __syncwarp();
+      // rows outside the stripe never hit
+      float tau = row_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+      for (int64_t J = J0; J < J1; ++J, ++t) {
+        const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+        mbar_wait(tfull0 + 8 * acc, aph);
+        tc_fence_after();
+        const int64_t j0 = J * TN;
+        const uint32_t tile = lane_base + acc * TN;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tile, v0);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int64_t gj = j0 + c0 + c;
-              if (gj >= a.n) break;
-              const float pv = __uint_as_float(v[c]);
-              float key;
-              if (a.euclid)
-                key = fmaf(-2.f * n_row * __ldg(a.nrmf + gj), pv, n2_row + __ldg(a.nrm2f + gj));
-              else
-                key = -pv;
-              if (beforef(key, (int)gj, tau, tauj)) {
-                int pos = KC - 1;
-                while (pos > 0 && beforef(key, (int)gj, lkey[r * STG_LD + pos - 1],
-                                          lidx[r * STG_LD + pos - 1])) {
-                  lkey[r * STG_LD + pos] = lkey[r * STG_LD + pos - 1];
-                  lidx[r * STG_LD + pos] = lidx[r * STG_LD + pos - 1];
-                  --pos;
-                }
-                lkey[r * STG_LD + pos] = key;
-                lidx[r * STG_LD + pos] = (int)gj;
-                tau = lkey[r * STG_LD + KC - 1];
-                tauj = lidx[r * STG_LD + KC - 1];
-              }
-            }
-          }
-        } else {
-          // metric in float64 from the FP32 similarity, staged for coalescing
+        for (int ch = 0; ch < TN / 32; ch += 2) {
+          tmem_ld32_async(tile + (ch + 1) * 32, v1);
+          scan_block(v0, tile + ch * 32, j0 + ch * 32, a.n, tau, lkey, lidx, q * 32, lane);
+          tmem_wait(v1);
+          if (ch + 2 < TN / 32) tmem_ld32_async(tile + (ch + 2) * 32, v0);
+          scan_block(v1, tile + (ch + 1) * 32, j0 + (ch + 1) * 32, a.n, tau, lkey, lidx, q * 32,
+                     lane);
+          if (ch + 2 < TN / 32) tmem_wait(v0);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * acc);
+      }
+      __syncwarp();
+      const int64_t rows = a.row_end - a.row_begin;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int64_t g2 = i0 + q * 32 + rr;
+        if (g2 < a.row_begin || g2 >= a.row_end) continue;
+        const int64_t o = ((int64_t)split * rows + (g2 - a.row_begin)) * KC;
+        a.part_key[o + lane] = lkey[(q * 32 + rr) * KC + lane];
+        a.part_idx[o + lane] = lidx[(q * 32 + rr) * KC + lane];
+      }
+    } else {
+      double* stg = reinterpret_cast<double*>(epi);
+      const double inv_s2 = a.scale[1];
+      const double n2_row = (a.euclid && gi < a.n) ? a.stat[gi] : 0.0;
+      for (int64_t J = J0; J < J1; ++J, ++t) {
+        const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+        mbar_wait(tfull0 + 8 * acc, aph);
+        tc_fence_after();
+        const int64_t j0 = J * TN;
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + acc * TN + c0, v);
+          // metric in float64 from the FP32 accumulator, staged for coalescing
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const int64_t gj = j0 + c0 + c;
             const double pv = (double)__uint_as_float(v[c]);
             double d;
             if (a.euclid) {
-              const double s_col = gj < a.n ? a.stat[gj] : 0.0;
-              double t2 = s_row + s_col - 2.0 * sqrt(s_row * s_col) * pv;
+              double t2 = fma(pv, inv_s2, n2_row);
               t2 = t2 < 0.0 ? 0.0 : t2;
               d = sqrt(t2);
             } else {
-              d = 1.0 - pv;
+              d = 1.0 + pv;
               d = d < 0.0 ? 0.0 : d;
             }
             stg[r * STG_LD + c] = gi == gj ? 0.0 : d;
@@ -303,16 +392,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);
-    }
-    if (TOPK && row_ok) {
-      const int64_t rows = a.row_end - a.row_begin;
-      const int64_t o = ((int64_t)split * rows + (gi - a.row_begin)) * KC;
-      for (int c = 0; c < KC; ++c) {
-        a.part_key[o + c] = lkey[r * STG_LD + c];
-        a.part_idx[o + c] = lidx[r * STG_LD + c];
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * acc);
       }
     }
   }
@@ -324,42 +405,86 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   }
 }
 
-// unit-length rows split into FP16 hi/lo: xh, xl [n256, p64]
-__global__ void __launch_bounds__(256)
-split_kernel(const double* __restrict__ xw, const double* __restrict__ stat, int64_t n_pad,
-             int64_t p_pad, int64_t n256, int64_t p64, int euclid, __half* __restrict__ xh,
-             __half* __restrict__ xl, float* __restrict__ nrm2f, float* __restrict__ nrmf) {
-  const int64_t row = blockIdx.x;
-  double scale = 0.0;
-  if (row < n_pad) {
-    const double s = stat[row];
-    scale = euclid ? (s > 0.0 ? 1.0 / sqrt(s) : 0.0) : s;
-    if (threadIdx.x == 0 && euclid) {
-      nrm2f[row] = (float)s;
-      nrmf[row] = (float)sqrt(s);
+// euclid: s = 2^h with max |x|^2 s^2 < 2^15 (FP16 holds the norm column and
+// every element); scale[0] = s, scale[1] = 1 / s^2.  One block.
+__global__ void __launch_bounds__(1024)
+fast_scale_kernel(const double* __restrict__ stat, int64_t n, int euclid,
+                  double* __restrict__ scale) {
+  __shared__ double part[32];
+  double m = 0.0;
+  if (euclid)
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, stat[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) m = fmax(m, part[w]);
+    int h = 0;
+    if (euclid && m > 0.0 && m < 1e300) {
+      int ex;
+      frexp(m, &ex);  // m < 2^ex
+      const int room = 15 - ex;
+      h = room >= 0 ? room / 2 : -((-room + 1) / 2);
     }
-  } else if (threadIdx.x == 0 && euclid) {
-    nrm2f[row] = 0.f;
-    nrmf[row] = 0.f;
-  }
-  for (int64_t c = threadIdx.x; c < p64; c += blockDim.x) {
-    double v = 0.0;
-    if (row < n_pad && c < p_pad) v = xw[row * p_pad + c] * scale;
-    const __half h = __double2half(v);
-    const __half l = __double2half(v - (double)__half2float(h));
-    xh[row * p64 + c] = h;
-    xl[row * p64 + c] = l;
+    scale[0] = ldexp(1.0, h);
+    scale[1] = ldexp(1.0, -2 * h);
   }
 }
 
-// merge the per-split candidate lists of a row, recompute the candidates'
-// distances in float64 (same accumulation order and epilogue as the FP64
-// Gram kernel), sort, emit k, and record what the margin check needs
+__device__ __forceinline__ void split_half(double v, __half& h, __half& l) {
+  h = __double2half(v);
+  l = __double2half(v - (double)__half2float(h));
+}
+
+// the A- and B-role splits of every cell: ah, al, bh, bl [n256, p64]
+__global__ void __launch_bounds__(256)
+split_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
+             const double* __restrict__ scale, int64_t n, int64_t p, int64_t p_pad,
+             int64_t p64, int euclid, __half* __restrict__ ah, __half* __restrict__ al,
+             __half* __restrict__ bh, __half* __restrict__ bl) {
+  const int64_t row = blockIdx.x;
+  const bool real = row < n;
+  double mul = 0.0, n2s = 0.0;
+  if (real) {
+    if (euclid) {
+      mul = scale[0];
+      n2s = stat[row] * scale[0] * scale[0];
+    } else {
+      mul = stat[row];   // sqrt(1/|x|^2): unit length (0 for a zero vector)
+    }
+  }
+  const double bmul = euclid ? -2.0 : -1.0;
+  for (int64_t c = threadIdx.x; c < p64; c += blockDim.x) {
+    double va = 0.0, vb = 0.0;
+    if (real && c < p) {
+      va = xw[row * p_pad + c] * mul;
+      vb = va * bmul;
+    } else if (real && euclid && c == p) {   // the augmented K column
+      va = 1.0;
+      vb = n2s;
+    }
+    __half h, l;
+    split_half(va, h, l);
+    ah[row * p64 + c] = h;
+    al[row * p64 + c] = l;
+    split_half(vb, h, l);
+    bh[row * p64 + c] = h;
+    bl[row * p64 + c] = l;
+  }
+}
+
+// Merge the per-split candidate lists of a row (top 32*R by approximate key),
+// recompute the candidates' distances in float64 (same accumulation order and
+// epilogue as the FP64 Gram kernel), sort, emit k, and record what the margin
+// check needs.  Error and margin live in the space where the approximate key
+// is linear: squared distance for euclidean, distance otherwise.
+template <int R>
 __global__ void __launch_bounds__(32 * RR_WARPS)
-rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat, int64_t n,
-              int64_t p_pad, int euclid, const float* __restrict__ part_key,
-              const int32_t* __restrict__ part_idx, int splits, int64_t rows, int64_t row_begin,
-              int k, int exclude, int64_t* __restrict__ idx_out, double* __restrict__ dist_out,
+rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
+              const double* __restrict__ scale, int64_t n, int64_t p_pad, int euclid,
+              const float* __restrict__ part_key, const int32_t* __restrict__ part_idx,
+              int splits, int64_t rows, int64_t row_begin, int k, int exclude,
+              int64_t* __restrict__ idx_out, double* __restrict__ dist_out,
               unsigned int* __restrict__ err_bits, double* __restrict__ tau_out,
               double* __restrict__ dk_out) {
   const int lane = threadIdx.x & 31;
@@ -367,19 +492,33 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat, in
   if (row >= rows) return;
   const int K = k + 1;
   const int64_t gi = row_begin + row;
-  // top-KC approximate candidates over all splits (order: key, index)
-  WarpList<1> L;
+  const double inv_s2 = scale[1];
+  const double si = stat[gi];
+  // every cell outside the union of the split lists has a key >= the last
+  // entry of its split's (full) list
+  WarpList<R> L;
   L.init();
+  double t1 = pos_inf();
   for (int s = 0; s < splits; ++s) {
     const int64_t o = ((int64_t)s * rows + row) * KC;
     const float kf = part_key[o + lane];
     const int j = part_idx[o + lane];
-    L.offer((double)kf, j, j != 0x7fffffff, KC, lane);
+    const double last = __shfl_sync(FULL, (double)kf, KC - 1);
+    const int last_j = __shfl_sync(FULL, j, KC - 1);
+    if (last_j != 0x7fffffff) t1 = fmin(t1, last);
+    L.offer((double)kf, j, j != 0x7fffffff, 32 * R, lane);
   }
-  const int j = L.i[0];
-  const bool valid = j != 0x7fffffff;
-  const double approx = euclid ? sqrt(L.d[0] < 0.0 ? 0.0 : L.d[0]) : 1.0 + L.d[0];
-  // exact distance of my candidate: the warp streams the 32 candidate rows
+  // ... and every listed cell that is not re-ranked has a key >= the last
+  // entry of the merged list
+  {
+    const double last = __shfl_sync(FULL, L.d[R - 1], 31);
+    const int last_j = __shfl_sync(FULL, L.i[R - 1], 31);
+    if (last_j != 0x7fffffff) t1 = fmin(t1, last);
+  }
+  auto to_metric = [&](double key) {   // approximate key -> margin space
+    return euclid ? fma(key, inv_s2, si) : 1.0 + key;
+  };
+  // exact distance of my candidates: the warp streams 32 candidate rows
   // through shared memory in 64-gene chunks (coalesced 512-byte row segments),
   // then every lane walks its own row in gene order with one FMA chain -- the
   // accumulation order of the FP64 Gram kernel
@@ -387,63 +526,97 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat, in
   double* buf = rr_smem + (threadIdx.x >> 5) * (32 * RR_LD + RR_CH);
   double* xs = buf + 32 * RR_LD;
   const double* __restrict__ xi = xw + gi * p_pad;
-  double acc = 0.0;
-  for (int64_t c0 = 0; c0 < p_pad; c0 += RR_CH) {
-    const int64_t left = p_pad - c0;
-    const bool in = 2 * lane < left;          // p_pad is a multiple of 16
+  double dist[R], lin[R];
+  float err = 0.f;
+#pragma unroll
+  for (int rg = 0; rg < R; ++rg) {
+    const int j = L.i[rg];
+    const bool valid = j != 0x7fffffff;
+    double acc = 0.0;
+    for (int64_t c0 = 0; c0 < p_pad; c0 += RR_CH) {
+      const int64_t left = p_pad - c0;
+      const bool in = 2 * lane < left;          // p_pad is a multiple of 16
 #pragma unroll 8
-    for (int m = 0; m < 32; ++m) {
-      const int jm = __shfl_sync(0xffffffffu, j, m);
-      double2 w = make_double2(0.0, 0.0);
-      if (jm != 0x7fffffff && in)
-        w = *reinterpret_cast<const double2*>(xw + (int64_t)jm * p_pad + c0 + 2 * lane);
-      buf[m * RR_LD + 2 * lane] = w.x;
-      buf[m * RR_LD + 2 * lane + 1] = w.y;
+      for (int m = 0; m < 32; ++m) {
+        const int jm = __shfl_sync(FULL, j, m);
+        double2 w = make_double2(0.0, 0.0);
+        if (jm != 0x7fffffff && in)
+          w = *reinterpret_cast<const double2*>(xw + (int64_t)jm * p_pad + c0 + 2 * lane);
+        buf[m * RR_LD + 2 * lane] = w.x;
+        buf[m * RR_LD + 2 * lane + 1] = w.y;
+      }
+      if (rg == 0 || p_pad > RR_CH) {
+        double2 u = make_double2(0.0, 0.0);
+        if (in) u = *reinterpret_cast<const double2*>(xi + c0 + 2 * lane);
+        xs[2 * lane] = u.x;
+        xs[2 * lane + 1] = u.y;
+      }
+      __syncwarp();
+      const int lim = left < RR_CH ? (int)left : RR_CH;
+      for (int c = 0; c < lim; ++c) acc = fma(xs[c], buf[lane * RR_LD + c], acc);
+      __syncwarp();
     }
-    {
-      double2 u = make_double2(0.0, 0.0);
-      if (in) u = *reinterpret_cast<const double2*>(xi + c0 + 2 * lane);
-      xs[2 * lane] = u.x;
-      xs[2 * lane + 1] = u.y;
+    dist[rg] = pos_inf();
+    lin[rg] = pos_inf();
+    if (valid) {
+      const bool lower = gi >= j;
+      const double sj = stat[j];
+      const double s_hi = lower ? si : sj, s_lo = lower ? sj : si;
+      dist[rg] = finish_entry(acc, s_hi, s_lo, gi == j, euclid);
+      if (euclid) {
+        double t2 = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, acc), s_hi), s_lo);
+        lin[rg] = gi == j ? 0.0 : (t2 < 0.0 ? 0.0 : t2);
+      } else {
+        lin[rg] = dist[rg];
+      }
+      // observed approximation error (feeds the global margin); the forced
+      // zero of the diagonal is not an approximation error
+      if (gi != j) err = fmaxf(err, (float)fabs(to_metric(L.d[rg]) - lin[rg]));
     }
-    __syncwarp();
-    const int lim = left < RR_CH ? (int)left : RR_CH;
-    for (int c = 0; c < lim; ++c) acc = fma(xs[c], buf[lane * RR_LD + c], acc);
-    __syncwarp();
   }
-  double dist = pos_inf();
-  if (valid) {
-    const bool lower = gi >= j;
-    const double si = stat[gi], sj = stat[j];
-    dist = finish_entry(acc, lower ? si : sj, lower ? sj : si, gi == j, euclid);
-  }
-  // observed approximation error (feeds the global margin)
-  float err = valid ? (float)fabs(approx - dist) : 0.f;
-  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
-  if (lane == 0) atomicMax(err_bits, __float_as_uint(err));
-  // threshold of the candidate set: the largest approximate distance kept
-  const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
-  const double tau = __shfl_sync(0xffffffffu, approx, n_valid > 0 ? n_valid - 1 : 0);
+  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(FULL, err, o));
+  if (lane == 0) atomicMax(err_bits, __float_as_uint(err * (1.f + 1e-6f)));
   // rank by (exact distance, index)
-  int rank = 0;
-  for (int m = 0; m < 32; ++m) {
-    const double dm = __shfl_sync(0xffffffffu, dist, m);
-    const int jm = __shfl_sync(0xffffffffu, j, m);
-    if (m != lane && before(dm, jm, dist, j)) ++rank;
+  int rank[R];
+#pragma unroll
+  for (int rg = 0; rg < R; ++rg) rank[rg] = 0;
+#pragma unroll
+  for (int sg = 0; sg < R; ++sg) {
+    for (int m = 0; m < 32; ++m) {
+      const double dm = __shfl_sync(FULL, dist[sg], m);
+      const int jm = __shfl_sync(FULL, L.i[sg], m);
+#pragma unroll
+      for (int rg = 0; rg < R; ++rg)
+        if (!(sg == rg && m == lane) && before(dm, jm, dist[rg], L.i[rg])) ++rank[rg];
+    }
   }
-  int src = 0;
-  for (int m = 0; m < 32; ++m) {
-    const int rm = __shfl_sync(0xffffffffu, rank, m);
-    if (rm == lane) src = m;
+  // scatter through shared memory into sorted order (entry e -> lane e%32, reg e/32)
+  __syncwarp();
+  int* sidx = reinterpret_cast<int*>(buf + 32 * R);
+#pragma unroll
+  for (int rg = 0; rg < R; ++rg) {
+    buf[rank[rg]] = dist[rg];
+    buf[32 * R + 32 * R + rank[rg]] = lin[rg];
+    sidx[rank[rg]] = L.i[rg];
   }
-  WarpList<1> S;
-  S.d[0] = __shfl_sync(0xffffffffu, dist, src);
-  S.i[0] = __shfl_sync(0xffffffffu, j, src);
+  __syncwarp();
+  WarpList<R> S;
+  double slin[R];
+#pragma unroll
+  for (int rg = 0; rg < R; ++rg) {
+    S.d[rg] = buf[rg * 32 + lane];
+    S.i[rg] = sidx[rg * 32 + lane];
+    slin[rg] = buf[32 * R + 32 * R + rg * 32 + lane];
+  }
   S.emit(K, exclude, (int)gi, idx_out + row * k, dist_out + row * k, lane);
-  const double dk = __shfl_sync(0xffffffffu, S.d[0], K - 1);
+  double dk = 0.0;
+#pragma unroll
+  for (int rg = 0; rg < R; ++rg) {
+    const double x = __shfl_sync(FULL, slin[rg], (K - 1) & 31);
+    if (rg == (K - 1) >> 5) dk = x;
+  }
   if (lane == 0) {
-    // all cells were candidates -> nothing can be missing
-    tau_out[row] = n_valid >= n ? pos_inf() : tau;
+    tau_out[row] = t1 == pos_inf() ? pos_inf() : to_metric(t1);
     dk_out[row] = dk;
   }
 }
@@ -454,10 +627,12 @@ margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
               unsigned char* __restrict__ tile_flag, int* __restrict__ n_flagged) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  // a cell outside the candidate set has approximate distance >= tau, hence
-  // exact distance >= tau - eps; it cannot enter the top k+1 if dk < tau - eps
-  const double eps = 8.0 * (double)__uint_as_float(*err_bits) + 1e-12;
-  if (!(dk[row] + eps < tau[row])) {
+  // a cell that was not re-ranked has approximate metric >= tau, hence exact
+  // metric >= tau - eps; it cannot enter the top k+1 if dk < tau - eps (the
+  // relative term keeps two squared distances that pass apart after sqrt)
+  const double d = dk[row];
+  const double eps = 8.0 * (double)__uint_as_float(*err_bits) + 1e-12 * (d > 1.0 ? d : 1.0);
+  if (!(d + eps < tau[row])) {
     tile_flag[(row_begin + row) / 128 - row_begin / 128] = 1;
     atomicAdd(n_flagged, 1);
   }
@@ -517,10 +692,11 @@ int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes,
 
 // fast-path working set of a cells handle (created on first use)
 struct FastState {
-  __half* xh = nullptr;
-  __half* xl = nullptr;
-  float* nrm2f = nullptr;
-  float* nrmf = nullptr;
+  __half* ah = nullptr;   // A role, hi / lo halves: [n256, p64]
+  __half* al = nullptr;
+  __half* bh = nullptr;   // B role
+  __half* bl = nullptr;
+  double* scale = nullptr;  // [2] on the device: s, 1/s^2
   int64_t n256 = 0, p64 = 0;
   FastMaps maps;
 };
@@ -528,10 +704,11 @@ struct FastState {
 void fast_state_free(void* p, cudaStream_t s) {
   FastState* f = static_cast<FastState*>(p);
   if (!f) return;
-  if (f->xh) cudaFreeAsync(f->xh, s);
-  if (f->xl) cudaFreeAsync(f->xl, s);
-  if (f->nrm2f) cudaFreeAsync(f->nrm2f, s);
-  if (f->nrmf) cudaFreeAsync(f->nrmf, s);
+  if (f->ah) cudaFreeAsync(f->ah, s);
+  if (f->al) cudaFreeAsync(f->al, s);
+  if (f->bh) cudaFreeAsync(f->bh, s);
+  if (f->bl) cudaFreeAsync(f->bl, s);
+  if (f->scale) cudaFreeAsync(f->scale, s);
   delete f;
 }
 
@@ -541,29 +718,33 @@ static int ensure_fast(const scedar_cells* c, cudaStream_t s, FastState** out) {
     *out = static_cast<FastState*>(mc->fast);
     return SCEDAR_OK;
   }
+  const int euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
   FastState* f = new FastState();
   f->n256 = round_up(c->n_pad, 256);
-  f->p64 = round_up(c->p_pad, TK);
+  // euclidean needs one spare K column for the norm term
+  f->p64 = round_up(c->p + (euclid ? 1 : 0), TK);
+  if (f->p64 < TK) f->p64 = TK;
   const size_t hb = sizeof(__half) * f->n256 * f->p64;
-  cudaError_t e = cudaMallocAsync(&f->xh, hb, s);
-  if (e == cudaSuccess) e = cudaMallocAsync(&f->xl, hb, s);
-  if (e == cudaSuccess) e = cudaMallocAsync(&f->nrm2f, sizeof(float) * f->n256, s);
-  if (e == cudaSuccess) e = cudaMallocAsync(&f->nrmf, sizeof(float) * f->n256, s);
+  cudaError_t e = cudaMallocAsync(&f->ah, hb, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->al, hb, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->bh, hb, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->bl, hb, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->scale, 2 * sizeof(double), s);
   if (e != cudaSuccess) {
     cudaGetLastError();
     fast_state_free(f, s);
     return fail(SCEDAR_ERR_NOMEM, std::string("fast-path buffers: ") + cudaGetErrorString(e));
   }
-  const int euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
-  split_kernel<<<(unsigned)f->n256, 256, 0, s>>>(c->xw, c->stat, c->n_pad, c->p_pad, f->n256,
-                                                 f->p64, euclid, f->xh, f->xl, f->nrm2f, f->nrmf);
-  count_launch();
+  fast_scale_kernel<<<1, 1024, 0, s>>>(c->stat, c->n, euclid, f->scale);
+  split_kernel<<<(unsigned)f->n256, 256, 0, s>>>(c->xw, c->stat, f->scale, c->n, c->p, c->p_pad,
+                                                 f->p64, euclid, f->ah, f->al, f->bh, f->bl);
+  count_launch(2);
   int rc = SCEDAR_OK;
   if (cudaGetLastError() != cudaSuccess) rc = fail(SCEDAR_ERR_CUDA, "split kernel launch failed");
-  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_hi, f->xh, f->n256, f->p64, TM);
-  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_lo, f->xl, f->n256, f->p64, TM);
-  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_hi, f->xh, f->n256, f->p64, TN);
-  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_lo, f->xl, f->n256, f->p64, TN);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_hi, f->ah, f->n256, f->p64, TM);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_lo, f->al, f->n256, f->p64, TM);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_hi, f->bh, f->n256, f->p64, TN);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_lo, f->bl, f->n256, f->p64, TN);
   if (rc != SCEDAR_OK) {
     fast_state_free(f, s);
     return rc;
@@ -577,8 +758,7 @@ static TcArgs tc_args(const scedar_cells* c, const FastState* f, int64_t row_beg
                       int64_t row_end) {
   TcArgs a{};
   a.stat = c->stat;
-  a.nrm2f = f->nrm2f;
-  a.nrmf = f->nrmf;
+  a.scale = f->scale;
   a.n = c->n;
   a.kblocks = (int)(f->p64 / TK);
   a.row_begin = row_begin;
@@ -607,7 +787,8 @@ int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   return SCEDAR_OK;
 }
 
-int fast_knn_max_k() { return KC - 9; }  // k + 1 + 8 spare candidates <= 32
+// k + 1 + 8 spare candidates must be re-ranked: up to 64 per cell
+int fast_knn_max_k() { return 2 * KC - 9; }
 
 int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin,
                     int64_t row_end, int64_t* idx_out, double* dist_out, cudaStream_t s) {
@@ -616,7 +797,10 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   FastState* f = nullptr;
   SCEDAR_CHECK(ensure_fast(c, s, &f));
   TcArgs a = tc_args(c, f, row_begin, row_end);
-  a.splits = tc_splits(rows, c->n, 1);
+  // lists hold 32 candidates per split: k + 1 + 8 <= 32 is served by any
+  // number of splits, larger k re-ranks 64 drawn from >= 4 splits
+  const bool wide = k + 1 + 8 > KC;
+  a.splits = tc_splits(rows, c->n, wide ? 4 : 1);
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   Scratch pk, pi, tau, dk, misc, flags;
   SCEDAR_CHECK(pk.alloc(sizeof(float) * a.splits * rows * KC, s));
@@ -636,11 +820,22 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   SCEDAR_CUDA(cudaGetLastError());
   unsigned int* err_bits = misc.as<unsigned int>();
   int* n_flagged = reinterpret_cast<int*>(misc.as<unsigned int>() + 1);
-  SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   RR_SMEM));
-  rerank_kernel<<<(unsigned)((rows + RR_WARPS - 1) / RR_WARPS), 32 * RR_WARPS, RR_SMEM, s>>>(
-      c->xw, c->stat, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits, rows, row_begin,
-      k, exclude, idx_out, dist_out, err_bits, tau.as<double>(), dk.as<double>());
+  const unsigned rr_grid = (unsigned)((rows + RR_WARPS - 1) / RR_WARPS);
+  if (wide) {
+    SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
+    rerank_kernel<2><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
+        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits,
+        rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
+        dk.as<double>());
+  } else {
+    SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
+    rerank_kernel<1><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
+        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits,
+        rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
+        dk.as<double>());
+  }
   margin_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
       tau.as<double>(), dk.as<double>(), err_bits, rows, row_begin, flags.as<unsigned char>(),
       n_flagged);
