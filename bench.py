@@ -349,7 +349,7 @@ def run_b200(a):
         return fi, fd
 
     fast = None
-    if k <= 23:
+    if k <= 55:
         for _ in range(a.warmup):
             fast_step()
         sync_all()

@@ -29,7 +29,7 @@ DEVICE_D_CACHE_BYTES = 48 << 30
 # stripe size used when D is streamed to the host in pieces
 STRIPE_BYTES = 2 << 30
 MAX_TOPK = 127
-FAST_MAX_K = 23     # tensor-core candidate lists hold 32 entries
+FAST_MAX_K = 55     # the tensor-core pass re-ranks up to 64 candidates
 
 
 def _check_is_valid_sfids(sfids):

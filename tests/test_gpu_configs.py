@@ -120,6 +120,11 @@ def test_config5_streaming_topk_1m_x_50(b200):
     x = synth.pcs(n, p, seed=1000000)
     cells = dev.Cells.from_dense(dev.to_device(x), "euclidean")
     idx_t, dist_t = cells.knn_stripe(k, EXCLUDE_SELF)
+    # tcgen05 candidates + FP64 re-rank (64 candidates per cell at k=30):
+    # the same lists bit for bit
+    fi, fd = cells.knn_stripe(k, EXCLUDE_SELF, precision="fast")
+    assert torch.equal(fi, idx_t) and torch.equal(fd, dist_t)
+    del fi, fd
     idx, dist = idx_t.cpu().numpy(), dist_t.cpu().numpy()
     cells.close()
     assert idx.shape == (n, k) and idx.min() >= 0 and idx.max() < n

@@ -450,8 +450,11 @@ def test_fast_path_tcgen05(b200, metric):
         assert torch.equal(dfast.diagonal(), torch.zeros_like(dfast.diagonal()))
         part = cells.pdist_stripe(200, 555, precision="fast")
         assert torch.equal(part, dfast[200:555])
+        # k + 9 <= 32: one 32-candidate list per cell; larger k re-ranks 64
+        # candidates drawn from >= 4 column splits (k <= 55)
         for k, ex in ((15, EXCLUDE_FIRST), (15, EXCLUDE_SELF), (1, EXCLUDE_SELF),
-                      (23, EXCLUDE_FIRST)):
+                      (23, EXCLUDE_FIRST), (24, EXCLUDE_SELF), (30, EXCLUDE_SELF),
+                      (47, EXCLUDE_FIRST), (55, EXCLUDE_SELF)):
             i64, v64 = cells.knn_stripe(k, ex)
             ifa, vfa = cells.knn_stripe(k, ex, precision="fast")
             assert torch.equal(i64, ifa), (metric, n, p, k, ex)
