@@ -246,11 +246,15 @@ int scedar_gather_rows(const double* x, int64_t ldx, int64_t p,
  * the k neighbour values and idc[s,f] = iter; every other entry is copied.
  * Reads x_curr only (the reference edits a copy).  stats_out (device
  * uint64[2], may be NULL) receives the number of entries and of cells with
- * idc > 0 after the iteration (imputation.py:105-109).  k <= 200. */
+ * idc > 0 after the iteration (imputation.py:105-109).  k <= 200.
+ * Only the cells [row_begin, row_end) are processed (a rank's row stripe; the
+ * whole matrix is 0, n): x_curr, x_next, knn and idc are the full [n, .]
+ * buffers, rows outside the range are neither written nor counted. */
 int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        const int64_t* knn, int k, int n_do_i,
-                       double min_present_val, int iter, double* x_next,
-                       int64_t ldn, int32_t* idc, int64_t ldi,
+                       double min_present_val, int iter, int64_t row_begin,
+                       int64_t row_end, double* x_next, int64_t ldn,
+                       int32_t* idc, int64_t ldi,
                        unsigned long long* stats_out, void* stream);
 
 /* ------------------------------------------------------------------------

@@ -69,8 +69,8 @@ SIGNATURES = {
                                    c_int64, c_void_p, c_int64, c_void_p]),
     "scedar_impute_iter": (c_int, [c_void_p, c_int64, c_int64, c_int64,
                                    c_void_p, c_int, c_int, c_double, c_int,
-                                   c_void_p, c_int64, c_void_p, c_int64,
-                                   c_void_p, c_void_p]),
+                                   c_int64, c_int64, c_void_p, c_int64,
+                                   c_void_p, c_int64, c_void_p, c_void_p]),
     "scedar_pdist_dense": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_int64, c_int64, c_void_p, c_void_p]),
     "scedar_pdist_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64,

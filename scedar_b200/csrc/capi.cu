@@ -400,8 +400,10 @@ int scedar_gather_rows(const double* x, int64_t ldx, int64_t p, const int64_t* s
 
 int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        const int64_t* knn, int k, int n_do_i, double min_present_val, int iter,
-                       double* x_next, int64_t ldn, int32_t* idc, int64_t ldi,
-                       unsigned long long* stats_out, void* stream) {
+                       int64_t row_begin, int64_t row_end, double* x_next, int64_t ldn,
+                       int32_t* idc, int64_t ldi, unsigned long long* stats_out, void* stream) {
+  if (row_begin < 0 || row_end < row_begin || row_end > n)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n");
   if (n < 0 || p < 0 || ldx < p || ldn < p || ldi < p)
     return fail(SCEDAR_ERR_ARG, "need n >= 0, p >= 0 and row strides >= p");
   if (k < 1 || k >= n) return fail(SCEDAR_ERR_ARG, "k should be >= 1 and < n_samples");
@@ -409,8 +411,9 @@ int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
   if (n == 0 || p == 0) return SCEDAR_OK;
   if (!x_curr || !knn || !x_next || !idc) return fail(SCEDAR_ERR_ARG, "NULL buffer");
   if (x_curr == x_next) return fail(SCEDAR_ERR_ARG, "x_next must not alias x_curr");
-  return launch_impute_iter(x_curr, ldx, n, p, knn, k, n_do_i, min_present_val, iter, x_next,
-                            ldn, idc, ldi, stats_out, static_cast<cudaStream_t>(stream));
+  return launch_impute_iter(x_curr, ldx, n, p, knn, k, n_do_i, min_present_val, iter, row_begin,
+                            row_end, x_next, ldn, idc, ldi, stats_out,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric, int precision,

@@ -144,9 +144,9 @@ int launch_gather_rows(const double* x, int64_t ldx, int64_t p,
                        cudaStream_t s);
 int launch_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        const int64_t* knn, int k, int n_do_i, double min_present,
-                       int iter, double* x_next, int64_t ldn, int32_t* idc,
-                       int64_t ldi, unsigned long long* counters,
-                       cudaStream_t s);
+                       int iter, int64_t row_begin, int64_t row_end,
+                       double* x_next, int64_t ldn, int32_t* idc, int64_t ldi,
+                       unsigned long long* counters, cudaStream_t s);
 
 // ncdm.cu
 int launch_ncdm(double* d, int64_t ldd, int64_t n, int has_ub, double ub,

@@ -412,17 +412,18 @@ int launch_gather_rows(const double* x, int64_t ldx, int64_t p, const int64_t* s
 
 int launch_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        const int64_t* knn, int k, int n_do_i, double min_present, int iter,
-                       double* x_next, int64_t ldn, int32_t* idc, int64_t ldi,
-                       unsigned long long* counters, cudaStream_t s) {
-  if (n <= 0 || p <= 0) return SCEDAR_OK;
+                       int64_t row_begin, int64_t row_end, double* x_next, int64_t ldn,
+                       int32_t* idc, int64_t ldi, unsigned long long* counters,
+                       cudaStream_t s) {
+  if (row_end <= row_begin || p <= 0) return SCEDAR_OK;
   const size_t smem = sizeof(double) * (size_t)k * IMP_TF;
   if (smem > 200 * 1024) return fail(SCEDAR_ERR_UNSUPPORTED, "imputation: k must be <= 200");
   if (n > 65535LL * 65535LL) return fail(SCEDAR_ERR_UNSUPPORTED, "imputation: too many cells");
   SCEDAR_CUDA(cudaFuncSetAttribute(impute_iter_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // grid.y is limited to 65535: walk the cells in slabs
-  for (int64_t s0 = 0; s0 < n; s0 += 65535) {
-    const int64_t ns = std::min<int64_t>(65535, n - s0);
+  for (int64_t s0 = row_begin; s0 < row_end; s0 += 65535) {
+    const int64_t ns = std::min<int64_t>(65535, row_end - s0);
     dim3 grid((unsigned)((p + IMP_TF - 1) / IMP_TF), (unsigned)ns);
     impute_iter_kernel<<<grid, IMP_TF, smem, s>>>(x_curr, ldx, n, p, knn, k, n_do_i, min_present,
                                                  iter, x_next, ldn, idc, ldi, s0);
@@ -431,7 +432,8 @@ int launch_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
   SCEDAR_CUDA(cudaGetLastError());
   if (counters) {
     SCEDAR_CUDA(cudaMemsetAsync(counters, 0, 16, s));
-    impute_stats_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(idc, ldi, n, p, counters);
+    impute_stats_kernel<<<(unsigned)((row_end - row_begin + 7) / 8), 256, 0, s>>>(
+        idc + row_begin * ldi, ldi, row_end - row_begin, p, counters);
     SCEDAR_CUDA(cudaGetLastError());
     count_launch();
   }

@@ -366,8 +366,9 @@ def gather_rows(x, sel):
 
 
 def impute_iter(x_curr, knn, n_do_i, min_present_val, it, x_next, idc,
-                stats=None):
-    """One imputation iteration (imputation.py:56-101), median statistic."""
+                stats=None, row_begin=0, row_end=None):
+    """One imputation iteration (imputation.py:56-101), median statistic, on
+    the cells [row_begin, row_end) (default: all)."""
     _guard()
     x_curr, x_next = _f64(x_curr), _f64(x_next)
     n, p = x_curr.shape
@@ -376,5 +377,6 @@ def impute_iter(x_curr, knn, n_do_i, min_present_val, it, x_next, idc,
     assert x_curr.is_contiguous() and x_next.is_contiguous()
     _capi.check(_capi.load().scedar_impute_iter(
         _ptr(x_curr), max(p, 1), n, p, _ptr(knn), knn.shape[1], int(n_do_i),
-        float(min_present_val), int(it), _ptr(x_next), max(p, 1), _ptr(idc),
-        max(p, 1), _ptr(stats), _stream()))
+        float(min_present_val), int(it), int(row_begin),
+        int(n if row_end is None else row_end), _ptr(x_next), max(p, 1),
+        _ptr(idc), max(p, 1), _ptr(stats), _stream()))

@@ -8,7 +8,11 @@ path shards by contiguous, tile-aligned row stripes:
 * every rank prepares the cells (the K1 pass is cheaper than shipping its
   output) and owns rows [row_begin, row_end) of D and of the kNN lists;
 * only the (index, distance) lists are all-gathered -- D stripes stay in the
-  HBM of their owner.
+  HBM of their owner;
+* the consumers behind the path shard the same way: rare-sample detection
+  (``rare_samples``) exchanges one float64 per cell and iteration (the k-th
+  neighbour distances, all-gathered; the keep / drop decision is replicated),
+  imputation (``impute``) all-gathers the updated rows of x once per iteration.
 
 The compute operators are injected (``ops``) so the sharding logic can be
 tested on CPU with the ``gloo`` backend; the default is the CUDA library.
@@ -53,8 +57,30 @@ class _DeviceOps(object):
         from . import device
         device.pdist_stripe_p2p(cells, peers, rank)
 
-    def knn_stripe(self, cells, k, exclude, r0, r1):
-        return cells.knn_stripe(k, exclude, r0, r1)
+    def knn_stripe(self, cells, k, exclude, r0, r1, precision="fp64"):
+        return cells.knn_stripe(k, exclude, r0, r1, precision=precision)
+
+    # -- consumers ------------------------------------------
+    def new_mask(self, n, device):
+        return torch.ones(n, dtype=torch.uint8, device=device)
+
+    def masked_kth(self, d, alive, rank, row_begin):
+        from . import device
+        return device.masked_kth(d, alive, rank, row_begin=row_begin)
+
+    def rare_update(self, kth, cutoff, it, alive, last_kept):
+        from . import device
+        return device.rare_update(kth, cutoff, it, alive, last_kept)
+
+    def vec_max(self, v):
+        from . import device
+        return device.masked_max(v, None)
+
+    def impute_iter(self, x_curr, knn, n_do_i, min_present_val, it, x_next,
+                    idc, stats, r0, r1):
+        from . import device
+        device.impute_iter(x_curr, knn, n_do_i, min_present_val, it, x_next,
+                           idc, stats, row_begin=r0, row_end=r1)
 
 
 class StripedDistanceMatrix(object):
@@ -129,23 +155,92 @@ class StripedDistanceMatrix(object):
         return self.ops.peer_stripes(self.stripes, self.n, self.rank,
                                      self.group)
 
-    def knn_local(self, k, exclude, from_d=True):
-        """(idx[rows, k] int64, dist[rows, k]) of this rank's rows."""
+    def knn_local(self, k, exclude, from_d=True, precision="fp64"):
+        """(idx[rows, k] int64, dist[rows, k]) of this rank's rows.
+        ``precision="fast"`` (only without D): tensor-core candidates + FP64
+        re-rank, the same lists bit for bit."""
         if from_d:
             if self.d_stripe is None:
                 self.compute_d()
             return self.ops.knn_from_d(self.d_stripe, k, exclude,
                                        self.row_begin)
+        if precision == "fp64":
+            return self.ops.knn_stripe(self.cells, k, exclude, self.row_begin,
+                                       self.row_end)
         return self.ops.knn_stripe(self.cells, k, exclude, self.row_begin,
-                                   self.row_end)
+                                   self.row_end, precision=precision)
 
-    def knn(self, k, exclude, from_d=True):
+    def knn(self, k, exclude, from_d=True, precision="fp64"):
         """kNN lists of ALL cells on every rank: the all-gather of the
         per-stripe lists (the only data-path collective)."""
-        idx, dd = self.knn_local(k, exclude, from_d=from_d)
+        idx, dd = self.knn_local(k, exclude, from_d=from_d,
+                                 precision=precision)
         if self.world == 1:
             return idx, dd
         return self._gather(idx), self._gather(dd)
+
+    # -- consumers behind the path (SURVEY.md 8f) ---------------------------
+    def rare_samples(self, k, d_cutoff, n_iter):
+        """``RareSampleDetection._pdist_rare_s_detect``
+        (scedar/knn/detection.py:81-123) on the row-striped D: every rank
+        takes the ``min(m-1, k)``-th smallest live entry of its own rows, the
+        n values are all-gathered, and the keep / drop decision is applied
+        identically on every rank.  Returns ``last_kept`` (int32 [n]): the
+        last iteration that kept each cell (== n_iter for the non-rare)."""
+        if self.d_stripe is None:
+            self.compute_d()
+        n = self.n
+        alive = self.ops.new_mask(n, self.d_device)
+        last_kept = torch.zeros(n, dtype=torch.int32, device=self.d_device)
+
+        def kth_all(rank):
+            mine = self.ops.masked_kth(self.d_stripe, alive, rank,
+                                       self.row_begin)
+            return mine if self.world == 1 else self._gather(mine)
+
+        kth = kth_all(k)
+        d_max = self.ops.vec_max(kth)
+        m, fresh_rank = n, k
+        for i in range(1, n_iter + 1):
+            cutoff = d_cutoff + (n_iter - i) / n_iter * max(0, d_max - d_cutoff)
+            if m == 0:
+                continue
+            i_k = min(m - 1, k)
+            if fresh_rank != i_k:
+                kth = kth_all(i_k)
+                fresh_rank = i_k
+            kept = self.ops.rare_update(kth, cutoff, i, alive, last_kept)
+            if kept != m:
+                fresh_rank = None
+            m = kept
+        return last_kept
+
+    def impute(self, x, knn, k, n_do, min_present_val, n_iter):
+        """``FeatureImputation._impute_features_runner``
+        (scedar/knn/imputation.py:35-135, median statistic) with the cells
+        row-striped: every rank imputes its own rows from the full current x
+        and the updated rows are all-gathered after each iteration.  ``x``
+        [n, p] float64 and ``knn`` [n, k] int64 are replicated.  Returns
+        (imputed x, indicator int32 [n, p], (entries, cells) picked up)."""
+        import math
+        n, p = x.shape
+        curr = x.clone()
+        nxt = torch.empty_like(curr)
+        idc = torch.zeros((n, p), dtype=torch.int32, device=x.device)
+        stats = torch.zeros(2, dtype=torch.int64, device=x.device)
+        r0, r1 = self.row_begin, self.row_end
+        for i in range(1, n_iter + 1):
+            n_do_i = n_do + int(math.ceil((n_iter - i) / n_iter * (k - n_do)))
+            self.ops.impute_iter(curr, knn, n_do_i, min_present_val, i, nxt,
+                                 idc, stats, r0, r1)
+            if self.world > 1:
+                curr = self._gather(nxt[r0:r1])   # fresh [n, p]; nxt is scratch
+            else:
+                curr, nxt = nxt, curr
+        if self.world > 1:
+            idc = self._gather(idc[r0:r1])
+            dist.all_reduce(stats, group=self.group)
+        return curr, idc, tuple(int(v) for v in stats.tolist())
 
     def _gather(self, t):
         """all-gather of ragged stripes: pad to the widest stripe, trim."""

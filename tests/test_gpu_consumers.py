@@ -256,3 +256,29 @@ def test_impute_larger_vs_oracle(b200):
         np.testing.assert_array_equal(got[1].toarray(), idc)
         assert "picked up {} total features in {} ".format(entries, cells) \
             in got[2].splitlines()[-2]
+
+
+def test_striped_consumers_single_rank(b200):
+    """StripedDistanceMatrix.rare_samples / impute (world 1, CUDA operators)
+    agree with the drop-in classes and the oracle."""
+    import torch
+    from scedar_b200 import device as dev, knn, synth
+    from scedar_b200._capi import EXCLUDE_FIRST
+    from scedar_b200.stripes import StripedDistanceMatrix
+    x = synth.blobs(1500, 25, seed=2, n_blobs=3, outlier_frac=0.03)
+    sdm = StripedDistanceMatrix(dev.to_device(x), "euclidean")
+    d = sdm.compute_d().cpu().numpy()
+    cut = float(np.median(np.sort(d, axis=0)[8]) * 1.1)
+    lk = sdm.rare_samples(8, cut, 5).cpu().numpy()
+    res, prog = korc.rare_pdist(d, 8, cut, 5)
+    assert np.array_equal(lk, last_kept(prog, 1500)) and 0 < len(res) < 1500
+    xi = synth.log_counts(1500, 90, seed=6)
+    s2 = StripedDistanceMatrix(dev.to_device(xi), "correlation")
+    idx, _ = s2.knn(9, EXCLUDE_FIRST)
+    got, idc, stats = s2.impute(dev.to_device(xi), idx, 9, 3, 0.6, 2)
+    wx, widc, wstats = korc.impute(xi, idx.cpu().numpy(), 9, 3, 0.6, 2)
+    np.testing.assert_array_equal(got.cpu().numpy(), wx)
+    np.testing.assert_array_equal(idc.cpu().numpy(), widc)
+    assert stats == wstats
+    sdm.close()
+    s2.close()

@@ -41,6 +41,99 @@ class OracleOps(object):
                                r0)
 
 
+    # -- consumers: NumPy stand-ins with the device operators' contract -----
+    def new_mask(self, n, device):
+        return torch.ones(n, dtype=torch.uint8)
+
+    def masked_kth(self, d, alive, rank, row_begin):
+        d, a = d.numpy(), alive.numpy().astype(bool)
+        out = np.full(d.shape[0], np.inf)
+        for r in range(d.shape[0]):
+            if a[row_begin + r]:
+                out[r] = np.sort(d[r][a])[rank]
+        return torch.from_numpy(out)
+
+    def rare_update(self, kth, cutoff, it, alive, last_kept):
+        a = alive.numpy().astype(bool)
+        keep = a & (kth.numpy() <= cutoff)
+        last_kept.numpy()[keep] = it
+        alive.numpy()[a & ~keep] = 0
+        return int(keep.sum())
+
+    def vec_max(self, v):
+        return float(v.max())
+
+    def impute_iter(self, x_curr, knn, n_do_i, mpv, it, x_next, idc, stats,
+                    r0, r1):
+        x, kn = x_curr.numpy(), knn.numpy()
+        present = x >= mpv
+        for s in range(r0, r1):
+            mask = (present[kn[s]].sum(axis=0) >= n_do_i) & ~present[s]
+            x_next.numpy()[s] = x[s]
+            if mask.any():
+                x_next.numpy()[s, mask] = np.median(x[kn[s]][:, mask], axis=0)
+                idc.numpy()[s, mask] = it
+        sub = idc.numpy()[r0:r1] > 0
+        stats[0] = int(sub.sum())
+        stats[1] = int(sub.any(axis=1).sum())
+
+
+def _consumer_worker(rank, world, port, n, p, k, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import knn_oracle as korc
+        from oracle import sdm_oracle as orc
+        from scedar_b200.stripes import StripedDistanceMatrix
+        rng = np.random.default_rng(5)
+        xn = np.concatenate([rng.normal(0, 1, (n - 12, p)),
+                             rng.uniform(-9, 9, (12, p))])
+        x = torch.from_numpy(xn) if rank == 0 else None
+        sdm = StripedDistanceMatrix(x, "euclidean", shape=(n, p),
+                                    device="cpu", ops=OracleOps())
+        d = orc.pdist(xn, "euclidean")
+        cut = float(np.median(np.sort(d, axis=0)[k]) * 1.1)
+        lk = sdm.rare_samples(k, cut, 4).numpy()
+        res, prog = korc.rare_pdist(d, k, cut, 4)
+        want = np.full(n, -1)
+        for i, kept in enumerate(prog):
+            want[kept] = i
+        ok_rare = bool(np.array_equal(lk, want)) and 0 < len(res) < n
+        # imputation on thresholded data, lists from the striped kNN
+        xi = np.where(xn > 0.3, xn, 0.0)
+        idx, _ = sdm.knn(k, exclude=0)
+        got, idc, (entries, cells) = sdm.impute(torch.from_numpy(xi), idx, k,
+                                                2, 0.3, 3)
+        wx, widc, wstats = korc.impute(xi, idx.numpy(), k, 2, 0.3, 3)
+        ok_imp = (np.array_equal(got.numpy(), wx)
+                  and np.array_equal(idc.numpy(), widc)
+                  and (entries, cells) == wstats and entries > 0)
+        q.put((rank, ok_rare, ok_imp))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_consumers():
+    """Row-striped rare-sample detection and imputation (world 2, gloo)
+    against the single-process NumPy restatement."""
+    world, n, p, k = 2, 300, 10, 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_consumer_worker,
+                         args=(r, world, port, n, p, k, q))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(g[1] is True and g[2] is True for g in got), got
+
+
 def _worker(rank, world, port, n, p, k, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
