@@ -60,10 +60,10 @@
 namespace scedar {
 namespace {
 
-constexpr int TM = 128, TN = 256, TK = 64;
-constexpr int TSTAGES = 2;
+constexpr int TM = 128, TN = 256, TK = 32;
+constexpr int TSTAGES = 4;
 constexpr int A_BYTES = TM * TK * 2, B_BYTES = TN * TK * 2;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 49152
 constexpr int KC = 32;       // candidates kept per row and column split
 constexpr int STG_LD = 33;   // staging row stride of the STORE epilogue (conflict-free)
 constexpr int EPI_BYTES = TM * STG_LD * 8;   // >= TM * KC * 8 (the TOPK lists)
@@ -85,22 +85,24 @@ struct TcArgs {
   int kblocks;
   int64_t row_begin, row_end;
   int euclid;
-  int splits;
+  int splits;           // column splits S; grid = groups * S persistent CTAs
+  int groups;           // CTA (g, s) walks row tiles g, g + groups, ...
+  int row_tiles;
   double* out;          // STORE: D stripe
   int64_t ldd;
   float* part_key;      // TOPK: [splits, rows, KC]
   int32_t* part_idx;
 };
 
-// K-major operand tile in 128B-swizzled shared memory: rows of 128 bytes,
-// 8-row swizzle atoms 1024 bytes apart
+// K-major operand tile in 64B-swizzled shared memory: rows of 64 bytes (one
+// K slab of 32 halves), 8-row swizzle atoms 512 bytes apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;              // leading byte offset (unused for SW128 K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 16;              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;     // stride byte offset between 8-row atoms
   d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  d |= (uint64_t)4 << 61;              // SWIZZLE_64B
   return d;
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t acc) {
@@ -226,15 +228,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   uint8_t* gbase = smem_raw + (base - raw);
   uint8_t* epi = gbase + TSTAGES * STAGE_BYTES;
   const uint32_t bars = base + TSTAGES * STAGE_BYTES + EPI_BYTES;
-  // barrier slots (8 bytes each): full[2], empty[2], tfull[2], tempty[2]
-  const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(epi + EPI_BYTES + 64);
+  // barrier slots (8 bytes each): full[4], empty[4], tfull[2], tempty[2]
+  const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tfull0 = bars + 16 * TSTAGES,
+                 tempty0 = tfull0 + 16;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(epi + EPI_BYTES + 16 * TSTAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
       mbar_init(tempty0 + 8 * s, 128);
     }
@@ -252,11 +258,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // 1-D grid, column splits fastest: the CTAs resident at one time cover few
-  // row tiles, so their A panels (and the B tiles they sweep) stay in L2
+  // 1-D grid of groups x splits CTAs, split fastest: CTA (g, s) sweeps the
+  // column tiles of split s for row tiles g, g + groups, ... (see tc_schedule;
+  // with groups == row_tiles every CTA owns one row tile and the CTAs resident
+  // at one time cover few row tiles, so their A panels stay in L2).
   const int split = (int)(blockIdx.x % a.splits);
-  const int64_t I = a.row_begin / TM + blockIdx.x / a.splits;
-  const int64_t i0 = I * TM;
+  const int group = (int)(blockIdx.x / a.splits);
+  const int64_t rt0 = a.row_begin / TM;
   const int64_t CT = (a.n + TN - 1) / TN;
   const int64_t J0 = CT * split / a.splits, J1 = CT * (split + 1) / a.splits;
   const int KB = a.kblocks;
@@ -264,24 +272,28 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t J = J0; J < J1; ++J) {
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-          const uint32_t st = base + s * STAGE_BYTES;
-          tma_load_2d(st, &map_a_hi, kb * TK, (int)i0, full0 + 8 * s);
-          tma_load_2d(st + A_BYTES, &map_a_lo, kb * TK, (int)i0, full0 + 8 * s);
-          tma_load_2d(st + 2 * A_BYTES, &map_b_hi, kb * TK, (int)(J * TN), full0 + 8 * s);
-          tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * TK, (int)(J * TN),
-                      full0 + 8 * s);
+      for (int rt = group; rt < a.row_tiles; rt += a.groups) {
+        const int i0 = (int)((rt0 + rt) * TM);
+        for (int64_t J = J0; J < J1; ++J) {
+          for (int kb = 0; kb < KB; ++kb, ++it) {
+            const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+            const uint32_t st = base + s * STAGE_BYTES;
+            tma_load_2d(st, &map_a_hi, kb * TK, i0, full0 + 8 * s);
+            tma_load_2d(st + A_BYTES, &map_a_lo, kb * TK, i0, full0 + 8 * s);
+            tma_load_2d(st + 2 * A_BYTES, &map_b_hi, kb * TK, (int)(J * TN), full0 + 8 * s);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * TK, (int)(J * TN),
+                        full0 + 8 * s);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, t = 0;
-      for (int64_t J = J0; J < J1; ++J, ++t) {
+      const int64_t tiles = (J1 - J0) * ((a.row_tiles - group + a.groups - 1) / a.groups);
+      for (int64_t tt = 0; tt < tiles; ++tt, ++t) {
         const uint32_t acc = t & 1, aph = (t >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
         tc_fence_after();
@@ -311,10 +323,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int e = (warp - 2) * 32 + lane;   // 0..127 inside the epilogue group
-    const int64_t gi = i0 + r;
-    const bool row_ok = gi >= a.row_begin && gi < a.row_end;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t t = 0;
+    for (int rt = group; rt < a.row_tiles; rt += a.groups) {
+    const int64_t i0 = (rt0 + rt) * TM;
+    const int64_t gi = i0 + r;
+    const bool row_ok = gi >= a.row_begin && gi < a.row_end;
     if (TOPK) {
       float* lkey = reinterpret_cast<float*>(epi);           // [TM][KC]
       int* lidx = reinterpret_cast<int*>(epi + TM * KC * 4);  // [TM][KC]
@@ -395,6 +409,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         tc_fence_before();
         mbar_arrive(tempty0 + 8 * acc);
       }
+    }
+    if (TOPK) __syncwarp();   // the lists are re-initialised for the next row tile
     }
   }
   tc_fence_before();
@@ -639,29 +655,38 @@ margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
 }
 
 int encode_map(CUtensorMap* m, const __half* ptr, int64_t rows, int64_t cols, int box_rows) {
-  return encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, rows, cols, box_rows, TK);
+  return encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, rows, cols, box_rows, TK,
+                           CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 struct FastMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-int tc_splits(int64_t rows, int64_t n, int64_t min_splits) {
-  // STORE: at least 8 column splits (L2 locality, see the kernel); TOPK: as few
-  // as fill the SMs twice, every split warms up its own candidate lists
-  const int64_t row_tiles = (rows + TM - 1) / TM + 1;
+// Schedule: S column splits x G groups of row tiles; CTA (g, s) walks the row
+// tiles g, g + G, ...  Measured on B200 (profiles/README.md): a persistent
+// lockstep grid (S * G = #SMs) is no faster when the operands exceed L2 -- the
+// kernel is bound by L2 -> shared-memory bandwidth, not by HBM -- and slower
+// when they fit (148 CTAs hammer the same L2 lines), so every row tile gets
+// its own CTAs (G = RT) and the hardware scheduler de-synchronises them.
+// STORE: at least 8 column splits; TOPK: as few as fill the SMs twice, every
+// split warms up its own candidate lists.
+void tc_schedule(int64_t RT, int64_t n, int64_t min_splits, int* splits, int* groups) {
   const int64_t CT = (n + TN - 1) / TN;
-  int64_t s = (2 * (int64_t)num_sms() + row_tiles - 1) / row_tiles;
+  int64_t s = (2 * (int64_t)num_sms() + RT) / (RT + 1);
   if (s < min_splits) s = min_splits;
   if (s > CT) s = CT;
   if (s > 32) s = 32;
-  return (int)s;
+  if (s < 1) s = 1;
+  *splits = (int)s;
+  *groups = (int)RT;
 }
 
 }  // namespace
 
 int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes, const void* ptr,
-                      int64_t rows, int64_t cols, int box_rows, int box_cols) {
+                      int64_t rows, int64_t cols, int box_rows, int box_cols,
+                      CUtensorMapSwizzle swizzle) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -682,7 +707,7 @@ int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes,
     encode = reinterpret_cast<encode_fn>(fn);
   }
   CUresult r = encode(m, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(SCEDAR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " +
@@ -697,7 +722,7 @@ struct FastState {
   __half* bh = nullptr;   // B role
   __half* bl = nullptr;
   double* scale = nullptr;  // [2] on the device: s, 1/s^2
-  int64_t n256 = 0, p64 = 0;
+  int64_t n256 = 0, p64 = 0;   // p64: K extent, a multiple of the slab width TK
   FastMaps maps;
 };
 
@@ -775,12 +800,12 @@ int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   TcArgs a = tc_args(c, f, row_begin, row_end);
   a.out = d_out;
   a.ldd = ldd;
-  const int64_t rows = row_end - row_begin;
-  a.splits = tc_splits(rows, c->n, 8);
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
+  tc_schedule(RT, c->n, 8, &a.splits, &a.groups);
+  a.row_tiles = (int)RT;
   SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  gram_tc_kernel<false><<<(unsigned)(RT * a.splits), TC_THREADS, TC_SMEM, s>>>(
+  gram_tc_kernel<false><<<(unsigned)(a.groups * a.splits), TC_THREADS, TC_SMEM, s>>>(
       f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
@@ -800,8 +825,9 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   // lists hold 32 candidates per split: k + 1 + 8 <= 32 is served by any
   // number of splits, larger k re-ranks 64 drawn from >= 4 splits
   const bool wide = k + 1 + 8 > KC;
-  a.splits = tc_splits(rows, c->n, wide ? 4 : 1);
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
+  tc_schedule(RT, c->n, wide ? 4 : 1, &a.splits, &a.groups);
+  a.row_tiles = (int)RT;
   Scratch pk, pi, tau, dk, misc, flags;
   SCEDAR_CHECK(pk.alloc(sizeof(float) * a.splits * rows * KC, s));
   SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * a.splits * rows * KC, s));
@@ -815,7 +841,7 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   a.part_idx = pi.as<int32_t>();
   SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  gram_tc_kernel<true><<<(unsigned)(RT * a.splits), TC_THREADS, TC_SMEM, s>>>(
+  gram_tc_kernel<true><<<(unsigned)(a.groups * a.splits), TC_THREADS, TC_SMEM, s>>>(
       f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
   SCEDAR_CUDA(cudaGetLastError());
   unsigned int* err_bits = misc.as<unsigned int>();

@@ -58,8 +58,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 
 // Row-major [rows, cols] matrix, boxes of box_rows x box_cols elements whose
-// inner extent is exactly 128 bytes, 128B-swizzled in shared memory.
+// inner extent in bytes equals the swizzle span (128 or 64).
 int encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int elem_bytes, const void* ptr,
-                      int64_t rows, int64_t cols, int box_rows, int box_cols);
+                      int64_t rows, int64_t cols, int box_rows, int box_cols,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 }  // namespace scedar
