@@ -232,7 +232,7 @@ int scedar_pdist_symmetric(const scedar_cells_t* c, int precision, double* d_out
   if (!d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
   if (precision == SCEDAR_PRECISION_FAST)
-    return launch_fast_stripe(c, 0, c->n, d_out, ldd, static_cast<cudaStream_t>(stream));
+    return launch_fast_stripe(c, 0, c->n, d_out, ldd, static_cast<cudaStream_t>(stream), 1);
   return launch_gram_symmetric(c, d_out, ldd, static_cast<cudaStream_t>(stream));
 }
 

@@ -101,7 +101,8 @@ int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,
 void fast_state_free(void* fast, cudaStream_t s);
 int fast_knn_max_k();
 int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end,
-                       double* d_out, int64_t ldd, cudaStream_t s);
+                       double* d_out, int64_t ldd, cudaStream_t s,
+                       int symmetric = 0);
 int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin,
                     int64_t row_end, int64_t* idx_out, double* dist_out,
                     cudaStream_t s);

@@ -90,6 +90,8 @@ struct TcArgs {
   int row_tiles;
   double* out;          // STORE: D stripe
   int64_t ldd;
+  int sym;              // STORE over the whole matrix: column tiles wholly above
+                        // the diagonal are skipped and written as transposes
   float* part_key;      // TOPK: [splits, rows, KC]
   int32_t* part_idx;
 };
@@ -266,14 +268,31 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const int group = (int)(blockIdx.x / a.splits);
   const int64_t rt0 = a.row_begin / TM;
   const int64_t CT = (a.n + TN - 1) / TN;
-  const int64_t J0 = CT * split / a.splits, J1 = CT * (split + 1) / a.splits;
   const int KB = a.kblocks;
+  // column tiles of row tile rt handled by this CTA: [J0, J1).  Symmetric
+  // STORE: only the tiles that touch the lower triangle (256 J < 128 (I + 1)),
+  // split evenly; the heavy (bottom) row tiles are scheduled first.
+  auto row_tile_of = [&](int rt) -> int64_t {
+    return rt0 + (a.sym ? a.row_tiles - 1 - rt : rt);
+  };
+  auto j_range = [&](int64_t I, int64_t& J0, int64_t& J1) {
+    int64_t L = CT;
+    if (a.sym) {
+      const int64_t ja = (I + 2) / 2;
+      L = ja < CT ? ja : CT;
+    }
+    J0 = L * split / a.splits;
+    J1 = L * (split + 1) / a.splits;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int rt = group; rt < a.row_tiles; rt += a.groups) {
-        const int i0 = (int)((rt0 + rt) * TM);
+        const int64_t I = row_tile_of(rt);
+        const int i0 = (int)(I * TM);
+        int64_t J0, J1;
+        j_range(I, J0, J1);
         for (int64_t J = J0; J < J1; ++J) {
           for (int kb = 0; kb < KB; ++kb, ++it) {
             const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
@@ -292,7 +311,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, t = 0;
-      const int64_t tiles = (J1 - J0) * ((a.row_tiles - group + a.groups - 1) / a.groups);
+      int64_t tiles = 0;
+      for (int rt = group; rt < a.row_tiles; rt += a.groups) {
+        int64_t J0, J1;
+        j_range(row_tile_of(rt), J0, J1);
+        tiles += J1 - J0;
+      }
       for (int64_t tt = 0; tt < tiles; ++tt, ++t) {
         const uint32_t acc = t & 1, aph = (t >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
@@ -326,7 +350,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t t = 0;
     for (int rt = group; rt < a.row_tiles; rt += a.groups) {
-    const int64_t i0 = (rt0 + rt) * TM;
+    const int64_t I = row_tile_of(rt);
+    const int64_t i0 = I * TM;
+    int64_t J0, J1;
+    j_range(I, J0, J1);
     const int64_t gi = i0 + r;
     const bool row_ok = gi >= a.row_begin && gi < a.row_end;
     if (TOPK) {
@@ -401,8 +428,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           for (int rr = 0; rr < 32; ++rr) {
             const int row = rr * 4 + (e >> 5), col = e & 31;
             const int64_t gi2 = i0 + row, gj = j0 + c0 + col;
-            if (gi2 >= a.row_begin && gi2 < a.row_end && gj < a.n)
+            if (gi2 >= a.row_begin && gi2 < a.row_end && gj < a.n && (!a.sym || gi2 >= gj))
               a.out[(gi2 - a.row_begin) * a.ldd + gj] = stg[row * STG_LD + col];
+          }
+          if (a.sym) {
+            // transposed copy: column gj of the block is row gj of D, entries
+            // strictly below the diagonal only (1 KB contiguous per column)
+            const int64_t gi2 = i0 + e;
+            for (int col = 0; col < 32; ++col) {
+              const int64_t gj = j0 + c0 + col;
+              if (gj < gi2 && gi2 < a.n) a.out[gj * a.ldd + gi2] = stg[e * STG_LD + col];
+            }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -793,13 +829,16 @@ static TcArgs tc_args(const scedar_cells* c, const FastState* f, int64_t row_beg
 }
 
 int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end, double* d_out,
-                       int64_t ldd, cudaStream_t s) {
+                       int64_t ldd, cudaStream_t s, int symmetric) {
   if (row_end <= row_begin) return SCEDAR_OK;
+  if (symmetric && (row_begin != 0 || row_end != c->n))
+    return fail(SCEDAR_ERR_ARG, "the symmetric fast path covers the whole matrix");
   FastState* f = nullptr;
   SCEDAR_CHECK(ensure_fast(c, s, &f));
   TcArgs a = tc_args(c, f, row_begin, row_end);
   a.out = d_out;
   a.ldd = ldd;
+  a.sym = symmetric;
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   tc_schedule(RT, c->n, 8, &a.splits, &a.groups);
   a.row_tiles = (int)RT;

@@ -450,6 +450,13 @@ def test_fast_path_tcgen05(b200, metric):
         assert torch.equal(dfast.diagonal(), torch.zeros_like(dfast.diagonal()))
         part = cells.pdist_stripe(200, 555, precision="fast")
         assert torch.equal(part, dfast[200:555])
+        # whole matrix: only the tiles touching the lower triangle are
+        # contracted, the rest is written as transposes -> bit-symmetric
+        dsym = cells.pdist_symmetric(precision="fast")
+        assert torch.equal(dsym, dsym.T)
+        assert torch.equal(dsym.diagonal(), torch.zeros_like(dsym.diagonal()))
+        assert (dsym - d64).abs().max().item() / d64.max().item() <= 1e-4
+        assert torch.equal(torch.tril(dsym), torch.tril(dfast))
         # k + 9 <= 32: one 32-candidate list per cell; larger k re-ranks 64
         # candidates drawn from >= 4 column splits (k <= 55)
         for k, ex in ((15, EXCLUDE_FIRST), (15, EXCLUDE_SELF), (1, EXCLUDE_SELF),

@@ -48,6 +48,8 @@ def main():
             d = torch.empty((n, n), dtype=torch.float64, device="cuda")
             t = timed(lambda: cells.pdist_stripe(0, n, out=d, precision="fast"))
             out["fast_d_ms"] = round(t, 3); out["fast_d_tflops_alg"] = round(2.0 * n * n * p / t * 1e-9, 2)
+            t = timed(lambda: cells.pdist_symmetric(out=d, precision="fast"))
+            out["fast_sym_ms"] = round(t, 3); out["fast_sym_tflops_alg"] = round(1.0 * n * (n + 1) * p / t * 1e-9, 2)
             del d
         cells.close(); del x
         torch.cuda.empty_cache()
