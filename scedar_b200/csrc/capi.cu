@@ -3,6 +3,7 @@
 // happens on the host and there is no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -120,38 +121,90 @@ int new_cells(int64_t n, int64_t p, int metric, cudaStream_t s, scedar_cells** o
 }
 
 }  // namespace
+// FP64 kNN of a row range.  Three ways to get there, chosen by cost:
+//   symmetric  whole matrix and D fits in free HBM: lower tiles contracted once
+//              (half the flops), mirrored into a scratch D, row-wise top-k from
+//              it -- 2.5x faster than the fused kernel at 60,000 x 2,000
+//   chunked    D in row chunks of a few GB through scratch + top-k per chunk
+//              (all n^2 p products, but at the STORE kernel's rate; only worth
+//              it for long rows, p >= 512)
+//   fused      Gram tile -> epilogue -> per-row lists in shared memory, D never
+//              reaches HBM (k + 1 <= 32); the only form that needs no scratch
+// SCEDAR_B200_KNN_FP64 = symmetric | chunked | fused forces one (testing).
 int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin,
                     int64_t row_end, int64_t* idx_out, double* dist_out, cudaStream_t s) {
   const int64_t rows = row_end - row_begin;
   if (k == 0 || rows <= 0) return SCEDAR_OK;
   const int K = k + 1;
-  if (K <= 32) {
-    // fused: Gram tile -> epilogue -> per-row lists in shared memory, D never
-    // reaches HBM; column splits give every SM work, then one merge pass
-    const int splits = gram_topk_splits(c, rows);
-    Scratch pd, pi;
-    SCEDAR_CHECK(pd.alloc(sizeof(double) * splits * rows * K, s));
-    SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * splits * rows * K, s));
-    SCEDAR_CHECK(launch_gram_topk(c, row_begin, row_end, K, splits, pd.as<double>(),
-                                  pi.as<int32_t>(), s));
-    return launch_topk_merge(pd.as<double>(), pi.as<int32_t>(), splits, rows, K, row_begin, k,
-                             exclude, idx_out, dist_out, s);
-  }
   if (K > 128) return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
-  // wider lists: materialise D in row chunks that stay L2-sized, select per chunk
-  int64_t chunk = (int64_t(256) << 20) / (8 * std::max<int64_t>(c->n, 1));
-  chunk = std::max<int64_t>(128, chunk / 128 * 128);
-  chunk = std::min(chunk, round_up(rows, 128));
-  Scratch dbuf;
-  SCEDAR_CHECK(dbuf.alloc(sizeof(double) * chunk * c->n, s));
-  for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk) {
-    const int64_t r1 = std::min(row_end, r0 + chunk);
-    SCEDAR_CHECK(launch_gram_stripe(c, r0, r1, dbuf.as<double>(), c->n, s));
-    SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), c->n, c->n, r0, r1, k, exclude,
-                                    idx_out + (r0 - row_begin) * k,
-                                    dist_out + (r0 - row_begin) * k, s));
+  const int64_t n = c->n;
+  const char* forced = getenv("SCEDAR_B200_KNN_FP64");
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    free_b = 0;
   }
-  return SCEDAR_OK;
+  // memory the stream-ordered pool already holds is reusable as well
+  cudaMemPool_t pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) ==
+            cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess &&
+        reserved > used)
+      free_b += (size_t)(reserved - used);
+  }
+  const double d_bytes = 8.0 * (double)n * (double)n;
+  enum { SYM, CHUNKED, FUSED } mode;
+  if (rows == n && d_bytes <= 0.45 * (double)free_b)
+    mode = SYM;
+  else if (K > 32 || ((double)free_b > 6e9 && c->p_pad >= 512))
+    mode = CHUNKED;   // measured: 1.2-1.4x over fused at p = 2000, 2x slower at p = 50
+  else
+    mode = FUSED;
+  if (forced && K <= 32) {
+    if (!strcmp(forced, "fused")) mode = FUSED;
+    if (!strcmp(forced, "chunked")) mode = CHUNKED;
+    if (!strcmp(forced, "symmetric") && rows == n) mode = SYM;
+  }
+  if (mode == SYM) {
+    Scratch dbuf;
+    if (dbuf.alloc((size_t)d_bytes, s) == SCEDAR_OK) {
+      SCEDAR_CHECK(launch_gram_symmetric(c, dbuf.as<double>(), n, s));
+      return launch_topk_from_d(dbuf.as<double>(), n, n, 0, n, k, exclude, idx_out, dist_out, s);
+    }
+    mode = CHUNKED;   // fragmentation: fall through with a smaller request
+  }
+  if (mode == CHUNKED) {
+    // row chunks of up to 4 GB (a quarter of what is free at most)
+    double budget = std::min(4e9, 0.25 * (double)free_b);
+    if (budget < 64e6) budget = 64e6;
+    int64_t chunk = (int64_t)(budget / (8.0 * (double)std::max<int64_t>(n, 1)));
+    chunk = std::max<int64_t>(128, chunk / 128 * 128);
+    chunk = std::min(chunk, round_up(rows, 128));
+    Scratch dbuf;
+    if (dbuf.alloc(sizeof(double) * (size_t)chunk * (size_t)n, s) == SCEDAR_OK) {
+      for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk) {
+        const int64_t r1 = std::min(row_end, r0 + chunk);
+        SCEDAR_CHECK(launch_gram_stripe(c, r0, r1, dbuf.as<double>(), n, s));
+        SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), n, n, r0, r1, k, exclude,
+                                        idx_out + (r0 - row_begin) * k,
+                                        dist_out + (r0 - row_begin) * k, s));
+      }
+      return SCEDAR_OK;
+    }
+    if (K > 32) return SCEDAR_ERR_NOMEM;
+  }
+  const int splits = gram_topk_splits(c, rows);
+  Scratch pd, pi;
+  SCEDAR_CHECK(pd.alloc(sizeof(double) * splits * rows * K, s));
+  SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * splits * rows * K, s));
+  SCEDAR_CHECK(launch_gram_topk(c, row_begin, row_end, K, splits, pd.as<double>(),
+                                pi.as<int32_t>(), s));
+  return launch_topk_merge(pd.as<double>(), pi.as<int32_t>(), splits, rows, K, row_begin, k,
+                           exclude, idx_out, dist_out, s);
 }
 
 }  // namespace scedar

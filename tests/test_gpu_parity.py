@@ -341,13 +341,20 @@ def test_stripes_and_fused_topk(b200):
         assert torch.equal(full, cells.pdist_stripe(0, 1000))
         assert torch.equal(full[100:333], cells.pdist_stripe(100, 333))
         assert torch.equal(full[997:], cells.pdist_stripe(997, 1000))
-        for k in (1, 15, 31):
-            for ex in (EXCLUDE_FIRST, EXCLUDE_SELF):
-                i0, d0 = dev.knn_from_d(full, k, ex)
-                i1, d1 = cells.knn_stripe(k, ex)
-                assert torch.equal(i0, i1) and torch.equal(d0, d1), (m, k, ex)
-                i2, d2 = cells.knn_stripe(k, ex, 130, 700)
-                assert torch.equal(i0[130:700], i2)
+        # the three routes of the FP64 kNN (capi.cu: knn_stripe_fp64) agree
+        import os
+        for mode in ("fused", "chunked", "symmetric", None):
+            if mode is None:
+                os.environ.pop("SCEDAR_B200_KNN_FP64", None)
+            else:
+                os.environ["SCEDAR_B200_KNN_FP64"] = mode
+            for k in (1, 15, 31):
+                for ex in (EXCLUDE_FIRST, EXCLUDE_SELF):
+                    i0, d0 = dev.knn_from_d(full, k, ex)
+                    i1, d1 = cells.knn_stripe(k, ex)
+                    assert torch.equal(i0, i1) and torch.equal(d0, d1), (m, k, ex)
+                    i2, d2 = cells.knn_stripe(k, ex, 130, 700)
+                    assert torch.equal(i0[130:700], i2)
         for k in (40, 100):   # unfused wide-list path
             i0, d0 = dev.knn_from_d(full, k, EXCLUDE_SELF)
             i1, d1 = cells.knn_stripe(k, EXCLUDE_SELF)
