@@ -305,7 +305,7 @@ class SampleDistanceMatrix(object):
             n = self._x.shape[0]
             out = np.empty((n, n), dtype=np.float64)
             for r0, r1, stripe in self._d_stripes():
-                out[r0:r1] = stripe.cpu().numpy()
+                dev.to_host(stripe, out[r0:r1])
             self._lazy_load_d = out
         return self._lazy_load_d
 
@@ -319,9 +319,9 @@ class SampleDistanceMatrix(object):
             for r0, r1, stripe in self._d_stripes():
                 s, a = dev.col_sort(stripe, want_sorted, want_arg)
                 if want_sorted:
-                    srt[r0:r1] = s.cpu().numpy()
+                    dev.to_host(s, srt[r0:r1])
                 if want_arg:
-                    arg[r0:r1] = a.cpu().numpy()
+                    dev.to_host(a, arg[r0:r1])
         # cell-major -> the reference's (rank, cell) orientation (a view)
         return (srt.T if want_sorted else None, arg.T if want_arg else None)
 
