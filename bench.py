@@ -13,8 +13,10 @@ epilogue into this rank's D stripe -> row-wise top-k from the stripe ->
 all-gather of the kNN lists.
 
 `value` times the step with x already resident in HBM; `e2e` times it through
-the public API from a pinned HOST x (H2D + NCCL broadcast inside the timed
-region) to the kNN lists back on the host.  The reference arm
+the public API from pinned HOST memory (at N=1 one H2D copy of x; at N>1 every
+rank uploads its 1/N row shard over its own PCIe link and the shards are
+all-gathered over NVLink -- all inside the timed region) to the kNN lists back
+on the host.  The reference arm
 (--impl reference) times the CPU oracle port of the reference's own path
 (oracle/sdm_oracle.py: pdist + full stable argsort, what s_knn_ind_lut costs)
 on a bounded row sample with all host threads.
@@ -308,10 +310,25 @@ def run_b200(a):
     prep_ms, gram_avg_ms, topk_ms = [sum(c) / len(c) for c in zip(*phases)]
 
     # ---- e2e: host x -> kNN lists on the host, through the public API ------
+    # With several ranks the rows of x sit sharded over the ranks' pinned host
+    # buffers (1/N each, as a per-process loader leaves them): every rank
+    # uploads its shard over its own PCIe link and the shards are all-gathered
+    # over NVLink (stripes.gather_x) -- 1.6 GB cross the host links once in
+    # total, in parallel, instead of through rank 0's link alone.
+    from scedar_b200.stripes import gather_x, shard_rows
+    sb, se = shard_rows(n, world)[rank]
+    if world > 1:
+        shard_host = x_dev[sb:se].cpu().pin_memory()      # set-up, not timed
+        shard_dev = torch.empty((se - sb, p), dtype=torch.float64, device=dev)
+
     def e2e_step():
-        if rank == 0:
+        if world == 1:
             x_dev.copy_(x_host, non_blocking=True)
-        idx, dd = step(x_dev if rank == 0 else None, world > 1)
+            x_in = x_dev
+        else:
+            shard_dev.copy_(shard_host, non_blocking=True)
+            x_in = gather_x(shard_dev, n)
+        idx, dd = step(x_in, False)
         if rank == 0:
             idx_host.copy_(idx, non_blocking=True)
             dist_host.copy_(dd, non_blocking=True)
@@ -445,7 +462,11 @@ def run_b200(a):
                      "topk_and_gather": topk_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "s_per_step": e2e_s,
                 "h2d_bytes_per_step": n * p * 8,
-                "d2h_bytes_per_step": n * k * 16},
+                "d2h_bytes_per_step": n * k * 16,
+                "input": ("x in rank 0's pinned host memory" if world == 1 else
+                          "x row-sharded over the {} ranks' pinned host "
+                          "buffers, uploaded in parallel, all-gathered over "
+                          "NVLink".format(world))},
         "gpu_launches": int(launches),
         "roofline": {
             "kernel": "gram_f64_kernel<STORE> (DMMA m8n8k4 + fused metric "

@@ -24,6 +24,10 @@
  *    across the ABI.  scedar_last_error() gives the message for the calling
  *    thread's last failure.
  *  - There is no CPU fallback anywhere behind this ABI.
+ *  - Inputs must be finite.  NaN / inf propagate into D as IEEE arithmetic
+ *    dictates, but the selection kernels order by (distance, index) with
+ *    ordinary comparisons, so a NaN distance is never selected (NumPy's sort
+ *    would place it last); rows that consist of NaN yield index -1.
  */
 #ifndef SCEDAR_B200_H
 #define SCEDAR_B200_H

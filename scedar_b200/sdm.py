@@ -469,6 +469,8 @@ class SampleDistanceMatrix(object):
                                   query_params=None, verbose=False):
         """sdm.py:872-947: CSR, entry (i, j) = distance when j is one of i's
         kNN; exact-zero distances stored as -inf."""
+        if k > 128:
+            raise NotImplementedError("connectivity matrix with k > 128")
         self._knn_dev = None
         targets, distances = self.s_knns(
             k=k, metric=metric, use_pca=use_pca, use_hnsw=use_hnsw,
@@ -481,8 +483,6 @@ class SampleDistanceMatrix(object):
         else:
             idx_dev = dev.to_device(np.asarray(targets, dtype=np.int64))
             dist_dev = dev.to_device(np.asarray(distances, dtype=np.float64))
-        if k > 128:
-            raise NotImplementedError("connectivity matrix with k > 128")
         indptr, indices, data = dev.knn_connectivity_csr(idx_dev, dist_dev)
         return spsparse.csr_matrix(
             (data.cpu().numpy(), indices.cpu().numpy(),

@@ -35,6 +35,30 @@ def partition(n, world):
     return out
 
 
+def shard_rows(n, world):
+    """Even split of the rows of x over the ranks' HOST buffers (independent
+    of the tile-aligned D stripes): list of (row_begin, row_end)."""
+    chunk = (n + world - 1) // world
+    return [(min(r * chunk, n), min((r + 1) * chunk, n)) for r in range(world)]
+
+
+def gather_x(x_rows, n, group=None):
+    """All-gather of the ranks' row shards of x (each uploaded over the rank's
+    own PCIe link) into the full [n, p] matrix on every rank -- N links feed
+    the node instead of one upload on rank 0 followed by a broadcast."""
+    world = dist.get_world_size(group)
+    chunk = (n + world - 1) // world
+    p = x_rows.shape[1]
+    pad = x_rows
+    if x_rows.shape[0] != chunk:
+        pad = torch.zeros((chunk, p), dtype=x_rows.dtype, device=x_rows.device)
+        pad[:x_rows.shape[0]] = x_rows
+    out = torch.empty((world * chunk, p), dtype=x_rows.dtype,
+                      device=x_rows.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    return out[:n]
+
+
 class _DeviceOps(object):
     """The CUDA library (default operators)."""
 
