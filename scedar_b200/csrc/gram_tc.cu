@@ -29,11 +29,20 @@
 // are recomputed by the FP64 kernel.
 //
 // Structure (one CTA per SM, 192 threads):
-//   warp 0   TMA producer: per K slab 4 boxes (A_hi, A_lo: 128 x 64 halves;
-//            B_hi, B_lo: 256 x 64) -> 96 KB stage, 2 stages, mbarrier full/empty
-//   warp 1   MMA issuer (one elected lane): per slab 4 k-steps x 3 products of
+//   warp 0   TMA producer: per 32-wide K slab 4 boxes (A_hi, A_lo: 128 rows;
+//            B_hi, B_lo: 256 rows, 64-byte swizzle) -> 48 KB stage, 4 stages,
+//            mbarrier full/empty
+//   warp 1   MMA issuer (one elected lane): per slab 2 k-steps x 3 products of
 //            UMMA 128 x 256 x 16 into one of two 256-column TMEM accumulators;
 //            tcgen05.commit frees the stage / publishes the accumulator
+//   CG = 2   (rows of >= 256 K columns) a cluster of two CTAs owns two row
+//            tiles: tcgen05.mma.cta_group::2 (M = 256) issued by the leader
+//            CTA reads each CTA's A rows and HALF of the B tile from each CTA's
+//            shared memory (32 KB stage, 6 stages); both producers' TMA bytes
+//            are counted on the leader's full barrier
+//            (cp.async.bulk.tensor.cta_group::2), the commits are multicast
+//            to both CTAs' empty / accumulator-full barriers, and both
+//            epilogues arrive on the leader's accumulator-empty barrier
 //   warps 2-5 epilogue, one thread per tile row, TMEM lane quarter = warp % 4:
 //            STORE  tcgen05.ld 32 columns -> metric in float64 -> coalesced
 //                   store of the D tile through shared memory
@@ -51,6 +60,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -61,21 +71,27 @@ namespace scedar {
 namespace {
 
 constexpr int TM = 128, TN = 256, TK = 32;
-constexpr int TSTAGES = 4;
-constexpr int A_BYTES = TM * TK * 2, B_BYTES = TN * TK * 2;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 49152
+constexpr int A_BYTES = TM * TK * 2;
+// CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 a cluster of two CTAs owns
+// two row tiles and each CTA stages only half of the B tile
+constexpr int b_bytes(int cg) { return TN / cg * TK * 2; }
+constexpr int stage_bytes(int cg) { return 2 * A_BYTES + 2 * b_bytes(cg); }  // 48 KB / 32 KB
+constexpr int n_stages(int cg) { return cg == 1 ? 4 : 6; }                   // 192 KB ring
 constexpr int KC = 32;       // candidates kept per row and column split
 constexpr int STG_LD = 33;   // staging row stride of the STORE epilogue (conflict-free)
 constexpr int EPI_BYTES = TM * STG_LD * 8;   // >= TM * KC * 8 (the TOPK lists)
-constexpr int BAR_BYTES = 128;
-constexpr int TC_SMEM = 1024 + TSTAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+constexpr int BAR_BYTES = 256;
+constexpr int TC_SMEM = 1024 + n_stages(1) * stage_bytes(1) + EPI_BYTES + BAR_BYTES;
+static_assert(n_stages(1) * stage_bytes(1) == n_stages(2) * stage_bytes(2), "one ring size");
 constexpr int TC_THREADS = 192;
 constexpr int RR_CH = 64, RR_LD = 65;   // re-rank: genes per chunk, padded row stride
 constexpr int RR_WARPS = 4;
 constexpr int RR_SMEM = RR_WARPS * (32 * RR_LD + RR_CH) * 8;
-constexpr uint32_t IDESC = (1u << 4)                   // accumulator FP32
-                           | ((uint32_t)(TN >> 3) << 17)  // N
-                           | ((uint32_t)(TM >> 4) << 24); // M; A,B = F16 K-major
+constexpr uint32_t idesc(int cg) {
+  return (1u << 4)                              // accumulator FP32
+         | ((uint32_t)(TN >> 3) << 17)          // N
+         | ((uint32_t)((TM * cg) >> 4) << 24);  // M (both CTAs' rows); A,B = F16 K-major
+}
 constexpr unsigned FULL = 0xffffffffu;
 
 struct TcArgs {
@@ -107,17 +123,65 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)4 << 61;              // SWIZZLE_64B
   return d;
 }
+template <int CG>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a), "l"(b), "r"(IDESC), "r"(acc)
-      : "memory");
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc(1)), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc(2)), "r"(acc)
+        : "memory");
 }
+// arrive on `bar` when the MMAs issued so far retire; with CG = 2 on the
+// barrier at the same offset in both CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     bar)
+                 : "memory");
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address) in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
+               ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
+}
+// CG = 2 TMA load: the bytes are counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0,
+                                                 int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -218,7 +282,7 @@ __device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t tad
   }
 }
 
-template <bool TOPK>
+template <bool TOPK, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
@@ -228,8 +292,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
+  constexpr int TSTAGES = n_stages(CG);
+  constexpr int STAGE_BYTES = stage_bytes(CG);
+  constexpr int B_BYTES = b_bytes(CG);
   uint8_t* epi = gbase + TSTAGES * STAGE_BYTES;
   const uint32_t bars = base + TSTAGES * STAGE_BYTES + EPI_BYTES;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
   // barrier slots (8 bytes each): full[4], empty[4], tfull[2], tempty[2]
   const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tfull0 = bars + 16 * TSTAGES,
                  tempty0 = tfull0 + 16;
@@ -244,19 +313,28 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, 128);
+      mbar_init(tempty0 + 8 * s, 128 * CG);   // the epilogue threads of the whole pair
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(const_cast<uint32_t*>(tmem_slot))),
-                 "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_slot))),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_slot))),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -264,16 +342,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   // column tiles of split s for row tiles g, g + groups, ... (see tc_schedule;
   // with groups == row_tiles every CTA owns one row tile and the CTAs resident
   // at one time cover few row tiles, so their A panels stay in L2).
-  const int split = (int)(blockIdx.x % a.splits);
-  const int group = (int)(blockIdx.x / a.splits);
+  const int unit = (int)(blockIdx.x / CG);     // a CTA (CG = 1) or a CTA pair
+  const int split = unit % a.splits;
+  const int group = unit / a.splits;
   const int64_t rt0 = a.row_begin / TM;
   const int64_t CT = (a.n + TN - 1) / TN;
   const int KB = a.kblocks;
   // column tiles of row tile rt handled by this CTA: [J0, J1).  Symmetric
   // STORE: only the tiles that touch the lower triangle (256 J < 128 (I + 1)),
   // split evenly; the heavy (bottom) row tiles are scheduled first.
+  // a.row_tiles counts row units: CG row tiles each
   auto row_tile_of = [&](int rt) -> int64_t {
-    return rt0 + (a.sym ? a.row_tiles - 1 - rt : rt);
+    return rt0 + (int64_t)CG * (a.sym ? a.row_tiles - 1 - rt : rt) + cta_rank;
   };
   auto j_range = [&](int64_t I, int64_t& J0, int64_t& J1) {
     int64_t L = CT;
@@ -297,19 +377,31 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           for (int kb = 0; kb < KB; ++kb, ++it) {
             const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
-            mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
             const uint32_t st = base + s * STAGE_BYTES;
-            tma_load_2d(st, &map_a_hi, kb * TK, i0, full0 + 8 * s);
-            tma_load_2d(st + A_BYTES, &map_a_lo, kb * TK, i0, full0 + 8 * s);
-            tma_load_2d(st + 2 * A_BYTES, &map_b_hi, kb * TK, (int)(J * TN), full0 + 8 * s);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * TK, (int)(J * TN),
-                        full0 + 8 * s);
+            if (CG == 1) {
+              mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+              tma_load_2d(st, &map_a_hi, kb * TK, i0, full0 + 8 * s);
+              tma_load_2d(st + A_BYTES, &map_a_lo, kb * TK, i0, full0 + 8 * s);
+              tma_load_2d(st + 2 * A_BYTES, &map_b_hi, kb * TK, (int)(J * TN), full0 + 8 * s);
+              tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * TK, (int)(J * TN),
+                          full0 + 8 * s);
+            } else {
+              // the leader's barrier counts both CTAs' bytes; each CTA brings its
+              // own A rows and its half of the B tile
+              if (leader) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);
+              const uint32_t lbar = map_to_cta(full0 + 8 * s, 0);
+              const int jb = (int)(J * TN) + (int)cta_rank * (TN / 2);
+              tma_load_2d_pair(st, &map_a_hi, kb * TK, i0, lbar);
+              tma_load_2d_pair(st + A_BYTES, &map_a_lo, kb * TK, i0, lbar);
+              tma_load_2d_pair(st + 2 * A_BYTES, &map_b_hi, kb * TK, jb, lbar);
+              tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES, &map_b_lo, kb * TK, jb, lbar);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       uint32_t it = 0, t = 0;
       int64_t tiles = 0;
       for (int rt = group; rt < a.row_tiles; rt += a.groups) {
@@ -333,13 +425,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint64_t al = umma_desc(st + A_BYTES + kk * 32);
             const uint64_t bh = umma_desc(st + 2 * A_BYTES + kk * 32);
             const uint64_t bl = umma_desc(st + 2 * A_BYTES + B_BYTES + kk * 32);
-            umma_f16(d_tmem, ah, bh, (kb | kk) != 0);
-            umma_f16(d_tmem, ah, bl, 1);
-            umma_f16(d_tmem, al, bh, 1);
+            umma_f16<CG>(d_tmem, ah, bh, (kb | kk) != 0);
+            umma_f16<CG>(d_tmem, ah, bl, 1);
+            umma_f16<CG>(d_tmem, al, bh, 1);
           }
-          umma_commit(empty0 + 8 * s);   // stage reusable once these MMAs retire
+          umma_commit<CG>(empty0 + 8 * s);   // stage reusable once these MMAs retire
         }
-        umma_commit(tfull0 + 8 * acc);   // accumulator complete
+        umma_commit<CG>(tfull0 + 8 * acc);   // accumulator complete
       }
     }
   } else {
@@ -385,7 +477,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           if (ch + 2 < TN / 32) tmem_wait(v0);
         }
         tc_fence_before();
-        mbar_arrive(tempty0 + 8 * acc);
+        if (CG == 1)
+          mbar_arrive(tempty0 + 8 * acc);
+        else
+          mbar_arrive_cluster(map_to_cta(tempty0 + 8 * acc, 0));   // the leader issues the MMAs
       }
       __syncwarp();
       const int64_t rows = a.row_end - a.row_begin;
@@ -443,7 +538,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         tc_fence_before();
-        mbar_arrive(tempty0 + 8 * acc);
+        if (CG == 1)
+          mbar_arrive(tempty0 + 8 * acc);
+        else
+          mbar_arrive_cluster(map_to_cta(tempty0 + 8 * acc, 0));   // the leader issues the MMAs
       }
     }
     if (TOPK) __syncwarp();   // the lists are re-initialised for the next row tile
@@ -451,9 +549,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();   // nobody leaves while the peer may still read its smem / TMEM
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
-                 : "memory");
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(512)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(512)
+                   : "memory");
   }
 }
 
@@ -696,8 +801,47 @@ int encode_map(CUtensorMap* m, const __half* ptr, int64_t rows, int64_t cols, in
 }
 
 struct FastMaps {
-  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;   // boxes of 128 (A) / 256 (B) rows
+  CUtensorMap b_hi_half, b_lo_half;     // B in boxes of 128 rows (CTA pairs)
 };
+
+// CTAs per MMA.  Measured on B200 (tools/fast_knn_bench.py): CTA pairs
+// (cta_group::2, half the B tile per CTA) are 1-8 % faster for long rows
+// (100,000 x 2,000: D 91.9 -> 88.1 ms; 68,579 x 2,000 kNN 61.7 -> 56.8 ms) and
+// 5-13 % slower for one- or two-slab rows (1,000,000 x 50: 394 -> 431 ms), so
+// pairs are used from 256 K columns up.  SCEDAR_B200_TC_CG = 1 | 2 forces one.
+int tc_cta_group(int64_t p64) {
+  const char* e = getenv("SCEDAR_B200_TC_CG");
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return p64 >= 256 ? 2 : 1;
+}
+
+template <bool TOPK, int CG>
+int launch_tc(const FastMaps& m, const TcArgs& a, cudaStream_t s) {
+  auto kern = gram_tc_kernel<TOPK, CG>;
+  SCEDAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  const unsigned grid = (unsigned)((int64_t)a.groups * a.splits * CG);
+  if (CG == 1) {
+    kern<<<grid, TC_THREADS, TC_SMEM, s>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, a);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    SCEDAR_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, m.b_hi_half, m.b_lo_half, a));
+  }
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
 
 // Schedule: S column splits x G groups of row tiles; CTA (g, s) walks the row
 // tiles g, g + G, ...  Measured on B200 (profiles/README.md): a persistent
@@ -806,6 +950,8 @@ static int ensure_fast(const scedar_cells* c, cudaStream_t s, FastState** out) {
   if (rc == SCEDAR_OK) rc = encode_map(&f->maps.a_lo, f->al, f->n256, f->p64, TM);
   if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_hi, f->bh, f->n256, f->p64, TN);
   if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_lo, f->bl, f->n256, f->p64, TN);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_hi_half, f->bh, f->n256, f->p64, TN / 2);
+  if (rc == SCEDAR_OK) rc = encode_map(&f->maps.b_lo_half, f->bl, f->n256, f->p64, TN / 2);
   if (rc != SCEDAR_OK) {
     fast_state_free(f, s);
     return rc;
@@ -840,15 +986,11 @@ int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
   a.ldd = ldd;
   a.sym = symmetric;
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
-  tc_schedule(RT, c->n, 8, &a.splits, &a.groups);
-  a.row_tiles = (int)RT;
-  SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  gram_tc_kernel<false><<<(unsigned)(a.groups * a.splits), TC_THREADS, TC_SMEM, s>>>(
-      f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
-  SCEDAR_CUDA(cudaGetLastError());
-  count_launch();
-  return SCEDAR_OK;
+  const int cg = tc_cta_group(f->p64);
+  const int64_t units = (RT + cg - 1) / cg;
+  tc_schedule(units, c->n, 8, &a.splits, &a.groups);
+  a.row_tiles = (int)units;
+  return cg == 2 ? launch_tc<false, 2>(f->maps, a, s) : launch_tc<false, 1>(f->maps, a, s);
 }
 
 // k + 1 + 8 spare candidates must be re-ranked: up to 64 per cell
@@ -865,8 +1007,10 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   // number of splits, larger k re-ranks 64 drawn from >= 4 splits
   const bool wide = k + 1 + 8 > KC;
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
-  tc_schedule(RT, c->n, wide ? 4 : 1, &a.splits, &a.groups);
-  a.row_tiles = (int)RT;
+  const int cg = tc_cta_group(f->p64);
+  const int64_t units = (RT + cg - 1) / cg;
+  tc_schedule(units, c->n, wide ? 4 : 1, &a.splits, &a.groups);
+  a.row_tiles = (int)units;
   Scratch pk, pi, tau, dk, misc, flags;
   SCEDAR_CHECK(pk.alloc(sizeof(float) * a.splits * rows * KC, s));
   SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * a.splits * rows * KC, s));
@@ -878,11 +1022,7 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   SCEDAR_CUDA(cudaMemsetAsync(flags.ptr, 0, RT + 16, s));
   a.part_key = pk.as<float>();
   a.part_idx = pi.as<int32_t>();
-  SCEDAR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  gram_tc_kernel<true><<<(unsigned)(a.groups * a.splits), TC_THREADS, TC_SMEM, s>>>(
-      f->maps.a_hi, f->maps.a_lo, f->maps.b_hi, f->maps.b_lo, a);
-  SCEDAR_CUDA(cudaGetLastError());
+  SCEDAR_CHECK(cg == 2 ? (launch_tc<true, 2>(f->maps, a, s)) : (launch_tc<true, 1>(f->maps, a, s)));
   unsigned int* err_bits = misc.as<unsigned int>();
   int* n_flagged = reinterpret_cast<int*>(misc.as<unsigned int>() + 1);
   const unsigned rr_grid = (unsigned)((rows + RR_WARPS - 1) / RR_WARPS);
@@ -905,7 +1045,7 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
       tau.as<double>(), dk.as<double>(), err_bits, rows, row_begin, flags.as<unsigned char>(),
       n_flagged);
   SCEDAR_CUDA(cudaGetLastError());
-  count_launch(3);
+  count_launch(2);
   // rows whose candidate margin is too thin are recomputed by the FP64 kernel
   int h_flagged = 0;
   SCEDAR_CUDA(cudaMemcpyAsync(&h_flagged, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
