@@ -79,11 +79,12 @@ constexpr int stage_bytes(int cg) { return 2 * A_BYTES + 2 * b_bytes(cg); }  // 
 constexpr int n_stages(int cg) { return cg == 1 ? 4 : 6; }                   // 192 KB ring
 constexpr int KC = 32;       // candidates kept per row and column split
 constexpr int STG_LD = 33;   // staging row stride of the STORE epilogue (conflict-free)
-constexpr int EPI_BYTES = TM * STG_LD * 8;   // >= TM * KC * 8 (the TOPK lists)
+constexpr int EPI_BYTES = TM * STG_LD * 8;   // == 2 * TM * (KC + 1) * 4 (the TOPK lists)
 constexpr int BAR_BYTES = 256;
 constexpr int TC_SMEM = 1024 + n_stages(1) * stage_bytes(1) + EPI_BYTES + BAR_BYTES;
 static_assert(n_stages(1) * stage_bytes(1) == n_stages(2) * stage_bytes(2), "one ring size");
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;       // producer + MMA + one epilogue group
+constexpr int TC_THREADS_AR = 320;    // ... + a second epilogue group (A-resident mode)
 constexpr int RR_CH = 64, RR_LD = 65;   // re-rank: genes per chunk, padded row stride
 constexpr int RR_WARPS = 4;
 constexpr int RR_SMEM = RR_WARPS * (32 * RR_LD + RR_CH) * 8;
@@ -233,8 +234,13 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   return v;
 }
 
+constexpr int LKC = KC + 1;   // list row stride in shared memory (conflict-free both ways)
+
 // TOPK: one 32-row x 32-column block of accumulators against the per-row
 // thresholds.  Hot path: 32 compares OR-ed into one predicate + one vote.
+// A column with hits re-reads its 32 accumulators from TMEM and the hits are
+// inserted one by one by the whole warp (ballot + shuffle).  (A per-lane
+// insertion path for cold lists was measured and was slower.)
 __device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t taddr, int64_t jbase,
                                            int64_t n, float& tau, float* lkey, int* lidx,
                                            int row0, int lane) {
@@ -251,15 +257,16 @@ __device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t tad
     cm &= cm - 1;
     const float key = __uint_as_float(tmem_ld1(taddr + c));
     const int64_t gj = jbase + c;
-    unsigned m = __ballot_sync(FULL, key < tau && gj < n);
+    const int nj = (int)gj;
+    const bool hit = key < tau && gj < n;
+    unsigned m = __ballot_sync(FULL, hit);
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const float nk = __shfl_sync(FULL, key, src);
-      const int nj = (int)gj;
       // warp-cooperative insert into the sorted list of row row0 + src
-      float* lk_row = lkey + (row0 + src) * KC;
-      int* li_row = lidx + (row0 + src) * KC;
+      float* lk_row = lkey + (row0 + src) * LKC;
+      int* li_row = lidx + (row0 + src) * LKC;
       float lk = lk_row[lane];
       int li = li_row[lane];
       const int pos = __popc(__ballot_sync(FULL, lk < nk || (lk == nk && li < nj)));
@@ -279,11 +286,19 @@ __device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t tad
       const float worst = __shfl_sync(FULL, lk, KC - 1);
       if (lane == src) tau = worst;
     }
+    __syncwarp();
   }
 }
 
-template <bool TOPK, int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// AR ("A resident", CG = 1, at most two K slabs -- e.g. 50 PCs): a tile is then
+// only 12 MMAs, and the single epilogue group (one warp per scheduler, a serial
+// chain of TMEM loads and compares) is what bounds the tile rate.  In this mode
+// the row tile's A panel is loaded once and stays in shared memory, the ring
+// carries only B (3 stages of 32 KB), and the freed shared memory holds a
+// second set of candidate lists for a SECOND epilogue group: group g drains
+// accumulator g (every other tile), so each has two MMA periods per tile.
+template <bool TOPK, int CG, bool AR>
+__global__ void __launch_bounds__(AR ? TC_THREADS_AR : TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi,
@@ -292,18 +307,23 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  constexpr int TSTAGES = n_stages(CG);
-  constexpr int STAGE_BYTES = stage_bytes(CG);
+  static_assert(!(AR && CG == 2), "A-resident mode is single-CTA");
   constexpr int B_BYTES = b_bytes(CG);
-  uint8_t* epi = gbase + TSTAGES * STAGE_BYTES;
-  const uint32_t bars = base + TSTAGES * STAGE_BYTES + EPI_BYTES;
+  constexpr int EG = AR ? 2 : 1;                   // epilogue groups
+  constexpr int TSTAGES = AR ? 3 : n_stages(CG);
+  constexpr int STAGE_BYTES = AR ? 2 * B_BYTES : stage_bytes(CG);
+  constexpr int RING_OFF = AR ? 4 * A_BYTES : 0;   // resident A: 2 slabs x (hi, lo)
+  constexpr int RING_BYTES = AR ? RING_OFF + TSTAGES * STAGE_BYTES : n_stages(1) * stage_bytes(1);
+  static_assert(1024 + RING_BYTES + EG * EPI_BYTES + BAR_BYTES <= TC_SMEM, "smem budget");
+  uint8_t* epi = gbase + RING_BYTES;
+  const uint32_t bars = base + RING_BYTES + EG * EPI_BYTES;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
-  // barrier slots (8 bytes each): full[4], empty[4], tfull[2], tempty[2]
-  const uint32_t full0 = bars, empty0 = bars + 8 * TSTAGES, tfull0 = bars + 16 * TSTAGES,
-                 tempty0 = tfull0 + 16;
+  // barrier slots (8 bytes each): full[<=6], empty[<=6], tfull[2], tempty[2], afull
+  const uint32_t full0 = bars, empty0 = bars + 48, tfull0 = bars + 96, tempty0 = bars + 112,
+                 afull = bars + 128;
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(epi + EPI_BYTES + 16 * TSTAGES + 32);
+      reinterpret_cast<volatile uint32_t*>(epi + EG * EPI_BYTES + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -315,6 +335,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       mbar_init(tfull0 + 8 * s, 1);
       mbar_init(tempty0 + 8 * s, 128 * CG);   // the epilogue threads of the whole pair
     }
+    mbar_init(afull, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -373,12 +394,24 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         const int i0 = (int)(I * TM);
         int64_t J0, J1;
         j_range(I, J0, J1);
+        if (AR) {
+          // one row tile per CTA in this mode (host: groups == row_tiles)
+          mbar_expect_tx(afull, KB * 2 * A_BYTES);
+          for (int kb = 0; kb < KB; ++kb) {
+            tma_load_2d(base + kb * 2 * A_BYTES, &map_a_hi, kb * TK, i0, afull);
+            tma_load_2d(base + kb * 2 * A_BYTES + A_BYTES, &map_a_lo, kb * TK, i0, afull);
+          }
+        }
         for (int64_t J = J0; J < J1; ++J) {
           for (int kb = 0; kb < KB; ++kb, ++it) {
             const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t st = base + s * STAGE_BYTES;
-            if (CG == 1) {
+            const uint32_t st = base + RING_OFF + s * STAGE_BYTES;
+            if (AR) {
+              mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+              tma_load_2d(st, &map_b_hi, kb * TK, (int)(J * TN), full0 + 8 * s);
+              tma_load_2d(st + B_BYTES, &map_b_lo, kb * TK, (int)(J * TN), full0 + 8 * s);
+            } else if (CG == 1) {
               mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
               tma_load_2d(st, &map_a_hi, kb * TK, i0, full0 + 8 * s);
               tma_load_2d(st + A_BYTES, &map_a_lo, kb * TK, i0, full0 + 8 * s);
@@ -409,6 +442,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         j_range(row_tile_of(rt), J0, J1);
         tiles += J1 - J0;
       }
+      if (AR && tiles > 0) mbar_wait(afull, 0);
       for (int64_t tt = 0; tt < tiles; ++tt, ++t) {
         const uint32_t acc = t & 1, aph = (t >> 1) & 1;
         mbar_wait(tempty0 + 8 * acc, aph ^ 1);
@@ -418,13 +452,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
           const uint32_t s = it % TSTAGES, ph = (it / TSTAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t st = base + s * STAGE_BYTES;
+          const uint32_t st = base + RING_OFF + s * STAGE_BYTES;
+          const uint32_t sa = AR ? base + kb * 2 * A_BYTES : st;       // A_hi, then A_lo
+          const uint32_t sb = AR ? st : st + 2 * A_BYTES;              // B_hi, then B_lo
 #pragma unroll
           for (int kk = 0; kk < TK / 16; ++kk) {
-            const uint64_t ah = umma_desc(st + kk * 32);
-            const uint64_t al = umma_desc(st + A_BYTES + kk * 32);
-            const uint64_t bh = umma_desc(st + 2 * A_BYTES + kk * 32);
-            const uint64_t bl = umma_desc(st + 2 * A_BYTES + B_BYTES + kk * 32);
+            const uint64_t ah = umma_desc(sa + kk * 32);
+            const uint64_t al = umma_desc(sa + A_BYTES + kk * 32);
+            const uint64_t bh = umma_desc(sb + kk * 32);
+            const uint64_t bl = umma_desc(sb + B_BYTES + kk * 32);
             umma_f16<CG>(d_tmem, ah, bh, (kb | kk) != 0);
             umma_f16<CG>(d_tmem, ah, bl, 1);
             umma_f16<CG>(d_tmem, al, bh, 1);
@@ -438,7 +474,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     // ---- epilogue warps 2..5: TMEM lane quarter q, one thread per tile row --
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int e = (warp - 2) * 32 + lane;   // 0..127 inside the epilogue group
+    const int eg = (warp - 2) >> 2;         // epilogue group: drains accumulator eg when EG == 2
+    const int e = ((warp - 2) & 3) * 32 + lane;   // 0..127 inside the epilogue group
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t t = 0;
     for (int rt = group; rt < a.row_tiles; rt += a.groups) {
@@ -449,17 +486,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const int64_t gi = i0 + r;
     const bool row_ok = gi >= a.row_begin && gi < a.row_end;
     if (TOPK) {
-      float* lkey = reinterpret_cast<float*>(epi);           // [TM][KC]
-      int* lidx = reinterpret_cast<int*>(epi + TM * KC * 4);  // [TM][KC]
+      float* lkey = reinterpret_cast<float*>(epi + eg * EPI_BYTES);               // [TM][LKC]
+      int* lidx = reinterpret_cast<int*>(epi + eg * EPI_BYTES + TM * LKC * 4);     // [TM][LKC]
       for (int rr = 0; rr < 32; ++rr) {
-        lkey[(q * 32 + rr) * KC + lane] = __int_as_float(0x7f800000);
-        lidx[(q * 32 + rr) * KC + lane] = 0x7fffffff;
+        lkey[(q * 32 + rr) * LKC + lane] = __int_as_float(0x7f800000);
+        lidx[(q * 32 + rr) * LKC + lane] = 0x7fffffff;
       }
       __syncwarp();
       // rows outside the stripe never hit
       float tau = row_ok ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
       for (int64_t J = J0; J < J1; ++J, ++t) {
         const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+        if (EG == 2 && (int)acc != eg) continue;   // the other group's tile
         mbar_wait(tfull0 + 8 * acc, aph);
         tc_fence_after();
         const int64_t j0 = J * TN;
@@ -487,9 +525,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       for (int rr = 0; rr < 32; ++rr) {
         const int64_t g2 = i0 + q * 32 + rr;
         if (g2 < a.row_begin || g2 >= a.row_end) continue;
-        const int64_t o = ((int64_t)split * rows + (g2 - a.row_begin)) * KC;
-        a.part_key[o + lane] = lkey[(q * 32 + rr) * KC + lane];
-        a.part_idx[o + lane] = lidx[(q * 32 + rr) * KC + lane];
+        const int64_t o = ((int64_t)(split * EG + eg) * rows + (g2 - a.row_begin)) * KC;
+        a.part_key[o + lane] = lkey[(q * 32 + rr) * LKC + lane];
+        a.part_idx[o + lane] = lidx[(q * 32 + rr) * LKC + lane];
       }
     } else {
       double* stg = reinterpret_cast<double*>(epi);
@@ -816,13 +854,13 @@ int tc_cta_group(int64_t p64) {
   return p64 >= 256 ? 2 : 1;
 }
 
-template <bool TOPK, int CG>
+template <bool TOPK, int CG, bool AR = false>
 int launch_tc(const FastMaps& m, const TcArgs& a, cudaStream_t s) {
-  auto kern = gram_tc_kernel<TOPK, CG>;
+  auto kern = gram_tc_kernel<TOPK, CG, AR>;
   SCEDAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   const unsigned grid = (unsigned)((int64_t)a.groups * a.splits * CG);
   if (CG == 1) {
-    kern<<<grid, TC_THREADS, TC_SMEM, s>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, a);
+    kern<<<grid, AR ? TC_THREADS_AR : TC_THREADS, TC_SMEM, s>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, a);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1009,11 +1047,16 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   const int cg = tc_cta_group(f->p64);
   const int64_t units = (RT + cg - 1) / cg;
-  tc_schedule(units, c->n, wide ? 4 : 1, &a.splits, &a.groups);
+  // one or two K slabs: A-resident kernel with two epilogue groups, each of
+  // which keeps (and emits) its own lists
+  const bool a_res = cg == 1 && a.kblocks <= 2 && !getenv("SCEDAR_B200_TC_NO_AR");
+  const int lists_per_split = a_res ? 2 : 1;
+  tc_schedule(units, c->n, wide ? 4 / lists_per_split : 1, &a.splits, &a.groups);
   a.row_tiles = (int)units;
+  const int n_lists = a.splits * lists_per_split;
   Scratch pk, pi, tau, dk, misc, flags;
-  SCEDAR_CHECK(pk.alloc(sizeof(float) * a.splits * rows * KC, s));
-  SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * a.splits * rows * KC, s));
+  SCEDAR_CHECK(pk.alloc(sizeof(float) * n_lists * rows * KC, s));
+  SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * n_lists * rows * KC, s));
   SCEDAR_CHECK(tau.alloc(sizeof(double) * rows, s));
   SCEDAR_CHECK(dk.alloc(sizeof(double) * rows, s));
   SCEDAR_CHECK(misc.alloc(16, s));
@@ -1022,7 +1065,10 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   SCEDAR_CUDA(cudaMemsetAsync(flags.ptr, 0, RT + 16, s));
   a.part_key = pk.as<float>();
   a.part_idx = pi.as<int32_t>();
-  SCEDAR_CHECK(cg == 2 ? (launch_tc<true, 2>(f->maps, a, s)) : (launch_tc<true, 1>(f->maps, a, s)));
+  if (a_res)
+    SCEDAR_CHECK((launch_tc<true, 1, true>(f->maps, a, s)));
+  else
+    SCEDAR_CHECK(cg == 2 ? (launch_tc<true, 2>(f->maps, a, s)) : (launch_tc<true, 1>(f->maps, a, s)));
   unsigned int* err_bits = misc.as<unsigned int>();
   int* n_flagged = reinterpret_cast<int*>(misc.as<unsigned int>() + 1);
   const unsigned rr_grid = (unsigned)((rows + RR_WARPS - 1) / RR_WARPS);
@@ -1030,14 +1076,14 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
     SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<2>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
     rerank_kernel<2><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
-        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits,
+        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
         rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
         dk.as<double>());
   } else {
     SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
     rerank_kernel<1><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
-        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, a.splits,
+        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
         rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
         dk.as<double>());
   }
