@@ -780,9 +780,14 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
     for (int m = 0; m < 32; ++m) {
       const double dm = __shfl_sync(FULL, dist[sg], m);
       const int jm = __shfl_sync(FULL, L.i[sg], m);
+      // empty slots all carry (+inf, INT_MAX): their position breaks the tie so
+      // that every entry gets its own rank (and every output slot is written)
 #pragma unroll
-      for (int rg = 0; rg < R; ++rg)
-        if (!(sg == rg && m == lane) && before(dm, jm, dist[rg], L.i[rg])) ++rank[rg];
+      for (int rg = 0; rg < R; ++rg) {
+        const bool same = dm == dist[rg] && jm == L.i[rg];
+        if (before(dm, jm, dist[rg], L.i[rg]) || (same && sg * 32 + m < rg * 32 + lane))
+          ++rank[rg];
+      }
     }
   }
   // scatter through shared memory into sorted order (entry e -> lane e%32, reg e/32)

@@ -493,3 +493,33 @@ def test_fast_path_ties_and_fallback(b200):
         ifa, vfa = cells.knn_stripe(10, EXCLUDE_FIRST, precision="fast")
         assert torch.equal(i64, ifa) and torch.equal(v64, vfa)
         cells.close()
+
+
+@pytest.mark.parametrize("n,p", [(2, 1), (5, 3), (33, 70), (129, 31), (257, 64),
+                                 (300, 256), (513, 257)])
+def test_fast_path_small_and_ragged(b200, n, p):
+    """Tiny and ragged shapes through the tcgen05 kernels (all three tile
+    variants: single CTA, CTA pair from 256 K columns, A-resident up to 64):
+    D within tolerance and bit-symmetric, kNN identical to the FP64 path."""
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200._capi import EXCLUDE_FIRST, EXCLUDE_SELF
+    rng = np.random.default_rng(n * 1000 + p)
+    x = torch.from_numpy(rng.normal(0.0, 1.0, size=(n, p)) + 0.3).cuda()
+    for metric in ("euclidean", "cosine", "correlation"):
+        if metric == "correlation" and p < 2:
+            continue
+        cells = dev.Cells.from_dense(x, metric)
+        d64 = cells.pdist_symmetric()
+        scale = max(d64.max().item(), 1e-300)
+        for d in (cells.pdist_stripe(0, n, precision="fast"),
+                  cells.pdist_symmetric(precision="fast")):
+            assert (d - d64).abs().max().item() / scale <= 1e-4, (metric, n, p)
+            assert float(d.diagonal().abs().max()) == 0.0
+        assert torch.equal(d, d.T)
+        for k in sorted({1, min(15, n - 1), min(40, n - 1)}):
+            for ex in (EXCLUDE_FIRST, EXCLUDE_SELF):
+                i64, v64 = cells.knn_stripe(k, ex)
+                ifa, vfa = cells.knn_stripe(k, ex, precision="fast")
+                assert torch.equal(i64, ifa) and torch.equal(v64, vfa), (metric, n, p, k)
+        cells.close()
