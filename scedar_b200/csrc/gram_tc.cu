@@ -21,8 +21,11 @@
 // d = 1 + acc, and for the top-k a bare compare of the accumulator against
 // the row's threshold.
 //
-// Stated tolerance of the fast distance matrix: |D_fast - D_fp64| <= 1e-4 *
-// max(D) (tests assert it; typical 1e-6).  The fast kNN is EXACT: the
+// Stated tolerance of the fast distance matrix (tests assert it): cosine and
+// correlation |D_fast - D_fp64| <= 1e-5; euclidean |D_fast^2 - D_fp64^2| <=
+// 2e-6 * max |x|^2, i.e. |D_fast - D_fp64| <= 1e-4 * max(D) except between
+// near-duplicate cells, where the square root turns a 1e-6 error of d^2 into
+// up to 1.5e-3 * max |x| of d.  The fast kNN is EXACT: the
 // tensor-core pass only proposes candidates (32 per cell and column split),
 // which are re-ranked with float64 distances computed like the FP64 path and
 // verified against the candidate threshold; cells whose margin is too small

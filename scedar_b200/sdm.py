@@ -58,8 +58,10 @@ class SampleDistanceMatrix(object):
     variable ``SCEDAR_B200_PRECISION``, else ``"fp64"``) selects the Gram
     kernel: ``"fp64"`` matches the reference's float64 to 1e-10;
     ``"fast"`` runs the contraction on the tcgen05 tensor cores -- the
-    distance matrix is then within 1e-4 * max(D), while kNN results stay
-    exact (float64 re-rank of the tensor-core candidates).
+    distance matrix is then within 1e-5 (cosine, correlation) or, for
+    euclidean, within 2e-6 * max|x|^2 on the squared distance (1e-4 * max(D)
+    unless two cells nearly coincide), while kNN results stay exact (float64
+    re-rank of the tensor-core candidates).
     """
     precision = os.environ.get("SCEDAR_B200_PRECISION", "fp64")
 

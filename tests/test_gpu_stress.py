@@ -1,0 +1,78 @@
+"""Seeded randomised stress of the CUDA path: odd shapes, integer data with
+exact ties, duplicated / all-zero / constant rows, random k -- FP64 D against
+the oracle, every kNN route against selection from that D, the tcgen05 route
+against the FP64 route (bit-identical)."""
+import numpy as np
+import pytest
+
+from oracle import sdm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 700))
+    p = int(rng.integers(1, 300))
+    kind = seed % 4
+    if kind == 0:
+        x = rng.normal(0.0, 1.0, size=(n, p))
+    elif kind == 1:
+        x = rng.poisson(0.8, size=(n, p)).astype(np.float64)       # exact ties
+    elif kind == 2:
+        x = np.log1p(rng.poisson(rng.gamma(0.3, 2.0, size=p), size=(n, p)))
+    else:
+        x = rng.uniform(-5.0, 5.0, size=(n, p)) * rng.lognormal(0, 2, size=(n, 1))
+    if n > 6 and seed % 3 == 0:                 # duplicates, a zero and a constant row
+        x[1] = x[0]
+        x[n - 1] = x[n // 2]
+        x[2] = 0.0
+        x[3] = 1.5
+    metric = ("euclidean", "cosine", "correlation")[int(rng.integers(0, 3))]
+    if metric == "correlation" and p < 2:
+        metric = "cosine"
+    k = int(rng.integers(1, min(n - 1, 55) + 1))
+    return x, metric, k
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_random_case(seed):
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200._capi import EXCLUDE_FIRST, EXCLUDE_SELF
+    x, metric, k = make_case(seed)
+    n, p = x.shape
+    cells = dev.Cells.from_dense(torch.from_numpy(x).cuda(), metric)
+    d = cells.pdist_symmetric()
+    dn = d.cpu().numpy()
+    want = orc.pdist(x, metric)
+    scale = max(want.max(), 1e-300)
+    integer = np.array_equal(x, np.round(x))
+    # exactly duplicated non-integer rows: the reference's own value is
+    # cancellation noise; everything else to 1e-10
+    mask = np.ones_like(want, dtype=bool)
+    if metric == "euclidean" and not integer and n > 6 and seed % 3 == 0:
+        for a, b in ((0, 1), (n - 1, n // 2)):
+            mask[a, b] = mask[b, a] = False
+    assert np.abs(dn - want)[mask].max() / scale <= 1e-10, (seed, metric, n, p)
+    assert np.array_equal(dn, dn.T) and not dn.diagonal().any() and (dn >= 0).all()
+    for ex in (EXCLUDE_FIRST, EXCLUDE_SELF):
+        i0, v0 = dev.knn_from_d(d, k, ex)
+        i1, v1 = cells.knn_stripe(k, ex)                      # FP64, auto route
+        assert torch.equal(i0, i1) and torch.equal(v0, v1), (seed, metric, n, p, k, ex)
+        i2, v2 = cells.knn_stripe(k, ex, precision="fast")    # tcgen05 + re-rank
+        assert torch.equal(i0, i2) and torch.equal(v0, v2), (seed, metric, n, p, k, ex)
+    ridx, _ = orc.knn_drop_first(dn, k)
+    assert np.array_equal(dev.knn_from_d(d, k, EXCLUDE_FIRST)[0].cpu().numpy(), ridx)
+    # stated tolerance of the tcgen05 matrix: cosine / correlation 1e-5
+    # absolute; euclidean 2e-6 * max |x|^2 on the SQUARED distance (a square
+    # root near zero turns a 1e-6 error of d^2 into 1e-3 of d: exact duplicates)
+    dfast = cells.pdist_symmetric(precision="fast")
+    if metric == "euclidean":
+        n2max = float((x * x).sum(axis=1).max())
+        err2 = (dfast * dfast - d * d).abs().max().item()
+        assert err2 <= 2e-6 * max(n2max, 1e-300), (seed, metric, n, p, err2, n2max)
+    else:
+        assert (dfast - d).abs().max().item() <= 1e-5, (seed, metric, n, p)
+    assert torch.equal(dfast, dfast.T)
+    cells.close()
