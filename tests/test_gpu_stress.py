@@ -76,3 +76,50 @@ def test_random_case(seed):
         assert (dfast - d).abs().max().item() <= 1e-5, (seed, metric, n, p)
     assert torch.equal(dfast, dfast.T)
     cells.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_stripes_and_csr(seed):
+    """Random row ranges (the multi-GPU stripes) of D and of the kNN lists equal
+    the rows of the whole-matrix result; CSR input equals its densified twin;
+    the consumers agree with the oracle on the same random case."""
+    import scipy.sparse as sps
+    import torch
+    from oracle import knn_oracle as korc
+    from scedar_b200 import SampleDistanceMatrix, device as dev, knn
+    from scedar_b200._capi import EXCLUDE_FIRST, EXCLUDE_SELF
+    rng = np.random.default_rng(1000 + seed)
+    n, p = int(rng.integers(130, 900)), int(rng.integers(2, 200))
+    dens = rng.random((n, p))
+    x = np.where(dens < 0.15, rng.lognormal(0, 1, size=(n, p)), 0.0)
+    x[5] = 0.0
+    x[7] = x[6]
+    metric = ("cosine", "euclidean")[seed % 2]
+    cells = dev.Cells.from_dense(torch.from_numpy(x).cuda(), metric)
+    full = cells.pdist_symmetric()
+    k = int(rng.integers(1, 32))
+    fi, fv = dev.knn_from_d(full, k, EXCLUDE_SELF)
+    for _ in range(3):
+        r0 = int(rng.integers(0, n - 1))
+        r1 = int(rng.integers(r0 + 1, n + 1))
+        assert torch.equal(cells.pdist_stripe(r0, r1), full[r0:r1]), (seed, r0, r1)
+        for prec in ("fp64", "fast"):
+            si, sv = cells.knn_stripe(k, EXCLUDE_SELF, r0, r1, precision=prec)
+            assert torch.equal(si, fi[r0:r1]) and torch.equal(sv, fv[r0:r1]), (seed, prec)
+    cells.close()
+    a = SampleDistanceMatrix(sps.csr_matrix(x), metric=metric)._d
+    assert np.array_equal(a, full.cpu().numpy())
+    # consumers on the same case
+    sdm = SampleDistanceMatrix(x, metric=metric)
+    d = sdm._d
+    kk = min(k, 20)
+    cut = float(np.median(np.sort(d, axis=0)[kk]) * 1.05) or 1e-3
+    res = knn.RareSampleDetection(sdm).detect_rare_samples(kk, cut, 4)[0]
+    assert res == korc.rare_pdist(d, kk, cut, 4)[0]
+    lut = sdm.s_knn_ind_lut(kk)
+    arr = np.array([lut[i] for i in range(n)])
+    n_do = int(rng.integers(1, kk + 1))
+    got = knn.FeatureImputation._impute_features_runner(x, lut, kk, n_do, 0.5, 2)
+    want, idc, _ = korc.impute(x, arr, kk, n_do, 0.5, 2)
+    np.testing.assert_array_equal(got[0], want)
+    np.testing.assert_array_equal(got[1].toarray(), idc)
