@@ -14,7 +14,7 @@ def __getattr__(name):
     if name == "SampleDistanceMatrix":
         from .sdm import SampleDistanceMatrix
         return SampleDistanceMatrix
-    if name in ("device", "sdm", "stripes", "synth", "_capi", "knn"):
+    if name in ("device", "sdm", "stripes", "synth", "_capi", "knn", "patch"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -207,7 +207,13 @@ class SampleDistanceMatrix(object):
     def _device_d(self):
         """D resident in HBM, or None when it is too large to keep."""
         n = self._x.shape[0]
-        if self._d_dev is None and n * n * 8 <= DEVICE_D_CACHE_BYTES:
+        limit = DEVICE_D_CACHE_BYTES
+        if self._d_dev is None and n * n * 8 > limit:
+            # a larger D is still kept (and computed symmetrically, half the
+            # work) when it takes less than half of the free device memory
+            free, _ = torch.cuda.mem_get_info()
+            limit = max(limit, free // 2)
+        if self._d_dev is None and n * n * 8 <= limit:
             if self._lazy_load_d is not None:
                 self._d_dev = dev.to_device(self._lazy_load_d)
             else:
@@ -354,6 +360,8 @@ class SampleDistanceMatrix(object):
         n = self._x.shape[0]
         idx = np.empty((n, k), dtype=np.int64)
         dist = np.empty((n, k), dtype=np.float64)
+        # no D anywhere yet and too large to be worth keeping: kNN without D
+        # (the library still routes through a scratch D when that is cheaper)
         fused = (self._lazy_load_d is None and self._d_dev is None
                  and k <= 31 and n * n * 8 > DEVICE_D_CACHE_BYTES)
         # a tensor-core D is approximate: exact neighbours come from the
