@@ -95,6 +95,11 @@ __device__ __forceinline__ int perm8(int g) { return ((g & 3) << 1) | (g >> 2); 
 
 // Consumer side of the pipeline: acc += A(i0.., :) . B(j0.., :)^T over the whole
 // padded K range.  `it` counts K slabs across tiles (stage = it % STAGES).
+// DIAG_ONLY (the |x|^2 pass): only the 8x8 fragments on the tile's diagonal are
+// contracted -- 4 of the 32 fragments of 4 of the 8 warps -- with the same
+// DMMA sequence per element as the full tile, so the statistic stays
+// bit-identical to the Gram diagonal while the pass becomes load-bound.
+template <bool DIAG_ONLY>
 __device__ __forceinline__ void gram_consume(double (&acc)[MF][NF][2], const double* pipe,
                                              uint32_t full0, uint32_t empty0, int KT,
                                              uint32_t& it) {
@@ -123,10 +128,24 @@ __device__ __forceinline__ void gram_consume(double (&acc)[MF][NF][2], const dou
       for (int mf = 0; mf < MF; ++mf) a[mf] = As[mf * 8 * BK + off[kk]];
 #pragma unroll
       for (int nf = 0; nf < NF; ++nf) b[nf] = Bs[nf * 8 * BK + off[kk]];
+      if (DIAG_ONLY) {
+        // rows wm*64 + mf*8 meet columns wn*32 + nf*8 when mf == (wn & 1) * 4 + nf
+        // in the warps with wn / 2 == wm
+        if ((wn >> 1) == wm) {
 #pragma unroll
-      for (int mf = 0; mf < MF; ++mf)
+          for (int nf = 0; nf < NF; ++nf) {
+            if (wn & 1)
+              dmma(acc[4 + nf][nf], a[4 + nf], b[nf]);
+            else
+              dmma(acc[nf][nf], a[nf], b[nf]);
+          }
+        }
+      } else {
 #pragma unroll
-        for (int nf = 0; nf < NF; ++nf) dmma(acc[mf][nf], a[mf], b[nf]);
+        for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+          for (int nf = 0; nf < NF; ++nf) dmma(acc[mf][nf], a[mf], b[nf]);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * s);   // this warp is done with the slab
@@ -291,7 +310,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
       __syncwarp();
     } else {
       double acc[MF][NF][2];
-      gram_consume(acc, smem, full0, empty0, KT, it);
+      gram_consume<MODE == MODE_DIAG>(acc, smem, full0, empty0, KT, it);
       consumer_sync();  // every slab is consumed: the epilogue tile may alias the ring
 
       if (MODE == MODE_DIAG) {
