@@ -159,6 +159,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         "h"((uint16_t)3)
         : "memory");
 }
+// one lane of a converged warp (the whole warp runs the MMA / TMA loops so
+// that ptxas keeps the descriptor arithmetic in uniform registers; only the
+// asynchronous instructions themselves are issued by the elected lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -437,7 +449,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
+      const bool el = elect_one();
       uint32_t it = 0, t = 0;
       int64_t tiles = 0;
       for (int rt = group; rt < a.row_tiles; rt += a.groups) {
@@ -464,13 +477,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint64_t al = umma_desc(sa + A_BYTES + kk * 32);
             const uint64_t bh = umma_desc(sb + kk * 32);
             const uint64_t bl = umma_desc(sb + B_BYTES + kk * 32);
-            umma_f16<CG>(d_tmem, ah, bh, (kb | kk) != 0);
-            umma_f16<CG>(d_tmem, ah, bl, 1);
-            umma_f16<CG>(d_tmem, al, bh, 1);
+            if (el) {
+              umma_f16<CG>(d_tmem, ah, bh, (kb | kk) != 0);
+              umma_f16<CG>(d_tmem, ah, bl, 1);
+              umma_f16<CG>(d_tmem, al, bh, 1);
+            }
           }
-          umma_commit<CG>(empty0 + 8 * s);   // stage reusable once these MMAs retire
+          if (el) umma_commit<CG>(empty0 + 8 * s);   // stage reusable once these MMAs retire
+          __syncwarp();
         }
-        umma_commit<CG>(tfull0 + 8 * acc);   // accumulator complete
+        if (el) umma_commit<CG>(tfull0 + 8 * acc);   // accumulator complete
+        __syncwarp();
       }
     }
   } else {
