@@ -13,10 +13,14 @@
 // Operands.  The row tile (A) and the column tile (B) are different splits of
 // the same cells, so that the accumulator IS the ranking key / the metric:
 //   cosine, correlation   A = u,            B = -u            acc = -cos
-//   euclidean             A = [s x, 1],     B = [-2 s x, s^2|x|^2]
-//                                           acc = s^2 (|x_c|^2 - 2 x_r.x_c)
-// (u = unit-length row, s = a power of two that brings max |x|^2 under 2^15;
-// the extra K column is one of the padding columns of the 64-wide K slab).
+//   euclidean             A = [s y, 1],     B = [-2 s y, s^2|y|^2]
+//                                           acc = s^2 (|y_c|^2 - 2 y_r.y_c)
+// (u = unit-length row; y = x - column means: distances do not change under a
+// translation, and cells far from the origin would otherwise spend the FP16
+// mantissa on their common offset -- blobs shifted to be non-negative made
+// 68,579 x 2,000 fall back to FP64 almost everywhere; s = a power of two that
+// brings max |y|^2 under 2^15; the extra K column is one of the padding
+// columns of the K slab).
 // The epilogue therefore needs no per-column loads: d^2 = acc / s^2 + |x_r|^2,
 // d = 1 + acc, and for the top-k a bare compare of the accumulator against
 // the row's threshold.
@@ -101,6 +105,7 @@ constexpr unsigned FULL = 0xffffffffu;
 struct TcArgs {
   const double* stat;   // sqrt(1/|x|^2) or |x|^2 (euclid), float64
   const double* scale;  // device: [0] = s, [1] = 1/s^2 (both 1 unless euclid)
+  const double* n2c;    // euclid: |x - mean|^2 of every cell (centred copy), float64
   int64_t n;
   int kblocks;
   int64_t row_begin, row_end;
@@ -552,7 +557,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     } else {
       double* stg = reinterpret_cast<double*>(epi);
       const double inv_s2 = a.scale[1];
-      const double n2_row = (a.euclid && gi < a.n) ? a.stat[gi] : 0.0;
+      const double n2_row = (a.euclid && gi < a.n) ? a.n2c[gi] : 0.0;
       for (int64_t J = J0; J < J1; ++J, ++t) {
         const uint32_t acc = t & 1, aph = (t >> 1) & 1;
         mbar_wait(tfull0 + 8 * acc, aph);
@@ -620,7 +625,55 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
   }
 }
 
-// euclid: s = 2^h with max |x|^2 s^2 < 2^15 (FP16 holds the norm column and
+// euclid: column means of the working copy, deterministic two-stage sum.
+// part: [CM_CHUNKS, p_pad]
+constexpr int CM_CHUNKS = 64;
+__global__ void __launch_bounds__(256)
+colsum_kernel(const double* __restrict__ xw, int64_t n, int64_t p_pad,
+              double* __restrict__ part) {
+  const int64_t c = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;                 // 8 row lanes
+  const int64_t rows_per = (n + CM_CHUNKS - 1) / CM_CHUNKS;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = r0 + rows_per < n ? r0 + rows_per : n;
+  double acc = 0.0;
+  if (c < p_pad)
+    for (int64_t r = r0 + ty; r < r1; r += 8) acc += xw[r * p_pad + c];
+  __shared__ double sm[8][33];
+  sm[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && c < p_pad) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += sm[q][threadIdx.x];
+    part[(int64_t)blockIdx.y * p_pad + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+colmean_kernel(const double* __restrict__ part, int64_t n, int64_t p_pad,
+               double* __restrict__ mu) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p_pad) return;
+  double t = 0.0;
+  for (int q = 0; q < CM_CHUNKS; ++q) t += part[(int64_t)q * p_pad + c];
+  mu[c] = n > 0 ? t / (double)n : 0.0;
+}
+// |x - mu|^2 of every cell (one warp per cell)
+__global__ void __launch_bounds__(256)
+n2c_kernel(const double* __restrict__ xw, const double* __restrict__ mu, int64_t n,
+           int64_t n256, int64_t p, int64_t p_pad, double* __restrict__ n2c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n256) return;
+  double acc = 0.0;
+  if (row < n)
+    for (int64_t c = lane; c < p; c += 32) {
+      const double v = xw[row * p_pad + c] - mu[c];
+      acc = fma(v, v, acc);
+    }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+  if (lane == 0) n2c[row] = acc;
+}
+
+// euclid: s = 2^h with max |y|^2 s^2 < 2^15 (FP16 holds the norm column and
 // every element); scale[0] = s, scale[1] = 1 / s^2.  One block.
 __global__ void __launch_bounds__(1024)
 fast_scale_kernel(const double* __restrict__ stat, int64_t n, int euclid,
@@ -654,7 +707,8 @@ __device__ __forceinline__ void split_half(double v, __half& h, __half& l) {
 // the A- and B-role splits of every cell: ah, al, bh, bl [n256, p64]
 __global__ void __launch_bounds__(256)
 split_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
-             const double* __restrict__ scale, int64_t n, int64_t p, int64_t p_pad,
+             const double* __restrict__ scale, const double* __restrict__ mu,
+             const double* __restrict__ n2c, int64_t n, int64_t p, int64_t p_pad,
              int64_t p64, int euclid, __half* __restrict__ ah, __half* __restrict__ al,
              __half* __restrict__ bh, __half* __restrict__ bl) {
   const int64_t row = blockIdx.x;
@@ -663,7 +717,7 @@ split_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
   if (real) {
     if (euclid) {
       mul = scale[0];
-      n2s = stat[row] * scale[0] * scale[0];
+      n2s = n2c[row] * scale[0] * scale[0];
     } else {
       mul = stat[row];   // sqrt(1/|x|^2): unit length (0 for a zero vector)
     }
@@ -672,7 +726,7 @@ split_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
   for (int64_t c = threadIdx.x; c < p64; c += blockDim.x) {
     double va = 0.0, vb = 0.0;
     if (real && c < p) {
-      va = xw[row * p_pad + c] * mul;
+      va = (xw[row * p_pad + c] - (euclid ? mu[c] : 0.0)) * mul;
       vb = va * bmul;
     } else if (real && euclid && c == p) {   // the augmented K column
       va = 1.0;
@@ -696,7 +750,8 @@ split_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
 template <int R>
 __global__ void __launch_bounds__(32 * RR_WARPS)
 rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
-              const double* __restrict__ scale, int64_t n, int64_t p_pad, int euclid,
+              const double* __restrict__ scale, const double* __restrict__ n2c, int64_t n,
+              int64_t p_pad, int euclid,
               const float* __restrict__ part_key, const int32_t* __restrict__ part_idx,
               int splits, int64_t rows, int64_t row_begin, int k, int exclude,
               int64_t* __restrict__ idx_out, double* __restrict__ dist_out,
@@ -730,8 +785,9 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
     const int last_j = __shfl_sync(FULL, L.i[R - 1], 31);
     if (last_j != 0x7fffffff) t1 = fmin(t1, last);
   }
+  const double n2c_i = euclid ? n2c[gi] : 0.0;
   auto to_metric = [&](double key) {   // approximate key -> margin space
-    return euclid ? fma(key, inv_s2, si) : 1.0 + key;
+    return euclid ? fma(key, inv_s2, n2c_i) : 1.0 + key;
   };
   // exact distance of my candidates: the warp streams 32 candidate rows
   // through shared memory in 64-gene chunks (coalesced 512-byte row segments),
@@ -965,6 +1021,8 @@ struct FastState {
   __half* bh = nullptr;   // B role
   __half* bl = nullptr;
   double* scale = nullptr;  // [2] on the device: s, 1/s^2
+  double* mu = nullptr;     // euclid: column means [p_pad]
+  double* n2c = nullptr;    // euclid: |x - mu|^2 [n256]
   int64_t n256 = 0, p64 = 0;   // p64: K extent, a multiple of the slab width TK
   FastMaps maps;
 };
@@ -977,6 +1035,8 @@ void fast_state_free(void* p, cudaStream_t s) {
   if (f->bh) cudaFreeAsync(f->bh, s);
   if (f->bl) cudaFreeAsync(f->bl, s);
   if (f->scale) cudaFreeAsync(f->scale, s);
+  if (f->mu) cudaFreeAsync(f->mu, s);
+  if (f->n2c) cudaFreeAsync(f->n2c, s);
   delete f;
 }
 
@@ -998,13 +1058,31 @@ static int ensure_fast(const scedar_cells* c, cudaStream_t s, FastState** out) {
   if (e == cudaSuccess) e = cudaMallocAsync(&f->bh, hb, s);
   if (e == cudaSuccess) e = cudaMallocAsync(&f->bl, hb, s);
   if (e == cudaSuccess) e = cudaMallocAsync(&f->scale, 2 * sizeof(double), s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->mu, sizeof(double) * c->p_pad, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&f->n2c, sizeof(double) * f->n256, s);
   if (e != cudaSuccess) {
     cudaGetLastError();
     fast_state_free(f, s);
     return fail(SCEDAR_ERR_NOMEM, std::string("fast-path buffers: ") + cudaGetErrorString(e));
   }
-  fast_scale_kernel<<<1, 1024, 0, s>>>(c->stat, c->n, euclid, f->scale);
-  split_kernel<<<(unsigned)f->n256, 256, 0, s>>>(c->xw, c->stat, f->scale, c->n, c->p, c->p_pad,
+  if (euclid) {
+    Scratch part;
+    int prc = part.alloc(sizeof(double) * CM_CHUNKS * c->p_pad, s);
+    if (prc != SCEDAR_OK) {
+      fast_state_free(f, s);
+      return prc;
+    }
+    colsum_kernel<<<dim3((unsigned)((c->p_pad + 31) / 32), CM_CHUNKS), 256, 0, s>>>(
+        c->xw, c->n, c->p_pad, part.as<double>());
+    colmean_kernel<<<(unsigned)((c->p_pad + 255) / 256), 256, 0, s>>>(part.as<double>(), c->n,
+                                                                     c->p_pad, f->mu);
+    n2c_kernel<<<(unsigned)((f->n256 + 7) / 8), 256, 0, s>>>(c->xw, f->mu, c->n, f->n256, c->p,
+                                                            c->p_pad, f->n2c);
+    count_launch(3);
+  }
+  fast_scale_kernel<<<1, 1024, 0, s>>>(euclid ? f->n2c : c->stat, c->n, euclid, f->scale);
+  split_kernel<<<(unsigned)f->n256, 256, 0, s>>>(c->xw, c->stat, f->scale, f->mu, f->n2c, c->n,
+                                                 c->p, c->p_pad,
                                                  f->p64, euclid, f->ah, f->al, f->bh, f->bl);
   count_launch(2);
   int rc = SCEDAR_OK;
@@ -1029,6 +1107,7 @@ static TcArgs tc_args(const scedar_cells* c, const FastState* f, int64_t row_beg
   TcArgs a{};
   a.stat = c->stat;
   a.scale = f->scale;
+  a.n2c = f->n2c;
   a.n = c->n;
   a.kblocks = (int)(f->p64 / TK);
   a.row_begin = row_begin;
@@ -1101,14 +1180,14 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
     SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<2>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
     rerank_kernel<2><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
-        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
+        c->xw, c->stat, f->scale, f->n2c, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
         rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
         dk.as<double>());
   } else {
     SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
     rerank_kernel<1><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
-        c->xw, c->stat, f->scale, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
+        c->xw, c->stat, f->scale, f->n2c, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
         rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
         dk.as<double>());
   }

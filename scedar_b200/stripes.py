@@ -66,6 +66,10 @@ class _DeviceOps(object):
         from . import device
         return device.Cells.from_dense(x, metric)
 
+    def prepare_csr(self, indptr, indices, data, shape, metric):
+        from . import device
+        return device.Cells.from_csr(indptr, indices, data, shape, metric)
+
     def pdist_stripe(self, cells, r0, r1, out=None):
         return cells.pdist_stripe(r0, r1, out=out)
 
@@ -119,6 +123,37 @@ class StripedDistanceMatrix(object):
     shape : (n, p), needed on ranks that pass x=None.
     broadcast : False when every rank already holds x.
     """
+
+    @classmethod
+    def from_csr(cls, csr, metric="cosine", shape=None, nnz=None, group=None,
+                 src=0, device=None, ops=None, broadcast=True):
+        """CSR cells (cosine / euclidean): ``csr = (indptr int64 [n+1], indices
+        int32 [nnz], data float64 [nnz])`` device tensors on the source rank
+        (None elsewhere; ``shape``, ``nnz`` and ``device`` are then required).
+        The three arrays are broadcast and every rank scatters them into its
+        own dense working copy."""
+        self = cls.__new__(cls)
+        self.ops = ops or _DeviceOps()
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        n, p = shape
+        if csr is None:
+            csr = (torch.empty(n + 1, dtype=torch.int64, device=device),
+                   torch.empty(nnz, dtype=torch.int32, device=device),
+                   torch.empty(nnz, dtype=torch.float64, device=device))
+        if self.world > 1 and broadcast:
+            for t in csr:
+                dist.broadcast(t, src=src, group=group)
+        self.n, self.p = n, p
+        self.d_device = csr[2].device
+        self.metric = metric
+        self.stripes = partition(self.n, self.world)
+        self.row_begin, self.row_end = self.stripes[self.rank]
+        self.cells = self.ops.prepare_csr(csr[0], csr[1], csr[2], (n, p), metric)
+        self.d_stripe = None
+        return self
 
     def __init__(self, x, metric="correlation", shape=None, group=None,
                  src=0, device=None, ops=None, broadcast=True):
