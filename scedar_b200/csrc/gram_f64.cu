@@ -374,7 +374,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
 #pragma unroll
             for (int q = 0; q < BN / 32; ++q) {
               const int c = lane + 32 * q;
-              if (j0 + c < a.n) dst[c] = smem[r * LDT + c];
+              if (j0 + c < a.n) __stcs(dst + c, smem[r * LDT + c]);   // D is write-once: evict first
             }
           }
           if (mirrored) {
@@ -386,7 +386,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
 #pragma unroll
               for (int q = 0; q < BM / 32; ++q) {
                 const int r = lane + 32 * q;
-                if (i0 + r < a.n) dst[r] = smem[r * LDT + c];
+                if (i0 + r < a.n) __stcs(dst + r, smem[r * LDT + c]);
               }
             }
           }
