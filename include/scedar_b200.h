@@ -108,6 +108,19 @@ int scedar_cells_from_csr(const void* indptr, int indptr_is_64,
                           int64_t n, int64_t p, int metric, void* stream,
                           scedar_cells_t** out);
 
+/* Incremental form, for cells that arrive in pieces (e.g. while the host ->
+ * device copy of x is still in flight): scedar_cells_alloc reserves the
+ * working copy, scedar_cells_fill_rows prepares the cells [row_begin, row_end)
+ * from x_rows (pointer to cell row_begin, row stride ldx) exactly as
+ * scedar_cells_from_dense does.  Ranges are 128-aligned (the last one ends at
+ * n) and may be filled in any order; a cell must be filled before a kernel
+ * reads it. */
+int scedar_cells_alloc(int64_t n, int64_t p, int metric, void* stream,
+                       scedar_cells_t** out);
+int scedar_cells_fill_rows(scedar_cells_t* cells, const double* x_rows,
+                           int64_t ldx, int64_t row_begin, int64_t row_end,
+                           void* stream);
+
 /* Stream-ordered on the stream the cells were created on (work that reads the
  * cells on another stream must have been synchronised with it). */
 int scedar_cells_free(scedar_cells_t* cells);
@@ -150,6 +163,15 @@ int scedar_stripe_free(void* dev_ptr);
 int scedar_stripe_export(void* dev_ptr, void* handle64);
 int scedar_stripe_open(const void* handle64, void** peer_ptr);
 int scedar_stripe_close(void* peer_ptr);
+
+/* The rows [row_begin, row_end) of the LOWER triangle (columns <= row) of the
+ * whole matrix d [n, n] (FP64 path), each tile written with its transpose.
+ * It reads only the cells [0, row_end): called for consecutive row ranges in
+ * ascending order it yields the matrix of scedar_pdist_symmetric bit for bit
+ * while later cells are still being uploaded (scedar_cells_fill_rows). */
+int scedar_pdist_lower_rows(const scedar_cells_t* cells, int64_t row_begin,
+                            int64_t row_end, double* d, int64_t ldd,
+                            void* stream);
 
 /* Whole matrix at once, computing only the lower-triangle tiles and writing
  * each tile and its transpose (half the contraction work). */

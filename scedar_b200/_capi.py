@@ -29,6 +29,12 @@ SIGNATURES = {
     "scedar_cells_from_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int, c_void_p,
                                       POINTER(c_void_p)]),
+    "scedar_cells_alloc": (c_int, [c_int64, c_int64, c_int, c_void_p,
+                                   POINTER(c_void_p)]),
+    "scedar_cells_fill_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64,
+                                       c_int64, c_void_p]),
+    "scedar_pdist_lower_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p,
+                                        c_int64, c_void_p]),
     "scedar_cells_free": (c_int, [c_void_p]),
     "scedar_cells_n": (c_int64, [c_void_p]),
     "scedar_cells_p": (c_int64, [c_void_p]),

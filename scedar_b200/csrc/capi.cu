@@ -252,6 +252,39 @@ int scedar_cells_from_csr(const void* indptr, int indptr_is_64, const int32_t* i
   return rc;
 }
 
+int scedar_cells_alloc(int64_t n, int64_t p, int metric, void* stream, scedar_cells_t** out) {
+  return new_cells(n, p, metric, static_cast<cudaStream_t>(stream), out);
+}
+
+int scedar_cells_fill_rows(scedar_cells_t* c, const double* x_rows, int64_t ldx,
+                           int64_t row_begin, int64_t row_end, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (row_begin < 0 || row_end < row_begin || row_end > c->n)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n");
+  if (row_begin % kRowPad != 0 || (row_end % kRowPad != 0 && row_end != c->n))
+    return fail(SCEDAR_ERR_ARG, "row ranges must be 128-aligned (the last one may end at n)");
+  if (row_end == row_begin) return SCEDAR_OK;
+  if (!x_rows && c->p > 0) return fail(SCEDAR_ERR_ARG, "x_rows is NULL");
+  if (ldx < c->p) return fail(SCEDAR_ERR_ARG, "ldx must be >= p");
+  // the range that ends at n also zero-fills the padding cells
+  const int64_t pad_end = row_end == c->n ? c->n_pad : row_end;
+  SCEDAR_CHECK(launch_prep_dense(x_rows, row_end - row_begin, c->p, ldx, c->metric,
+                                 c->xw + row_begin * c->p_pad, pad_end - row_begin, c->p_pad, s));
+  return launch_gram_diag_rows(c, row_begin, pad_end, s);
+}
+
+int scedar_pdist_lower_rows(const scedar_cells_t* c, int64_t row_begin, int64_t row_end,
+                            double* d, int64_t ldd, void* stream) {
+  SCEDAR_CHECK(check_rows(c, row_begin, row_end));
+  if (row_begin % kRowPad != 0)
+    return fail(SCEDAR_ERR_ARG, "row_begin must be 128-aligned");
+  if (row_end == row_begin) return SCEDAR_OK;
+  if (!d) return fail(SCEDAR_ERR_ARG, "d is NULL");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  return launch_gram_lower_rows(c, row_begin, row_end, d, ldd, static_cast<cudaStream_t>(stream));
+}
+
 int scedar_cells_free(scedar_cells_t* c) {
   if (!c) return SCEDAR_OK;
   if (c->fast) fast_state_free(c->fast, c->stream);

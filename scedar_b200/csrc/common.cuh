@@ -83,6 +83,10 @@ int launch_prep_csr(const void* indptr, int indptr_is_64,
 
 // gram_f64.cu
 int launch_gram_diag(const scedar_cells* c, cudaStream_t s);
+int launch_gram_diag_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                          cudaStream_t s);
+int launch_gram_lower_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                           double* d_full, int64_t ldd, cudaStream_t s);
 int launch_gram_stripe(const scedar_cells* c, int64_t row_begin,
                        int64_t row_end, double* d_out, int64_t ldd,
                        cudaStream_t s);

@@ -69,6 +69,10 @@ struct GramArgs {
   int euclid;
   int mirror;  // STORE: tiles above the diagonal of the stripe's own square
                // block are not computed but written as transposes
+  int lower;   // STORE: `out` is the WHOLE matrix (row 0 first); only tiles with
+               // J <= I are computed and every one is mirrored -- the rows of D
+               // can then be produced range by range, in ascending order, while
+               // later cells are still being uploaded
   // STORE over peer memory (world > 1): every off-diagonal tile pair of the
   // WHOLE matrix is computed once, by the owner of one of its two row tiles,
   // and its transpose is stored straight into the other owner's stripe
@@ -249,7 +253,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
     J0 = CT * blockIdx.y / a.splits;
     J1 = CT * (blockIdx.y + 1) / a.splits;
   } else if (MODE == MODE_DIAG) {
-    I = J0 = blockIdx.x;
+    I = J0 = a.row_begin / BM + blockIdx.x;
     J1 = J0 + 1;
   } else {
     const int64_t rt0 = a.row_begin / BM;
@@ -260,7 +264,11 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
     const int64_t rows_here = left < GROUP_ROWS ? left : GROUP_ROWS;
     I = rt0 + grp * GROUP_ROWS + rem % rows_here;
     J = rem / rows_here;
-    if (a.world > 1 && I != J) {
+    if (a.lower) {
+      if (J > I) return;
+      mirrored = J != I;
+      mirror_begin = 0;
+    } else if (a.world > 1 && I != J) {
       // balanced ownership of the pair {I, J}: the higher row tile computes it
       // when I+J is even, the lower one when odd
       const int64_t lo = I < J ? I : J, hi = I < J ? J : I;
@@ -370,7 +378,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
           for (int r = warp; r < BM; r += NCONS / 32) {
             const int64_t gi = i0 + r;
             if (gi < a.row_begin || gi >= a.row_end) continue;
-            double* __restrict__ dst = a.out + (gi - a.row_begin) * a.ldd + j0;
+            double* __restrict__ dst = a.out + (gi - (a.lower ? 0 : a.row_begin)) * a.ldd + j0;
 #pragma unroll
             for (int q = 0; q < BN / 32; ++q) {
               const int c = lane + 32 * q;
@@ -437,11 +445,36 @@ GramArgs base_args(const scedar_cells* c) {
 }  // namespace
 
 int launch_gram_diag(const scedar_cells* c, cudaStream_t s) {
+  return launch_gram_diag_rows(c, 0, c->n_pad, s);
+}
+
+// statistic of the cells [row_begin, row_end) only (128-aligned, padded rows allowed)
+int launch_gram_diag_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                          cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
   GramArgs a = base_args(c);
-  a.row_begin = 0;
-  a.row_end = c->n_pad;
+  a.row_begin = row_begin;
+  a.row_end = row_end;
   a.out = c->stat;
-  return launch<MODE_DIAG>(c, a, dim3((unsigned)(c->n_pad / BM)), s);
+  return launch<MODE_DIAG>(c, a, dim3((unsigned)((row_end - row_begin + BM - 1) / BM)), s);
+}
+
+int launch_gram_lower_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end,
+                           double* d_full, int64_t ldd, cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  GramArgs a = base_args(c);
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.out = d_full;
+  a.ldd = ldd;
+  a.lower = 1;
+  const int64_t RT = (row_end + BM - 1) / BM - row_begin / BM;
+  // column tiles beyond the last row tile of the range are never needed
+  const int64_t CT = (row_end + BN - 1) / BN;
+  const int64_t tiles = RT * CT;
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "range too large for one launch");
+  a.n_pad = CT * BN;   // the tile swizzle walks CT column tiles
+  return launch<MODE_STORE>(c, a, dim3((unsigned)tiles), s);
 }
 
 int launch_gram_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end,

@@ -72,6 +72,36 @@ class Cells(object):
         return cls(h, n, p, metric)
 
     @classmethod
+    def alloc(cls, n, p, metric):
+        """Empty cells to be filled range by range (``fill_rows``)."""
+        _guard()
+        h = ctypes.c_void_p()
+        _capi.check(_capi.load().scedar_cells_alloc(
+            int(n), int(p), METRIC_IDS[metric], _stream(), ctypes.byref(h)))
+        return cls(h, n, p, metric)
+
+    def fill_rows(self, x_rows, row_begin):
+        """Prepare the cells [row_begin, row_begin + len(x_rows)) from a
+        float64 device tensor (128-aligned ranges, the last one ends at n)."""
+        x_rows = _f64(x_rows)
+        if x_rows.dim() != 2 or x_rows.shape[1] != self.p:
+            raise ValueError("x_rows has shape (rows, n_features)")
+        if x_rows.stride(1) != 1 and self.p > 1:
+            x_rows = x_rows.contiguous()
+        ldx = x_rows.stride(0) if x_rows.shape[0] > 1 else max(self.p, 1)
+        _capi.check(_capi.load().scedar_cells_fill_rows(
+            self._h, _ptr(x_rows), max(ldx, self.p), int(row_begin),
+            int(row_begin) + x_rows.shape[0], _stream()))
+
+    def pdist_lower_rows(self, row_begin, row_end, out):
+        """Rows [row_begin, row_end) of the lower triangle of the whole
+        matrix ``out`` [n, n], mirrored; needs the cells [0, row_end) only."""
+        _capi.check(_capi.load().scedar_pdist_lower_rows(
+            self._h, int(row_begin), int(row_end), _ptr(out),
+            out.stride(0) if self.n > 1 else self.n, _stream()))
+        return out
+
+    @classmethod
     def from_csr(cls, indptr, indices, data, shape, metric):
         _guard()
         lib = _capi.load()
@@ -389,3 +419,54 @@ def impute_iter(x_curr, knn, n_do_i, min_present_val, it, x_next, idc,
         float(min_present_val), int(it), int(row_begin),
         int(n if row_end is None else row_end), _ptr(x_next), max(p, 1),
         _ptr(idc), max(p, 1), _ptr(stats), _stream()))
+
+
+def upload_ranges(n, first=2048):
+    """128-aligned row ranges that double in size: the first is small so the
+    contraction starts almost at once, every later range is uploaded while the
+    (longer) contraction of the previous ones runs."""
+    out, b = [], 0
+    e = min(n, max(128, first // 128 * 128))
+    while b < n:
+        out.append((b, e))
+        b, e = e, min(n, 2 * e)
+    return out
+
+
+def pdist_symmetric_from_host(x_host, metric, out=None, x_dev=None):
+    """FP64 distance matrix of a pinned HOST matrix with the upload hidden
+    behind the contraction: x is copied range by range on a second stream,
+    each range is prepared (K1 + diagonal) as it lands and the rows of the
+    lower triangle it completes are contracted and mirrored at once
+    (``scedar_pdist_lower_rows``) -- the result is bit-identical to
+    ``Cells.from_dense(x).pdist_symmetric()``.  Returns (cells, d)."""
+    _guard()
+    assert x_host.dtype == torch.float64 and x_host.dim() == 2
+    n, p = x_host.shape
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    if x_dev is None:
+        x_dev = torch.empty((n, p), dtype=torch.float64, device="cuda")
+    main = torch.cuda.current_stream()
+    copy = _copy_stream()
+    copy.wait_stream(main)          # x_dev may still be read by earlier work
+    cells = Cells.alloc(n, p, metric)
+    for b, e in upload_ranges(n):
+        with torch.cuda.stream(copy):
+            x_dev[b:e].copy_(x_host[b:e], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(copy)
+        main.wait_event(landed)
+        cells.fill_rows(x_dev[b:e], b)
+        cells.pdist_lower_rows(b, e, out)
+    return cells, out
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream():
+    d = torch.cuda.current_device()
+    if d not in _COPY_STREAMS:
+        _COPY_STREAMS[d] = torch.cuda.Stream(device=d)
+    return _COPY_STREAMS[d]

@@ -125,6 +125,30 @@ class StripedDistanceMatrix(object):
     """
 
     @classmethod
+    def from_host(cls, x_host, metric="correlation", out=None, x_dev=None,
+                  ops=None):
+        """Single-GPU form for a pinned HOST matrix: the upload of x is hidden
+        behind the contraction (``device.pdist_symmetric_from_host``); on
+        return the cells are prepared and D (float64, symmetric) is already
+        being computed into ``out``.  With several ranks use the row-sharded
+        upload (``gather_x``) and the regular constructor instead."""
+        if dist.is_available() and dist.is_initialized() and \
+                dist.get_world_size() > 1:
+            raise ValueError("from_host is the single-GPU form")
+        from . import device
+        self = cls.__new__(cls)
+        self.ops = ops or _DeviceOps()
+        self.group, self.distributed, self.rank, self.world = None, False, 0, 1
+        self.n, self.p = x_host.shape
+        self.metric = metric
+        self.stripes = partition(self.n, 1)
+        self.row_begin, self.row_end = self.stripes[0]
+        self.cells, self.d_stripe = device.pdist_symmetric_from_host(
+            x_host, metric, out=out, x_dev=x_dev)
+        self.d_device = self.d_stripe.device
+        return self
+
+    @classmethod
     def from_csr(cls, csr, metric="cosine", shape=None, nnz=None, group=None,
                  src=0, device=None, ops=None, broadcast=True):
         """CSR cells (cosine / euclidean): ``csr = (indptr int64 [n+1], indices
