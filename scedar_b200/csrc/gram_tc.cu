@@ -67,6 +67,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -117,6 +118,8 @@ struct TcArgs {
   int64_t ldd;
   int sym;              // STORE over the whole matrix: column tiles wholly above
                         // the diagonal are skipped and written as transposes
+  int kc;               // TOPK: list entries that count (<= KC): the row threshold is
+                        // entry kc - 1; shorter lists for small k mean fewer inserts
   float* part_key;      // TOPK: [splits, rows, KC]
   int32_t* part_idx;
 };
@@ -263,7 +266,7 @@ constexpr int LKC = KC + 1;   // list row stride in shared memory (conflict-free
 // insertion path for cold lists was measured and was slower.)
 __device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t taddr, int64_t jbase,
                                            int64_t n, float& tau, float* lkey, int* lidx,
-                                           int row0, int lane) {
+                                           int row0, int lane, int kc) {
   bool any = false;
 #pragma unroll
   for (int c = 0; c < 32; ++c) any |= __uint_as_float(v[c]) < tau;
@@ -303,7 +306,7 @@ __device__ __forceinline__ void scan_block(const uint32_t (&v)[32], uint32_t tad
         lk_row[lane] = lk;
         li_row[lane] = li;
       }
-      const float worst = __shfl_sync(FULL, lk, KC - 1);
+      const float worst = __shfl_sync(FULL, lk, kc - 1);
       if (lane == src) tau = worst;
     }
     __syncwarp();
@@ -532,11 +535,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
 #pragma unroll
         for (int ch = 0; ch < TN / 32; ch += 2) {
           tmem_ld32_async(tile + (ch + 1) * 32, v1);
-          scan_block(v0, tile + ch * 32, j0 + ch * 32, a.n, tau, lkey, lidx, q * 32, lane);
+          scan_block(v0, tile + ch * 32, j0 + ch * 32, a.n, tau, lkey, lidx, q * 32, lane, a.kc);
           tmem_wait(v1);
           if (ch + 2 < TN / 32) tmem_ld32_async(tile + (ch + 2) * 32, v0);
           scan_block(v1, tile + (ch + 1) * 32, j0 + (ch + 1) * 32, a.n, tau, lkey, lidx, q * 32,
-                     lane);
+                     lane, a.kc);
           if (ch + 2 < TN / 32) tmem_wait(v0);
         }
         tc_fence_before();
@@ -551,8 +554,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         const int64_t g2 = i0 + q * 32 + rr;
         if (g2 < a.row_begin || g2 >= a.row_end) continue;
         const int64_t o = ((int64_t)(split * EG + eg) * rows + (g2 - a.row_begin)) * KC;
-        a.part_key[o + lane] = lkey[(q * 32 + rr) * LKC + lane];
-        a.part_idx[o + lane] = lidx[(q * 32 + rr) * LKC + lane];
+        // entries beyond kc were kept sorted but never thresholded: not a
+        // complete set, so they are not handed on
+        const bool keep = lane < a.kc;
+        a.part_key[o + lane] = keep ? lkey[(q * 32 + rr) * LKC + lane] : __int_as_float(0x7f800000);
+        a.part_idx[o + lane] = keep ? lidx[(q * 32 + rr) * LKC + lane] : 0x7fffffff;
       }
     } else {
       double* stg = reinterpret_cast<double*>(epi);
@@ -753,7 +759,7 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
               const double* __restrict__ scale, const double* __restrict__ n2c, int64_t n,
               int64_t p_pad, int euclid,
               const float* __restrict__ part_key, const int32_t* __restrict__ part_idx,
-              int splits, int64_t rows, int64_t row_begin, int k, int exclude,
+              int splits, int kc, int64_t rows, int64_t row_begin, int k, int exclude,
               int64_t* __restrict__ idx_out, double* __restrict__ dist_out,
               unsigned int* __restrict__ err_bits, double* __restrict__ tau_out,
               double* __restrict__ dk_out) {
@@ -773,8 +779,8 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
     const int64_t o = ((int64_t)s * rows + row) * KC;
     const float kf = part_key[o + lane];
     const int j = part_idx[o + lane];
-    const double last = __shfl_sync(FULL, (double)kf, KC - 1);
-    const int last_j = __shfl_sync(FULL, j, KC - 1);
+    const double last = __shfl_sync(FULL, (double)kf, kc - 1);
+    const int last_j = __shfl_sync(FULL, j, kc - 1);
     if (last_j != 0x7fffffff) t1 = fmin(t1, last);
     L.offer((double)kf, j, j != 0x7fffffff, 32 * R, lane);
   }
@@ -1148,6 +1154,9 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   // lists hold 32 candidates per split: k + 1 + 8 <= 32 is served by any
   // number of splits, larger k re-ranks 64 drawn from >= 4 splits
   const bool wide = k + 1 + 8 > KC;
+  // k + 1 results + 8 spare candidates per list, at least 16
+  a.kc = wide ? KC : std::max(16, k + 1 + 8);
+  if (getenv("SCEDAR_B200_TC_KC32")) a.kc = KC;
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   const int cg = tc_cta_group(f->p64);
   const int64_t units = (RT + cg - 1) / cg;
@@ -1180,14 +1189,14 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
     SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<2>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
     rerank_kernel<2><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
-        c->xw, c->stat, f->scale, f->n2c, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
+        c->xw, c->stat, f->scale, f->n2c, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists, a.kc,
         rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
         dk.as<double>());
   } else {
     SCEDAR_CUDA(cudaFuncSetAttribute(rerank_kernel<1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RR_SMEM));
     rerank_kernel<1><<<rr_grid, 32 * RR_WARPS, RR_SMEM, s>>>(
-        c->xw, c->stat, f->scale, f->n2c, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists,
+        c->xw, c->stat, f->scale, f->n2c, c->n, c->p_pad, a.euclid, a.part_key, a.part_idx, n_lists, a.kc,
         rows, row_begin, k, exclude, idx_out, dist_out, err_bits, tau.as<double>(),
         dk.as<double>());
   }
