@@ -78,6 +78,61 @@ class OracleOps(object):
         stats[1] = int(sub.any(axis=1).sum())
 
 
+    def prepare_csr(self, indptr, indices, data, shape, metric):
+        import scipy.sparse as sps
+        from oracle import sdm_oracle as orc
+        m = sps.csr_matrix((data.numpy(), indices.numpy(), indptr.numpy()), shape=shape)
+        return {"d": orc.pdist(m, metric)}
+
+
+def _input_worker(rank, world, port, n, p, k, q):
+    """gather_x (row shards of x -> full x on every rank) and the CSR entry."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sps
+        from oracle import sdm_oracle as orc
+        from scedar_b200.stripes import (StripedDistanceMatrix, gather_x,
+                                         shard_rows)
+        rng = np.random.default_rng(9)
+        xn = rng.random((n, p))
+        b, e = shard_rows(n, world)[rank]
+        full = gather_x(torch.from_numpy(xn[b:e].copy()), n)
+        ok_gather = bool(np.array_equal(full.numpy(), xn))
+        xs = sps.random(n, p, density=0.2, format="csr", random_state=3).astype(np.float64)
+        csr = None
+        if rank == 0:
+            csr = (torch.from_numpy(xs.indptr.astype(np.int64)),
+                   torch.from_numpy(xs.indices.astype(np.int32)),
+                   torch.from_numpy(xs.data.copy()))
+        sdm = StripedDistanceMatrix.from_csr(csr, "cosine", shape=(n, p), nnz=xs.nnz,
+                                             device="cpu", ops=OracleOps())
+        idx, dd = sdm.knn(k, exclude=1)
+        ridx, rdist = orc.knns_precomputed(orc.pdist(xs, "cosine"), k)
+        ok_csr = bool(np.array_equal(idx.numpy(), ridx) and np.array_equal(dd.numpy(), rdist))
+        q.put((rank, ok_gather, ok_csr))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_inputs():
+    world, n, p, k = 2, 301, 9, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_input_worker, args=(r, world, port, n, p, k, q))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(g[1] is True and g[2] is True for g in got), got
+
+
 def _consumer_worker(rank, world, port, n, p, k, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
