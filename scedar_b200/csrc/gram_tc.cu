@@ -1154,8 +1154,11 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   // lists hold 32 candidates per split: k + 1 + 8 <= 32 is served by any
   // number of splits, larger k re-ranks 64 drawn from >= 4 splits
   const bool wide = k + 1 + 8 > KC;
-  // k + 1 results + 8 spare candidates per list, at least 16
-  a.kc = wide ? KC : std::max(16, k + 1 + 8);
+  // k + 1 results + 16 spare candidates per list: 8 spare were measured to be
+  // too few on log-count data (near-ties at the threshold: the margin check
+  // sent a third of the 100,000 x 2,000 bench workload to the FP64 fallback,
+  // 117 -> 182 ms), so k = 15 keeps full 32-entry lists
+  a.kc = wide ? KC : std::min(KC, k + 1 + 16);
   if (getenv("SCEDAR_B200_TC_KC32")) a.kc = KC;
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   const int cg = tc_cta_group(f->p64);
