@@ -95,6 +95,9 @@ int launch_gram_stripe_p2p(const scedar_cells* c, int rank, int world,
                            int64_t ldd, cudaStream_t s);
 int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
                           cudaStream_t s);
+int launch_gram_gathered(const scedar_cells* c, const double* g, const int64_t* row_ids,
+                         int64_t m, int64_t m_pad, double* d_out, int64_t ldd,
+                         cudaStream_t s);
 // fused Gram -> top-K; part_d/part_i: [splits, rows, K] partial lists
 int gram_topk_splits(const scedar_cells* c, int64_t rows);
 int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,
@@ -118,7 +121,8 @@ int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin
 // topk.cu
 int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols,
                        int64_t row_begin, int64_t row_end, int k, int exclude,
-                       int64_t* idx_out, double* dist_out, cudaStream_t s);
+                       int64_t* idx_out, double* dist_out, cudaStream_t s,
+                       const int64_t* row_ids = nullptr, int64_t out_base = 0);
 int launch_topk_merge(const double* part_d, const int32_t* part_i, int splits,
                       int64_t rows, int K, int64_t row_begin, int k,
                       int exclude, int64_t* idx_out, double* dist_out,
@@ -147,6 +151,8 @@ int launch_compact_alive(const uint8_t* alive, int64_t n, int64_t* sel,
 int launch_gather_rows(const double* x, int64_t ldx, int64_t p,
                        const int64_t* sel, int64_t m, double* out, int64_t ldo,
                        cudaStream_t s);
+int launch_flag_to_ids(const uint8_t* flag, int64_t n, int64_t id0, int64_t* ids,
+                       int64_t m, int64_t ids_cap, cudaStream_t s);
 int launch_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        const int64_t* knn, int k, int n_do_i, double min_present,
                        int iter, int64_t row_begin, int64_t row_end,

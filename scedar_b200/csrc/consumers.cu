@@ -398,6 +398,28 @@ int launch_compact_alive(const uint8_t* alive, int64_t n, int64_t* sel, cudaStre
   return SCEDAR_OK;
 }
 
+namespace {
+// ids[0..m) += id0 (local row -> cell index), ids[m..cap) = -1 (padding)
+__global__ void __launch_bounds__(256)
+ids_fix_kernel(int64_t* __restrict__ ids, int64_t m, int64_t cap, int64_t id0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  ids[i] = i < m ? ids[i] + id0 : -1;
+}
+}  // namespace
+
+// flagged rows of a stripe -> ascending cell indices (m of them, known to the
+// host), padded with -1 up to ids_cap
+int launch_flag_to_ids(const uint8_t* flag, int64_t n, int64_t id0, int64_t* ids, int64_t m,
+                       int64_t ids_cap, cudaStream_t s) {
+  if (ids_cap <= 0) return SCEDAR_OK;
+  SCEDAR_CHECK(launch_compact_alive(flag, n, ids, s));
+  ids_fix_kernel<<<(unsigned)((ids_cap + 255) / 256), 256, 0, s>>>(ids, m, ids_cap, id0);
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
 int launch_gather_rows(const double* x, int64_t ldx, int64_t p, const int64_t* sel, int64_t m,
                        double* out, int64_t ldo, cudaStream_t s) {
   if (m <= 0 || p <= 0) return SCEDAR_OK;

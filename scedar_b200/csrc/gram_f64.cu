@@ -69,6 +69,9 @@ struct GramArgs {
   int euclid;
   int mirror;  // STORE: tiles above the diagonal of the stripe's own square
                // block are not computed but written as transposes
+  const int64_t* row_ids;  // STORE over gathered rows: the A panels come from a second
+                           // matrix (its own tensor map) whose row r is cell
+                           // row_ids[r] (-1: padding); D rows stay in gathered order
   int lower;   // STORE: `out` is the WHOLE matrix (row 0 first); only tiles with
                // J <= I are computed and every one is mirrored -- the rows of D
                // can then be produced range by range, in ascending order, while
@@ -158,15 +161,15 @@ __device__ __forceinline__ void gram_consume(double (&acc)[MF][NF][2], const dou
 
 // Producer side (one lane of the producer warp): stream the K slabs of row
 // panels i0 and j0 through the stage ring.
-__device__ __forceinline__ void gram_produce(const CUtensorMap* map, uint32_t pipe_u32,
-                                             uint32_t full0, uint32_t empty0, int KT,
-                                             int64_t i0, int64_t j0, uint32_t& it) {
+__device__ __forceinline__ void gram_produce(const CUtensorMap* amap, const CUtensorMap* map,
+                                             uint32_t pipe_u32, uint32_t full0, uint32_t empty0,
+                                             int KT, int64_t i0, int64_t j0, uint32_t& it) {
   for (int kt = 0; kt < KT; ++kt, ++it) {
     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
     mbar_wait(empty0 + 8 * s, ph ^ 1);
     mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
     const uint32_t st = pipe_u32 + s * STAGE_BYTES;
-    tma_load_2d(st, map, kt * BK, (int)i0, full0 + 8 * s);
+    tma_load_2d(st, amap, kt * BK, (int)i0, full0 + 8 * s);
     tma_load_2d(st + PANEL_DOUBLES * 8, map, kt * BK, (int)j0, full0 + 8 * s);
   }
 }
@@ -179,13 +182,19 @@ __device__ __forceinline__ void consumer_sync() {
 template <bool RAW>
 __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], double* T,
                                              const double* __restrict__ stat,
-                                             int64_t i0, int64_t j0, int euclid) {
+                                             int64_t i0, int64_t j0, int euclid,
+                                             const int64_t* __restrict__ row_ids = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N, g = lane >> 2, t = lane & 3;
   double sr[8], sc[4][2];
+  int64_t rid[8];   // cell index of the tile rows (gathered rows: through row_ids)
   if (!RAW) {
 #pragma unroll
-    for (int mf = 0; mf < 8; ++mf) sr[mf] = __ldg(stat + i0 + wm * 64 + mf * 8 + perm8(g));
+    for (int mf = 0; mf < 8; ++mf) {
+      const int64_t lr = i0 + wm * 64 + mf * 8 + perm8(g);
+      rid[mf] = row_ids ? row_ids[lr] : lr;
+      sr[mf] = rid[mf] >= 0 ? __ldg(stat + rid[mf]) : 0.0;
+    }
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
       sc[nf][0] = __ldg(stat + j0 + wn * 32 + nf * 8 + perm8(2 * t));
@@ -195,7 +204,7 @@ __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], doubl
 #pragma unroll
   for (int mf = 0; mf < 8; ++mf) {
     const int r = wm * 64 + mf * 8 + perm8(g);   // fragment row -> tile row
-    const int64_t gi = i0 + r;
+    const int64_t gi = RAW ? i0 + r : rid[mf];
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
 #pragma unroll
@@ -231,7 +240,8 @@ __device__ __forceinline__ void warp_insert(double& ld, int& li, double d, int j
 
 template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
-gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
+gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap,
+                const GramArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // the TMA swizzle needs 1 KB alignment
@@ -314,7 +324,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
   for (J = J0; J < J1; ++J) {
     const int64_t j0 = J * BN;
     if (producer) {
-      if (lane == 0) gram_produce(&xmap, base, full0, empty0, KT, i0, j0, it);
+      if (lane == 0) gram_produce(&amap, &xmap, base, full0, empty0, KT, i0, j0, it);
       __syncwarp();
     } else {
       double acc[MF][NF][2];
@@ -336,7 +346,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
           a.out[i0 + tid] = sv;
         }
       } else {
-        tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid);
+        tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid, a.row_ids);
         consumer_sync();
         if (MODE == MODE_TOPK) {
           // warp w scans rows w, w+8, ...; lane l holds entry l of the row's list
@@ -421,11 +431,12 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const GramArgs a) {
 }
 
 template <int MODE>
-int launch(const scedar_cells* c, const GramArgs& a, dim3 grid, cudaStream_t s) {
+int launch(const scedar_cells* c, const GramArgs& a, dim3 grid, cudaStream_t s,
+           const CUtensorMap* amap = nullptr) {
   const int smem_bytes = SMEM_BASE + (MODE == MODE_TOPK ? LIST_BYTES : 0);
   SCEDAR_CUDA(cudaFuncSetAttribute(gram_f64_kernel<MODE>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  gram_f64_kernel<MODE><<<grid, NT, smem_bytes, s>>>(c->xmap, a);
+  gram_f64_kernel<MODE><<<grid, NT, smem_bytes, s>>>(c->xmap, amap ? *amap : c->xmap, a);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
   return SCEDAR_OK;
@@ -523,6 +534,28 @@ int launch_gram_stripe_p2p(const scedar_cells* c, int rank, int world,
   const int64_t tiles = RT * (c->n_pad / BN);
   if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "stripe too large for one launch");
   return launch<MODE_STORE>(c, a, dim3((unsigned)tiles), s);
+}
+
+// D rows of an arbitrary set of cells: g [m_pad, p_pad] holds the working-copy
+// rows of the cells row_ids[0..m) (zero rows / -1 beyond m, m_pad a multiple of
+// 128); d_out [m, n] row r = distances of cell row_ids[r] to every cell, each
+// entry bit-identical to the same entry of the whole matrix.
+int launch_gram_gathered(const scedar_cells* c, const double* g, const int64_t* row_ids,
+                         int64_t m, int64_t m_pad, double* d_out, int64_t ldd, cudaStream_t s) {
+  if (m <= 0) return SCEDAR_OK;
+  CUtensorMap gmap;
+  SCEDAR_CHECK(encode_tensor_map(&gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, g, m_pad, c->p_pad,
+                                 128, 16));
+  GramArgs a = base_args(c);
+  a.row_begin = 0;
+  a.row_end = m;
+  a.out = d_out;
+  a.ldd = ldd;
+  a.row_ids = row_ids;
+  const int64_t RT = (m + BM - 1) / BM;
+  const int64_t tiles = RT * (c->n_pad / BN);
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "too many rows for one launch");
+  return launch<MODE_STORE>(c, a, dim3((unsigned)tiles), s, &gmap);
 }
 
 int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,

@@ -906,7 +906,8 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
 __global__ void __launch_bounds__(256)
 margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
               const unsigned int* __restrict__ err_bits, int64_t rows, int64_t row_begin,
-              unsigned char* __restrict__ tile_flag, int* __restrict__ n_flagged) {
+              unsigned char* __restrict__ tile_flag, unsigned char* __restrict__ row_flag,
+              int* __restrict__ n_flagged) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   // a cell that was not re-ranked has approximate metric >= tau, hence exact
@@ -914,7 +915,9 @@ margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
   // relative term keeps two squared distances that pass apart after sqrt)
   const double d = dk[row];
   const double eps = 8.0 * (double)__uint_as_float(*err_bits) + 1e-12 * (d > 1.0 ? d : 1.0);
-  if (!(d + eps < tau[row])) {
+  const bool bad = !(d + eps < tau[row]);
+  row_flag[row] = bad;
+  if (bad) {
     tile_flag[(row_begin + row) / 128 - row_begin / 128] = 1;
     atomicAdd(n_flagged, 1);
   }
@@ -1154,11 +1157,14 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   // lists hold 32 candidates per split: k + 1 + 8 <= 32 is served by any
   // number of splits, larger k re-ranks 64 drawn from >= 4 splits
   const bool wide = k + 1 + 8 > KC;
-  // k + 1 results + 16 spare candidates per list: 8 spare were measured to be
-  // too few on log-count data (near-ties at the threshold: the margin check
-  // sent a third of the 100,000 x 2,000 bench workload to the FP64 fallback,
-  // 117 -> 182 ms), so k = 15 keeps full 32-entry lists
-  a.kc = wide ? KC : std::min(KC, k + 1 + 16);
+  // k + 1 results + 8 spare candidates per list (fewer list entries = fewer
+  // inserts).  On data with near-ties at the threshold (log counts) some cells
+  // then fail the margin check; they are recomputed row by row below, which
+  // costs nothing measurable (100,000 x 2,000: 112 ms with 8 spare, 114 ms with
+  // 16; with the tile-granular fallback 8 spare cost 158-182 ms).
+  int spare = 8;
+  if (const char* e = getenv("SCEDAR_B200_TC_SPARE")) spare = std::max(1, atoi(e));
+  a.kc = wide ? KC : std::min(KC, k + 1 + spare);
   if (getenv("SCEDAR_B200_TC_KC32")) a.kc = KC;
   const int64_t RT = (row_end + TM - 1) / TM - row_begin / TM;
   const int cg = tc_cta_group(f->p64);
@@ -1170,7 +1176,8 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   tc_schedule(units, c->n, wide ? 4 / lists_per_split : 1, &a.splits, &a.groups);
   a.row_tiles = (int)units;
   const int n_lists = a.splits * lists_per_split;
-  Scratch pk, pi, tau, dk, misc, flags;
+  Scratch pk, pi, tau, dk, misc, flags, rflags;
+  SCEDAR_CHECK(rflags.alloc((size_t)rows + 16, s));
   SCEDAR_CHECK(pk.alloc(sizeof(float) * n_lists * rows * KC, s));
   SCEDAR_CHECK(pi.alloc(sizeof(int32_t) * n_lists * rows * KC, s));
   SCEDAR_CHECK(tau.alloc(sizeof(double) * rows, s));
@@ -1205,7 +1212,7 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   }
   margin_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
       tau.as<double>(), dk.as<double>(), err_bits, rows, row_begin, flags.as<unsigned char>(),
-      n_flagged);
+      rflags.as<unsigned char>(), n_flagged);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch(2);
   // rows whose candidate margin is too thin are recomputed by the FP64 kernel
@@ -1213,6 +1220,34 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
   SCEDAR_CUDA(cudaMemcpyAsync(&h_flagged, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, s));
   SCEDAR_CUDA(cudaStreamSynchronize(s));
   if (h_flagged == 0) return SCEDAR_OK;
+  if ((int64_t)h_flagged * 8 <= rows && !getenv("SCEDAR_B200_TC_TILE_FALLBACK")) {
+    // a few cells: recompute exactly those -- gather their working-copy rows,
+    // contract them against all cells with the FP64 kernel (entries
+    // bit-identical to the whole matrix), select, and scatter the lists into
+    // the cells' own slots.  128 x n x p flops per 128 flagged cells instead of
+    // per tile that happens to contain one.
+    const int64_t m = h_flagged, m_pad = round_up(m, 128), n = c->n;
+    Scratch ids, gbuf, dbuf;
+    SCEDAR_CHECK(ids.alloc(sizeof(int64_t) * m_pad, s));
+    SCEDAR_CHECK(gbuf.alloc(sizeof(double) * m_pad * c->p_pad, s));
+    SCEDAR_CHECK(launch_flag_to_ids(rflags.as<unsigned char>(), rows, row_begin,
+                                    ids.as<int64_t>(), m, m_pad, s));
+    SCEDAR_CUDA(cudaMemsetAsync(gbuf.ptr, 0, sizeof(double) * m_pad * c->p_pad, s));
+    SCEDAR_CHECK(launch_gather_rows(c->xw, c->p_pad, c->p_pad, ids.as<int64_t>(), m,
+                                    gbuf.as<double>(), c->p_pad, s));
+    int64_t chunk = (int64_t)(2e9 / (8.0 * (double)n)) / 128 * 128;
+    chunk = std::max<int64_t>(128, std::min(chunk, m_pad));
+    SCEDAR_CHECK(dbuf.alloc(sizeof(double) * (size_t)chunk * (size_t)n, s));
+    for (int64_t c0 = 0; c0 < m; c0 += chunk) {
+      const int64_t mc = std::min(chunk, m - c0);
+      SCEDAR_CHECK(launch_gram_gathered(c, gbuf.as<double>() + c0 * c->p_pad,
+                                        ids.as<int64_t>() + c0, mc, round_up(mc, 128),
+                                        dbuf.as<double>(), n, s));
+      SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), n, n, 0, mc, k, exclude, idx_out,
+                                      dist_out, s, ids.as<int64_t>() + c0, row_begin));
+    }
+    return SCEDAR_OK;
+  }
   std::vector<unsigned char> hf((size_t)RT);
   SCEDAR_CUDA(cudaMemcpyAsync(hf.data(), flags.ptr, (size_t)RT, cudaMemcpyDeviceToHost, s));
   SCEDAR_CUDA(cudaStreamSynchronize(s));

@@ -27,7 +27,8 @@ template <int R>
 __global__ void __launch_bounds__(256)
 topk_from_d_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols,
                    int64_t row_begin, int64_t rows, int k, int exclude,
-                   int64_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+                   int64_t* __restrict__ idx_out, double* __restrict__ dist_out,
+                   const int64_t* __restrict__ row_ids, int64_t out_base) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -49,7 +50,10 @@ topk_from_d_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols,
       L.offer(v[u], (int)c, c < n_cols, K, lane);
     }
   }
-  L.emit(K, exclude, (int)(row_begin + row), idx_out + row * k, dist_out + row * k, lane);
+  // gathered rows: row r of d is cell row_ids[r]; its lists go to that cell's slot
+  const int64_t self = row_ids ? row_ids[row] : row_begin + row;
+  const int64_t orow = row_ids ? self - out_base : row;
+  L.emit(K, exclude, (int)self, idx_out + orow * k, dist_out + orow * k, lane);
 }
 
 template <int R>
@@ -178,17 +182,18 @@ sort_emit_kernel(const double* __restrict__ kd, const int* __restrict__ ki, int6
 
 int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row_begin,
                        int64_t row_end, int k, int exclude, int64_t* idx_out,
-                       double* dist_out, cudaStream_t s) {
+                       double* dist_out, cudaStream_t s, const int64_t* row_ids,
+                       int64_t out_base) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0 || k == 0) return SCEDAR_OK;
   const int K = k + 1;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (K <= 32)
-    topk_from_d_kernel<1><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out);
+    topk_from_d_kernel<1><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out, row_ids, out_base);
   else if (K <= 64)
-    topk_from_d_kernel<2><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out);
+    topk_from_d_kernel<2><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out, row_ids, out_base);
   else if (K <= 32 * kMaxR)
-    topk_from_d_kernel<4><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out);
+    topk_from_d_kernel<4><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out, row_ids, out_base);
   else
     return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
   SCEDAR_CUDA(cudaGetLastError());

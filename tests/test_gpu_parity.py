@@ -558,3 +558,36 @@ def test_incremental_cells_and_lower_rows(b200, n, p):
         ref_cells.close()
     with pytest.raises(ValueError):
         dev.Cells.alloc(n, p, "cosine").fill_rows(x[5:100], 5)   # not 128-aligned
+
+
+def test_fast_path_row_granular_fallback(b200):
+    """A few cells whose candidate margin cannot be verified (40 + 31 exact
+    duplicates: more than 32 candidates at distance 0) are recomputed by the
+    FP64 kernel row by row (gathered rows), the rest keep the tensor-core
+    result: bit-identical lists either way, also through the tile-granular
+    fallback."""
+    import os
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200._capi import EXCLUDE_FIRST, EXCLUDE_SELF
+    rng = np.random.default_rng(12)
+    x = rng.normal(0.0, 1.0, size=(3000, 40))
+    x[100:140] = x[100]
+    x[2000:2031] = x[2950]
+    x[2950] = x[2000]
+    xt = torch.from_numpy(x).cuda()
+    for metric in ("euclidean", "cosine"):
+        cells = dev.Cells.from_dense(xt, metric)
+        for k, ex in ((15, EXCLUDE_SELF), (15, EXCLUDE_FIRST), (30, EXCLUDE_SELF)):
+            i64, v64 = cells.knn_stripe(k, ex)
+            for forced in (None, "1"):
+                if forced:
+                    os.environ["SCEDAR_B200_TC_TILE_FALLBACK"] = forced
+                else:
+                    os.environ.pop("SCEDAR_B200_TC_TILE_FALLBACK", None)
+                ifa, vfa = cells.knn_stripe(k, ex, precision="fast")
+                assert torch.equal(i64, ifa) and torch.equal(v64, vfa), (metric, k, ex, forced)
+                sfa, _ = cells.knn_stripe(k, ex, 64, 2500, precision="fast")
+                assert torch.equal(sfa, i64[64:2500])
+            os.environ.pop("SCEDAR_B200_TC_TILE_FALLBACK", None)
+        cells.close()

@@ -18,10 +18,16 @@ def timed(fn, reps=3):
 
 
 for arg in sys.argv[1:]:
-    n, p, k = (int(v) for v in arg.split("x"))
-    g = torch.Generator(device="cuda").manual_seed(n)
-    x = torch.randn((n, p), dtype=torch.float64, device="cuda", generator=g)
-    cells = dev.Cells.from_dense(x, "euclidean")
+    f = arg.split("x")
+    n, p, k = (int(v) for v in f[:3])
+    if len(f) > 3 and f[3] == "log":     # the bench workload's data and metric
+        from scedar_b200 import synth
+        x = dev.to_device(synth.log_counts(n, p, seed=n))
+        cells = dev.Cells.from_dense(x, "correlation")
+    else:
+        g = torch.Generator(device="cuda").manual_seed(n)
+        x = torch.randn((n, p), dtype=torch.float64, device="cuda", generator=g)
+        cells = dev.Cells.from_dense(x, "euclidean")
     out = {"n": n, "p": p, "k": k, "cg": os.environ.get("SCEDAR_B200_TC_CG", "default")}
     out["fast_knn_ms"] = round(timed(lambda: cells.knn_stripe(k, EXCLUDE_SELF, precision="fast")), 2)
     if 8.0 * n * n < 90e9:
