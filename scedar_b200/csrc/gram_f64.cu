@@ -95,6 +95,12 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 // Fragment row g of an 8-row group lives in tile row perm8(g): with the
 // 128-byte TMA swizzle (16-byte chunk index XOR row%8) the 16 lanes of a
 // half-warp (4 fragment rows x 4 k) then read 16 distinct 8-byte banks.
@@ -113,11 +119,13 @@ __device__ __forceinline__ void gram_consume(double (&acc)[MF][NF][2], const dou
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N, g = lane >> 2, t = lane & 3;
   const int pa = perm8(g);
-  int off[BK / 4];  // swizzled position of k = 4*kk + t inside a 16-double row
-#pragma unroll
-  for (int kk = 0; kk < BK / 4; ++kk) off[kk] = (((2 * kk + (t >> 1)) ^ pa) << 1) | (t & 1);
-  const double* Arow = pipe + (wm * WTM + pa) * BK;
-  const double* Brow = pipe + PANEL_DOUBLES + (wn * WTN + pa) * BK;
+  // swizzled byte offset of k = 4*kk + t inside a 16-double row: off0 ^ (32 * kk)
+  const uint32_t off0 = (uint32_t)(((((t >> 1) ^ pa) << 1) | (t & 1)) * 8);
+  // 32-bit shared-window addresses: the accumulators leave no room for 64-bit
+  // pointer arithmetic in the main loop
+  const uint32_t pipe32 = smem_u32(pipe);
+  const uint32_t Arow = pipe32 + (uint32_t)((wm * WTM + pa) * BK * 8);
+  const uint32_t Brow = pipe32 + (uint32_t)((PANEL_DOUBLES + (wn * WTN + pa) * BK) * 8);
 #pragma unroll
   for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
@@ -125,16 +133,17 @@ __device__ __forceinline__ void gram_consume(double (&acc)[MF][NF][2], const dou
 
   for (int kt = 0; kt < KT; ++kt, ++it) {
     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-    mbar_wait(full0 + 8 * s, ph);   // the TMA boxes of this slab have landed
-    const double* As = Arow + s * STAGE_DOUBLES;
-    const double* Bs = Brow + s * STAGE_DOUBLES;
+    mbar_wait_lite(full0 + 8 * s, ph);   // the TMA boxes of this slab have landed
+    const uint32_t As = Arow + s * STAGE_BYTES;
+    const uint32_t Bs = Brow + s * STAGE_BYTES;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
       double a[MF], b[NF];
+      const uint32_t ok = off0 ^ (uint32_t)(32 * kk);
 #pragma unroll
-      for (int mf = 0; mf < MF; ++mf) a[mf] = As[mf * 8 * BK + off[kk]];
+      for (int mf = 0; mf < MF; ++mf) a[mf] = lds_f64(As + ok + mf * 8 * BK * 8);
 #pragma unroll
-      for (int nf = 0; nf < NF; ++nf) b[nf] = Bs[nf * 8 * BK + off[kk]];
+      for (int nf = 0; nf < NF; ++nf) b[nf] = lds_f64(Bs + ok + nf * 8 * BK * 8);
       if (DIAG_ONLY) {
         // rows wm*64 + mf*8 meet columns wn*32 + nf*8 when mf == (wn & 1) * 4 + nf
         // in the warps with wn / 2 == wm
@@ -186,15 +195,8 @@ __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], doubl
                                              const int64_t* __restrict__ row_ids = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N, g = lane >> 2, t = lane & 3;
-  double sr[8], sc[4][2];
-  int64_t rid[8];   // cell index of the tile rows (gathered rows: through row_ids)
+  double sc[4][2];
   if (!RAW) {
-#pragma unroll
-    for (int mf = 0; mf < 8; ++mf) {
-      const int64_t lr = i0 + wm * 64 + mf * 8 + perm8(g);
-      rid[mf] = row_ids ? row_ids[lr] : lr;
-      sr[mf] = rid[mf] >= 0 ? __ldg(stat + rid[mf]) : 0.0;
-    }
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
       sc[nf][0] = __ldg(stat + j0 + wn * 32 + nf * 8 + perm8(2 * t));
@@ -204,7 +206,14 @@ __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], doubl
 #pragma unroll
   for (int mf = 0; mf < 8; ++mf) {
     const int r = wm * 64 + mf * 8 + perm8(g);   // fragment row -> tile row
-    const int64_t gi = RAW ? i0 + r : rid[mf];
+    // cell index of the row (gathered rows: through row_ids) and its statistic,
+    // fetched row by row: keeping all eight in registers spills
+    int64_t gi = i0 + r;
+    double srm = 0.0;
+    if (!RAW) {
+      if (row_ids) gi = row_ids[gi];
+      if (gi >= 0) srm = __ldg(stat + gi);
+    }
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
 #pragma unroll
@@ -214,8 +223,8 @@ __device__ __forceinline__ void tile_to_smem(const double (&acc)[8][4][2], doubl
         if (!RAW) {
           const int64_t gj = j0 + c;
           const bool lower = gi >= gj;
-          v = finish_entry(v, lower ? sr[mf] : sc[nf][e], lower ? sc[nf][e] : sr[mf],
-                           gi == gj, euclid);
+          v = finish_entry(v, lower ? srm : sc[nf][e], lower ? sc[nf][e] : srm, gi == gj,
+                           euclid);
         }
         T[r * LDT + c] = v;
       }

@@ -46,6 +46,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   } while (!ok);
 }
+// The same wait for register-starved loops (the FP64 Gram consumers hold 128
+// accumulator registers): 32-bit clock, no printf call on the time-out path.
+__device__ __forceinline__ void mbar_wait_lite(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t t0 = (uint32_t)clock();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (uint32_t)clock() - t0 > 3000000000u) __trap();   // ~1.5 s: a protocol bug
+  } while (!ok);
+}
 // 2-D tiled TMA load: box at (c0 = inner element, c1 = row) -> shared memory,
 // completion counted in bytes on the mbarrier
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
