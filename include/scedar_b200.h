@@ -76,6 +76,13 @@ enum {
 #define SCEDAR_NCDM_BAD_DIAG 1 /* some |diag| > 1e-5           (sdm.py:196-203) */
 #define SCEDAR_NCDM_ASYMMETRIC 2 /* triangles differ, rtol 1e-3 (sdm.py:205-213) */
 
+/* flags OR-ed into *flags_out by scedar_squareform_rows: what scipy's
+ * squareform(checks=True) -> is_valid_dm rejects with a ValueError */
+#define SCEDAR_SQF_NAN 1      /* a NaN above the diagonal (D == D.T fails)  */
+#define SCEDAR_SQF_BAD_DIAG 2 /* a diagonal entry that is not exactly zero  */
+/* flag OR-ed into *flags_out by scedar_d_gather_block */
+#define SCEDAR_GATHER_BAD_INDEX 1 /* a selected row / column is out of range */
+
 int scedar_abi_version(void);
 const char* scedar_last_error(void);
 
@@ -284,6 +291,39 @@ int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        int64_t row_end, double* x_next, int64_t ldn,
                        int32_t* idc, int64_t ldi,
                        unsigned long long* stats_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Clustering consumers of D: the data movement between
+ * the distance matrix and the sequential CPU linkage, on the device.
+ * ---------------------------------------------------------------------- */
+
+/* Condensed form of a symmetric D: scipy.spatial.distance.squareform(dmat) as
+ * HClustTree.hclust_linkage calls it before sch.linkage (sdm.py:1666-1668).
+ * d is the stripe [(row_end-row_begin), n] of D (row r = cell row_begin + r,
+ * row stride ldd); the strict upper triangle of those rows, row after row, is
+ * the contiguous segment [base(row_begin), base(row_end)) of the condensed
+ * vector, base(i) = i(2n-i-1)/2; condensed_out points at entry
+ * base(row_begin) (the whole vector for row_begin = 0).  Symmetry of D is the
+ * caller's contract (the Gram kernels and scedar_num_correct_dist_mat both
+ * establish it bit for bit); what scipy's validity check can still reject is
+ * OR-ed into *flags_out (device int32, zeroed by the caller, shared by the
+ * calls of all stripes): SCEDAR_SQF_*. */
+int scedar_squareform_rows(const double* d, int64_t ldd, int64_t n,
+                           int64_t row_begin, int64_t row_end,
+                           double* condensed_out, int32_t* flags_out,
+                           void* stream);
+
+/* Sub-matrix out[r, c] = d[row_sel[r], col_sel[c]] (m x c, row stride ldo) of
+ * a matrix / stripe d [n_rows, n_cols] (row stride ldd): the slicing
+ * self._d[s][:, s] of SampleDistanceMatrix.ind_x (sdm.py:684-692) and
+ * self._sdm._d[a][:, b] of MIRAC (scedar/cluster/mirac.py:316-331).  Indices
+ * are int64, already non-negative (NumPy's wrap-around is the caller's);
+ * an index outside [0, n_rows) / [0, n_cols) sets SCEDAR_GATHER_BAD_INDEX in
+ * *flags_out (device int32, zeroed by the caller) and a NaN in its slot. */
+int scedar_d_gather_block(const double* d, int64_t ldd, int64_t n_rows,
+                          int64_t n_cols, const int64_t* row_sel, int64_t m,
+                          const int64_t* col_sel, int64_t c, double* out,
+                          int64_t ldo, int32_t* flags_out, void* stream);
 
 /* ------------------------------------------------------------------------
  * One-shot forms (prepare + run + free), the signatures SURVEY.md 8b lists.

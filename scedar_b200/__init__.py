@@ -14,7 +14,11 @@ def __getattr__(name):
     if name == "SampleDistanceMatrix":
         from .sdm import SampleDistanceMatrix
         return SampleDistanceMatrix
-    if name in ("device", "sdm", "stripes", "synth", "_capi", "knn", "patch"):
+    if name == "HClustTree":
+        from .hclust import HClustTree
+        return HClustTree
+    if name in ("device", "sdm", "stripes", "synth", "_capi", "knn", "patch",
+                "hclust"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -17,6 +17,8 @@ PRECISION_IDS = {"fp64": 0, "fast": 1}
 EXCLUDE_FIRST, EXCLUDE_SELF = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4
 NCDM_BAD_DIAG, NCDM_ASYMMETRIC = 1, 2
+SQF_NAN, SQF_BAD_DIAG = 1, 2
+GATHER_BAD_INDEX = 1
 
 # name -> (restype, argtypes); every symbol the header declares
 SIGNATURES = {
@@ -77,6 +79,11 @@ SIGNATURES = {
                                    c_void_p, c_int, c_int, c_double, c_int,
                                    c_int64, c_int64, c_void_p, c_int64,
                                    c_void_p, c_int64, c_void_p, c_void_p]),
+    "scedar_squareform_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64,
+                                       c_int64, c_void_p, c_void_p, c_void_p]),
+    "scedar_d_gather_block": (c_int, [c_void_p, c_int64, c_int64, c_int64,
+                                      c_void_p, c_int64, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_void_p, c_void_p]),
     "scedar_pdist_dense": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_int64, c_int64, c_void_p, c_void_p]),
     "scedar_pdist_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64,

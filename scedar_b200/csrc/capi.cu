@@ -484,6 +484,33 @@ int scedar_gather_rows(const double* x, int64_t ldx, int64_t p, const int64_t* s
   return launch_gather_rows(x, ldx, p, sel, m, out, ldo, static_cast<cudaStream_t>(stream));
 }
 
+int scedar_squareform_rows(const double* d, int64_t ldd, int64_t n, int64_t row_begin,
+                           int64_t row_end, double* condensed_out, int32_t* flags_out,
+                           void* stream) {
+  if (n < 0 || row_begin < 0 || row_end < row_begin || row_end > n)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n");
+  if (ldd < n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (!flags_out) return fail(SCEDAR_ERR_ARG, "flags_out is NULL");
+  if (row_end == row_begin) return SCEDAR_OK;
+  // the last row of D has no entry above the diagonal, but its diagonal is checked
+  const int64_t seg = row_end * (2 * n - row_end - 1) / 2 - row_begin * (2 * n - row_begin - 1) / 2;
+  if (!d || (!condensed_out && seg > 0)) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_squareform_rows(d, ldd, n, row_begin, row_end, condensed_out, flags_out,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int scedar_d_gather_block(const double* d, int64_t ldd, int64_t n_rows, int64_t n_cols,
+                          const int64_t* row_sel, int64_t m, const int64_t* col_sel, int64_t c,
+                          double* out, int64_t ldo, int32_t* flags_out, void* stream) {
+  if (n_rows < 0 || n_cols < 0 || m < 0 || c < 0 || ldd < n_cols || ldo < c)
+    return fail(SCEDAR_ERR_ARG, "need non-negative sizes, ldd >= n_cols and ldo >= c");
+  if (!flags_out) return fail(SCEDAR_ERR_ARG, "flags_out is NULL");
+  if (m == 0 || c == 0) return SCEDAR_OK;
+  if (!d || !row_sel || !col_sel || !out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  return launch_gather_block(d, ldd, n_rows, n_cols, row_sel, m, col_sel, c, out, ldo,
+                             flags_out, static_cast<cudaStream_t>(stream));
+}
+
 int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        const int64_t* knn, int k, int n_do_i, double min_present_val, int iter,
                        int64_t row_begin, int64_t row_end, double* x_next, int64_t ldn,

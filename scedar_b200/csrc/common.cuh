@@ -159,6 +159,13 @@ int launch_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                        double* x_next, int64_t ldn, int32_t* idc, int64_t ldi,
                        unsigned long long* counters, cudaStream_t s);
 
+// hclust.cu (condensed D, sub-matrix gather)
+int launch_squareform_rows(const double* d, int64_t ldd, int64_t n, int64_t row_begin,
+                           int64_t row_end, double* out, int32_t* flags, cudaStream_t s);
+int launch_gather_block(const double* d, int64_t ldd, int64_t n_rows, int64_t n_cols,
+                        const int64_t* row_sel, int64_t m, const int64_t* col_sel, int64_t c,
+                        double* out, int64_t ldo, int32_t* flags, cudaStream_t s);
+
 // ncdm.cu
 int launch_ncdm(double* d, int64_t ldd, int64_t n, int has_ub, double ub,
                 int32_t* flags, cudaStream_t s);

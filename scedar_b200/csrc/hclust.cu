@@ -1,0 +1,116 @@
+// Data side of the clustering consumers of D.
+// Both kernels are pure data movement, HBM-bound, and keep D on the device
+// between the Gram kernel and the (sequential, CPU) linkage.
+//
+//   squareform_rows   rows [row_begin, row_end) of the strict upper triangle of
+//                     a symmetric n x n D, concatenated: the condensed vector
+//                     scipy.spatial.distance.squareform(dmat) hands to
+//                     sch.linkage in HClustTree.hclust_linkage
+//                     (scedar/eda/sdm.py:1666-1668).  Row i owns the contiguous
+//                     run [base(i), base(i+1)) of the vector, base(i) =
+//                     i(2n-i-1)/2, so a row stripe of D yields one contiguous
+//                     segment and D never has to be whole anywhere.
+//                     Algorithmic bytes: 8 read + 8 written per pair i < j,
+//                     i.e. 8n(n-1) for the whole matrix -- half of what a host
+//                     copy of D alone costs.
+//   gather_block      out[r, c] = d[row_sel[r], col_sel[c]]: the sub-matrix
+//                     slicing d[a][:, b] of SampleDistanceMatrix.ind_x
+//                     (sdm.py:684-692) and of MIRAC's cluster encoders
+//                     (scedar/cluster/mirac.py:316-331).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace scedar {
+namespace {
+
+__global__ void __launch_bounds__(256)
+squareform_rows_kernel(const double* __restrict__ d, int64_t ldd, int64_t n, int64_t row_begin,
+                       int64_t row_end, double* __restrict__ out, int32_t* __restrict__ flags) {
+  const int64_t base0 = row_begin * (2 * n - row_begin - 1) / 2;
+  int bad = 0;
+  // rows get shorter towards the end of the matrix: interleaving them over the
+  // blocks gives every block the same mix of long and short rows
+  for (int64_t i = row_begin + blockIdx.x; i < row_end; i += gridDim.x) {
+    const double* __restrict__ src = d + (i - row_begin) * ldd;
+    double* __restrict__ dst = out + (i * (2 * n - i - 1) / 2 - base0);
+    if (threadIdx.x == 0 && !(src[i] == 0.0)) bad |= SCEDAR_SQF_BAD_DIAG;
+    const int64_t len = n - 1 - i;  // entries (i, i+1) .. (i, n-1)
+    src += i + 1;
+    int64_t q = threadIdx.x;
+    for (; q + 3 * 256 < len; q += 4 * 256) {  // four loads in flight per thread
+      const double v0 = __ldcs(src + q), v1 = __ldcs(src + q + 256);
+      const double v2 = __ldcs(src + q + 512), v3 = __ldcs(src + q + 768);
+      if (v0 != v0 || v1 != v1 || v2 != v2 || v3 != v3) bad |= SCEDAR_SQF_NAN;
+      __stcs(dst + q, v0);
+      __stcs(dst + q + 256, v1);
+      __stcs(dst + q + 512, v2);
+      __stcs(dst + q + 768, v3);
+    }
+    for (; q < len; q += 256) {
+      const double v = __ldcs(src + q);
+      if (v != v) bad |= SCEDAR_SQF_NAN;
+      __stcs(dst + q, v);
+    }
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+constexpr int GB_COLS = 1024;  // columns of one block's chunk
+
+__global__ void __launch_bounds__(256)
+gather_block_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_rows, int64_t n_cols,
+                    const int64_t* __restrict__ row_sel, int64_t m,
+                    const int64_t* __restrict__ col_sel, int64_t c, double* __restrict__ out,
+                    int64_t ldo, int32_t* __restrict__ flags) {
+  int bad = 0;
+  for (int64_t r = blockIdx.x; r < m; r += gridDim.x) {
+    const int64_t gr = row_sel[r];
+    const bool row_ok = gr >= 0 && gr < n_rows;
+    if (!row_ok) bad = 1;
+    const double* __restrict__ src = d + (row_ok ? gr : 0) * ldd;
+    for (int64_t q0 = (int64_t)blockIdx.y * GB_COLS; q0 < c; q0 += (int64_t)gridDim.y * GB_COLS) {
+      const int64_t q1 = q0 + GB_COLS < c ? q0 + GB_COLS : c;
+      for (int64_t q = q0 + threadIdx.x; q < q1; q += 256) {
+        const int64_t gc = col_sel[q];
+        const bool ok = row_ok && gc >= 0 && gc < n_cols;
+        if (!ok) bad = 1;
+        // an out-of-range selection is reported through the flag; its slot
+        // gets a NaN so it cannot pass for a distance
+        out[r * ldo + q] = ok ? src[gc] : __longlong_as_double(0x7ff8000000000000LL);
+      }
+    }
+  }
+  if (bad) atomicOr(flags, SCEDAR_GATHER_BAD_INDEX);
+}
+
+}  // namespace
+
+int launch_squareform_rows(const double* d, int64_t ldd, int64_t n, int64_t row_begin,
+                           int64_t row_end, double* out, int32_t* flags, cudaStream_t s) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0) return SCEDAR_OK;
+  const int64_t grid = std::min<int64_t>(rows, (int64_t)num_sms() * 8);
+  squareform_rows_kernel<<<(unsigned)grid, 256, 0, s>>>(d, ldd, n, row_begin, row_end, out,
+                                                        flags);
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
+int launch_gather_block(const double* d, int64_t ldd, int64_t n_rows, int64_t n_cols,
+                        const int64_t* row_sel, int64_t m, const int64_t* col_sel, int64_t c,
+                        double* out, int64_t ldo, int32_t* flags, cudaStream_t s) {
+  if (m <= 0 || c <= 0) return SCEDAR_OK;
+  const int64_t chunks = (c + GB_COLS - 1) / GB_COLS;
+  const int64_t want = (int64_t)num_sms() * 8;
+  const int64_t gx = std::min<int64_t>(m, want);
+  const int64_t gy = std::max<int64_t>(1, std::min<int64_t>(chunks, want / gx));
+  gather_block_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(
+      d, ldd, n_rows, n_cols, row_sel, m, col_sel, c, out, ldo, flags);
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
+}  // namespace scedar

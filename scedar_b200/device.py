@@ -421,6 +421,69 @@ def impute_iter(x_curr, knn, n_do_i, min_present_val, it, x_next, idc,
         _ptr(idc), max(p, 1), _ptr(stats), _stream()))
 
 
+# ---------------------------------------------------------------------------
+# clustering consumers of D: condensed form, sub-matrix
+# ---------------------------------------------------------------------------
+def condensed_len(n):
+    """Length of the condensed vector of an n x n distance matrix."""
+    return n * (n - 1) // 2 if n > 1 else 0
+
+
+def condensed_base(i, n):
+    """Offset of row i's run (i, i+1) .. (i, n-1) in the condensed vector."""
+    return i * (2 * n - i - 1) // 2
+
+
+def squareform_rows(d, n, row_begin=0, out=None, flags=None):
+    """Strict upper triangle of the rows of a stripe ``d`` [rows, n] of a
+    symmetric D, row after row: the segment ``[condensed_base(row_begin),
+    condensed_base(row_begin + rows))`` of ``scipy.spatial.distance.squareform
+    (D)`` (sdm.py:1666).  ``flags`` (int32[1], zeroed by the caller, shared by
+    all stripes) collects the SQF_* bits.  Returns (segment, flags)."""
+    _guard()
+    d = _f64(d)
+    rows = d.shape[0]
+    assert d.dim() == 2 and d.shape[1] == n and row_begin + rows <= n
+    if d.stride(1) != 1 and n > 1:
+        d = d.contiguous()
+    seg = condensed_base(row_begin + rows, n) - condensed_base(row_begin, n)
+    if out is None:
+        out = torch.empty(seg, dtype=torch.float64, device="cuda")
+    assert out.is_cuda and out.dtype == torch.float64 and out.numel() == seg
+    assert out.is_contiguous()
+    if flags is None:
+        flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _capi.check(_capi.load().scedar_squareform_rows(
+        _ptr(d), d.stride(0) if rows > 1 else max(n, 1), n, int(row_begin),
+        int(row_begin) + rows, _ptr(out), _ptr(flags), _stream()))
+    return out, flags
+
+
+def gather_block(d, row_sel, col_sel):
+    """``d[row_sel][:, col_sel]`` on the device for int64 index tensors
+    (sdm.py:684-692, mirac.py:316-331); raises IndexError like NumPy when a
+    selected index is out of range."""
+    _guard()
+    d = _f64(d)
+    assert d.dim() == 2
+    if d.stride(1) != 1 and d.shape[1] > 1:
+        d = d.contiguous()
+    for sel in (row_sel, col_sel):
+        assert sel.is_cuda and sel.dtype == torch.int64 and sel.dim() == 1
+    row_sel, col_sel = row_sel.contiguous(), col_sel.contiguous()
+    m, c = row_sel.numel(), col_sel.numel()
+    out = torch.empty((m, c), dtype=torch.float64, device="cuda")
+    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _capi.check(_capi.load().scedar_d_gather_block(
+        _ptr(d), d.stride(0) if d.shape[0] > 1 else max(d.shape[1], 1),
+        d.shape[0], d.shape[1], _ptr(row_sel), m, _ptr(col_sel), c, _ptr(out),
+        max(c, 1), _ptr(flags), _stream()))
+    if int(flags.item()) & _capi.GATHER_BAD_INDEX:
+        raise IndexError("index out of bounds for a matrix of shape "
+                         "{}".format(tuple(d.shape)))
+    return out
+
+
 def upload_ranges(n, first=2048):
     """128-aligned row ranges that double in size: the first is small so the
     contraction starts almost at once, every later range is uploaded while the

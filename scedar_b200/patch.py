@@ -5,6 +5,9 @@
 t-SNE / UMAP / PCA, ``to_classified`` ... and gets ``_d``, the sorted-column
 accessors and the kNN accessors from :class:`scedar_b200.SampleDistanceMatrix`
 (scedar/eda/sdm.py:187-222, 751-947, 1053-1083, 1193-1305);
+``scedar.eda.HClustTree.hclust_linkage`` (sdm.py:1629-1669) gets the device
+clean-up + condensed form of :mod:`scedar_b200.hclust` and accepts the SDM
+itself in place of its ``_d``;
 ``scedar.knn.RareSampleDetection`` / ``FeatureImputation`` get the device
 loops of :mod:`scedar_b200.knn` (scedar/knn/detection.py:33-123,
 scedar/knn/imputation.py:35-135).
@@ -18,10 +21,11 @@ SDM_HOOKS = (
     "s_knn_ind_lut", "s_knn_connectivity_matrix", "s_ith_nn_d", "s_ith_nn_ind",
     "_validate_pdist", "_check_metric", "_cells", "_device_d", "_d_stripes",
     "_col_sort", "_knn_from_pdist", "release_device", "_is_sparse",
+    "d_block", "_condensed_d",
 )
 SDM_STATIC_HOOKS = (
     "cosine_pdist", "correlation_pdist", "num_correct_dist_mat", "_static_pdist",
-    "knn_conn_mat_to_aff_edges", "knn_conn_mat_to_aff_graph",
+    "knn_conn_mat_to_aff_edges", "knn_conn_mat_to_aff_graph", "_warn_ncdm",
 )
 
 
@@ -66,10 +70,19 @@ def install_knn(rare_cls=None, impute_cls=None):
     return rare_cls, impute_cls
 
 
+def install_hclust(cls):
+    """Patch an ``HClustTree``-like class: ``hclust_linkage`` only -- the
+    reference's ``hclust_tree`` / ``sort_x_by_d`` / MIRAC call it by name."""
+    from . import hclust as _hclust
+    cls.hclust_linkage = staticmethod(_hclust.HClustTree.hclust_linkage)
+    return cls
+
+
 def install():
     """Patch the installed ``scedar`` package."""
     import scedar.eda.sdm as ref_sdm
     import scedar.knn as ref_knn
     install_sdm(ref_sdm.SampleDistanceMatrix)
+    install_hclust(ref_sdm.HClustTree)
     install_knn(ref_knn.RareSampleDetection, ref_knn.FeatureImputation)
     return ref_sdm.SampleDistanceMatrix

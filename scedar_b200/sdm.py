@@ -162,12 +162,62 @@ class SampleDistanceMatrix(object):
             selected_f_inds = slice(None, None)
         sub_d = None
         if self._use_pdist:
-            sub_d = self._d[selected_s_inds, :][:, selected_s_inds].copy()
+            sub_d = self.d_block(selected_s_inds, selected_s_inds)
         return SampleDistanceMatrix(
             x=self._x[selected_s_inds, :][:, selected_f_inds].copy(),
             d=sub_d, metric=self._metric, use_pdist=self._use_pdist,
             sids=self._sids[selected_s_inds].tolist(),
             fids=self._fids[selected_f_inds].tolist(), nprocs=self._nprocs)
+
+    def d_block(self, row_inds, col_inds):
+        """``self._d[row_inds][:, col_inds]`` as a fresh array -- the slicing
+        of ``ind_x`` (sdm.py:684-692) and of MIRAC's cluster encoders
+        (scedar/cluster/mirac.py:316-331).  A D that so far lives only in HBM
+        is sliced there (``scedar_d_gather_block``) and only the block comes
+        to the host; a D already on the host is sliced where it is."""
+        self._validate_pdist()
+        n = self._x.shape[0]
+        if self._lazy_load_d is None and self._device_d() is not None:
+            pos = np.arange(n, dtype=np.int64)
+            rows = np.atleast_1d(pos[row_inds])     # NumPy's own index rules
+            cols = np.atleast_1d(pos[col_inds])
+            blk = dev.gather_block(self._d_dev, dev.to_device(rows),
+                                   dev.to_device(cols))
+            return blk.cpu().numpy()
+        return self._d[row_inds][:, col_inds].copy()
+
+    def _condensed_d(self):
+        """``scipy.spatial.distance.squareform(self._d)`` (the input of
+        ``sch.linkage``, sdm.py:1666) without the n x n host matrix: the
+        strict upper triangle is packed on the device, stripe by stripe when D
+        is not resident, and only n(n-1)/2 doubles cross to the host."""
+        from .hclust import _condensed_flags_check
+        self._validate_pdist()
+        n = self._x.shape[0]
+        out = np.empty(dev.condensed_len(n), dtype=np.float64)
+        if n == 0:
+            return out
+        flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for r0, r1, stripe in self._d_stripes():
+            seg, _ = dev.squareform_rows(stripe, n, row_begin=r0, flags=flags)
+            b0, b1 = dev.condensed_base(r0, n), dev.condensed_base(r1, n)
+            if b1 > b0:
+                dev.to_host(seg, out[b0:b1])
+        _condensed_flags_check(int(flags.item()))
+        return out
+
+    def sort_features(self, fdist_metric="cosine", optimal_ordering=False):
+        """sdm.py:178-184: reorder the features by the leaf order of the
+        auto-linkage tree of their pairwise distances."""
+        from .hclust import HClustTree
+        order = HClustTree.sort_x_by_d(
+            self._x.T, metric=fdist_metric, optimal_ordering=optimal_ordering,
+            nprocs=self._nprocs)
+        self._x = self._x[:, order]
+        self._fids = self._fids[order]
+        for c in self._cells_lut.values():   # prepared from the old order
+            c.close()
+        self._cells_lut = {}
 
     def id_x(self, selected_sids=None, selected_fids=None):
         s = None if selected_sids is None else self.s_id_to_ind(selected_sids)
@@ -252,15 +302,21 @@ class SampleDistanceMatrix(object):
         if dmat.shape[0] == 0:
             return dmat
         t = dev.to_device(dmat.astype(np.float64, copy=False))
-        flags = dev.num_correct_dist_mat_(t, upper_bound)
+        SampleDistanceMatrix._warn_ncdm(
+            dev.num_correct_dist_mat_(t, upper_bound))
+        dmat[...] = t.cpu().numpy()
+        return dmat
+
+    @staticmethod
+    def _warn_ncdm(flags):
+        """The two ``UserWarning``s of sdm.py:196-213 from the kernel's flag
+        bits."""
         if flags & NCDM_BAD_DIAG:
             warnings.warn("distance matrix might not be numerically "
                           "correct. diag vals should be close to 0.")
         if flags & NCDM_ASYMMETRIC:
             warnings.warn("distance matrix might not be numerically "
                           "correct. should be approximately symmetric.")
-        dmat[...] = t.cpu().numpy()
-        return dmat
 
     @staticmethod
     def _static_pdist(x, metric):

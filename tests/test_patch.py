@@ -28,6 +28,9 @@ def test_install_wiring_cpu():
     from scedar_b200 import patch
     cls = type("RefCopy", (RefLike,), {})
     patch.install_sdm(cls)
+    tree = patch.install_hclust(type("T", (object,), {}))
+    with pytest.raises(ValueError):
+        tree.hclust_linkage(np.arange(5))        # rejected before any device use
     patch.install_sdm(cls)                       # idempotent
     s = cls(np.zeros((0, 3)), metric="euclidean")
     assert s._cells_lut == {} and s._d_dev is None and s._d_user is False
@@ -72,3 +75,38 @@ def test_patched_class_matches_dropin():
         assert np.array_equal(a._col_argsorted_d, b._col_argsorted_d)
         ca, cb = a.s_knn_connectivity_matrix(5), b.s_knn_connectivity_matrix(5)
         assert (ca != cb).nnz == 0
+        assert np.array_equal(a._condensed_d(), b._condensed_d())
+        sel = [7, 399, 0]
+        assert np.array_equal(a.d_block(sel, sel), b._d[sel][:, sel])
+
+
+@pytest.mark.gpu
+def test_patched_hclust_matches_dropin():
+    import scipy.cluster.hierarchy as sch
+    import scedar_b200
+    from scedar_b200 import patch, synth
+
+    class RefTree(object):
+        """The call structure of the reference (sdm.py:1671-1682)."""
+        @staticmethod
+        def hclust_linkage(dmat, linkage="complete", **kw):
+            raise AssertionError("not patched")
+
+        @staticmethod
+        def hclust_tree(dmat, linkage="complete", **kw):
+            return sch.to_tree(RefTree.hclust_linkage(dmat, linkage=linkage,
+                                                      **kw))
+
+    patch.install_hclust(RefTree)
+    sdm_cls = patch.install_sdm(type("RefCopy", (RefLike,), {}))
+    x = synth.blobs(300, 20, seed=2, n_blobs=3)
+    a = sdm_cls(x, metric="euclidean")
+    want = scedar_b200.HClustTree.hclust_linkage(
+        scedar_b200.SampleDistanceMatrix(x, metric="euclidean")._d,
+        linkage="ward")
+    # the patched SDM itself (D stays in HBM) and its host matrix
+    got = RefTree.hclust_tree(a, linkage="ward")
+    assert got.pre_order(lambda nd: nd.get_id()) == \
+        sch.to_tree(want).pre_order(lambda nd: nd.get_id())
+    assert a._lazy_load_d is None
+    assert np.array_equal(RefTree.hclust_linkage(a._d, linkage="ward"), want)
