@@ -38,14 +38,15 @@ squareform_rows_kernel(const double* __restrict__ d, int64_t ldd, int64_t n, int
     const int64_t len = n - 1 - i;  // entries (i, i+1) .. (i, n-1)
     src += i + 1;
     int64_t q = threadIdx.x;
-    for (; q + 3 * 256 < len; q += 4 * 256) {  // four loads in flight per thread
-      const double v0 = __ldcs(src + q), v1 = __ldcs(src + q + 256);
-      const double v2 = __ldcs(src + q + 512), v3 = __ldcs(src + q + 768);
-      if (v0 != v0 || v1 != v1 || v2 != v2 || v3 != v3) bad |= SCEDAR_SQF_NAN;
-      __stcs(dst + q, v0);
-      __stcs(dst + q + 256, v1);
-      __stcs(dst + q + 512, v2);
-      __stcs(dst + q + 768, v3);
+    for (; q + 7 * 256 < len; q += 8 * 256) {  // eight loads in flight per thread
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + q + u * 256);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (v[u] != v[u]) bad |= SCEDAR_SQF_NAN;
+        __stcs(dst + q + u * 256, v[u]);
+      }
     }
     for (; q < len; q += 256) {
       const double v = __ldcs(src + q);

@@ -61,7 +61,10 @@ def main():
         dm.copy(), linkage="complete")
 
     # ---- sort_features (sdm.py:178-184) --------------------------------------
-    xs = synth.log_counts(40, 25, seed=19)
+    # continuous, tie-free features: with exactly tied distances (e.g. the
+    # all-zero genes of log counts) the merge order follows the rounding
+    # noise of the reference's BLAS and no other implementation reproduces it
+    xs = synth.blobs(40, 25, seed=19, n_blobs=4, outlier_frac=0.0)
     s = SDM(xs, metric="correlation")
     s.sort_features(fdist_metric="euclidean", optimal_ordering=True)
     out["sf_x"] = xs
