@@ -112,6 +112,36 @@ def bipartition_counts(hac_z, n_rounds):
     return rounds
 
 
+def linkage_from_condensed(dmat_sf, n, linkage="complete", n_eval_rounds=None,
+                           is_euc_dist=False, optimal_ordering=False,
+                           verbose=False):
+    """The part of ``hclust_linkage`` behind ``squareform`` (sdm.py:1636-1669):
+    the ``linkage="auto"`` selection and ``sch.linkage`` on the condensed
+    vector of an n x n matrix.  Host only."""
+    if linkage == "auto":
+        try_linkages = ("single", "complete", "average", "weighted")
+        if is_euc_dist:
+            try_linkages += ("centroid", "median", "ward")
+        if n_eval_rounds is None:
+            n_eval_rounds = int(np.ceil(np.log2(n)))
+        else:
+            n_eval_rounds = int(np.ceil(max(np.log2(n), n_eval_rounds)))
+        scores = []
+        for lt in try_linkages:
+            # the clean-up and squareform are idempotent, so the condensed
+            # vector is shared by every candidate (the reference redoes both
+            # per candidate, sdm.py:1651)
+            z = sch.linkage(dmat_sf, method=lt, optimal_ordering=False)
+            mdls = np.array([_multinomial_mdl(c) for c in
+                             bipartition_counts(z, n_eval_rounds)])
+            scores.append(np.sum(mdls / np.arange(1, n_eval_rounds + 1)))
+        linkage = try_linkages[scores.index(max(scores))]
+        if verbose:
+            print(linkage, tuple(zip(try_linkages, scores)), sep="\n")
+    return sch.linkage(dmat_sf, method=linkage,
+                       optimal_ordering=optimal_ordering)
+
+
 class HClustTree(object):
     """Hierarchical clustering tree over ``scipy.cluster.hierarchy.ClusterNode``
     (sdm.py:1369-1436): a binary tree whose missing children are empty trees
@@ -173,30 +203,10 @@ class HClustTree(object):
                        verbose=False):
         """sdm.py:1629-1669 -> the scipy linkage matrix."""
         dmat_sf, n = _condensed_of(dmat)
-
-        if linkage == "auto":
-            try_linkages = ("single", "complete", "average", "weighted")
-            if is_euc_dist:
-                try_linkages += ("centroid", "median", "ward")
-            if n_eval_rounds is None:
-                n_eval_rounds = int(np.ceil(np.log2(n)))
-            else:
-                n_eval_rounds = int(np.ceil(max(np.log2(n), n_eval_rounds)))
-            scores = []
-            for lt in try_linkages:
-                # the clean-up and squareform are idempotent, so the condensed
-                # vector is shared by every candidate (the reference redoes
-                # both per candidate, sdm.py:1651)
-                z = sch.linkage(dmat_sf, method=lt, optimal_ordering=False)
-                mdls = np.array([_multinomial_mdl(c) for c in
-                                 bipartition_counts(z, n_eval_rounds)])
-                scores.append(np.sum(mdls / np.arange(1, n_eval_rounds + 1)))
-            linkage = try_linkages[scores.index(max(scores))]
-            if verbose:
-                print(linkage, tuple(zip(try_linkages, scores)), sep="\n")
-
-        return sch.linkage(dmat_sf, method=linkage,
-                           optimal_ordering=optimal_ordering)
+        return linkage_from_condensed(
+            dmat_sf, n, linkage=linkage, n_eval_rounds=n_eval_rounds,
+            is_euc_dist=is_euc_dist, optimal_ordering=optimal_ordering,
+            verbose=verbose)
 
     @staticmethod
     def hclust_tree(dmat, linkage="complete", n_eval_rounds=None,

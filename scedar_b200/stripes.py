@@ -89,6 +89,10 @@ class _DeviceOps(object):
         return cells.knn_stripe(k, exclude, r0, r1, precision=precision)
 
     # -- consumers ------------------------------------------
+    def squareform_rows(self, d, n, row_begin, out=None):
+        from . import device
+        return device.squareform_rows(d, n, row_begin=row_begin, out=out)
+
     def new_mask(self, n, device):
         return torch.ones(n, dtype=torch.uint8, device=device)
 
@@ -324,6 +328,82 @@ class StripedDistanceMatrix(object):
             idc = self._gather(idc[r0:r1])
             dist.all_reduce(stats, group=self.group)
         return curr, idc, tuple(int(v) for v in stats.tolist())
+
+    def condensed(self, dst=0):
+        """``scipy.spatial.distance.squareform(D)`` (the input of
+        ``sch.linkage``, sdm.py:1666) assembled on rank ``dst``: every rank
+        packs the strict upper triangle of its own rows -- one contiguous
+        segment of the vector -- and sends exactly that segment (rank 0's is
+        the longest, the last rank's the shortest: a padded gather would move
+        up to twice the bytes).  Returns the float64 device vector
+        [n(n-1)/2] on ``dst``, None elsewhere; what scipy's validity check
+        rejects raises ``ValueError`` on every rank."""
+        from . import hclust
+        if self.d_stripe is None:
+            self.compute_d()
+        n = self.n
+        base = [b * (2 * n - b - 1) // 2 for b, _ in self.stripes]
+        base.append(n * (n - 1) // 2 if n > 1 else 0)
+        total = base[-1]
+        if self.world == 1:
+            seg, flags = self.ops.squareform_rows(self.d_stripe, n, 0)
+            hclust._condensed_flags_check(int(flags.item()))
+            return seg
+        out = None
+        if self.rank == dst:
+            out = torch.empty(total, dtype=torch.float64,
+                              device=self.d_stripe.device)
+            mine = out[base[self.rank]:base[self.rank + 1]]
+            seg, flags = self.ops.squareform_rows(
+                self.d_stripe, n, self.row_begin, out=mine)
+            if seg.data_ptr() != mine.data_ptr():
+                mine.copy_(seg)
+            for r in range(self.world):
+                if r != dst and base[r + 1] > base[r]:
+                    dist.recv(out[base[r]:base[r + 1]], src=self._global(r),
+                              group=self.group)
+        else:
+            seg, flags = self.ops.squareform_rows(self.d_stripe, n,
+                                                  self.row_begin)
+            if seg.numel():
+                dist.send(seg.contiguous(), dst=self._global(dst),
+                          group=self.group)
+        # NCCL has no bitwise reduction: one slot per flag bit, MAX
+        bits = torch.stack([(flags.reshape(-1)[0] & 1), (flags.reshape(-1)[0] & 2)]
+                           ).to(torch.int32)
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.group)
+        bits = bits.tolist()
+        hclust._condensed_flags_check((1 if bits[0] else 0) |
+                                      (2 if bits[1] else 0))
+        return out
+
+    def _global(self, group_rank):
+        """Rank in the default group of a rank of ``self.group``."""
+        if self.group is None:
+            return group_rank
+        return dist.get_global_rank(self.group, group_rank)
+
+    def hclust_linkage(self, linkage="complete", n_eval_rounds=None,
+                       is_euc_dist=False, optimal_ordering=False,
+                       verbose=False, dst=0):
+        """``HClustTree.hclust_linkage`` (sdm.py:1629-1669) of the striped D:
+        the condensed vector is assembled on rank ``dst``, scipy's
+        (sequential) linkage runs there, and the (n-1) x 4 linkage matrix is
+        broadcast, so every rank returns it."""
+        from . import hclust
+        sf = self.condensed(dst=dst)
+        z = None
+        if self.rank == dst or self.world == 1:
+            z = hclust.linkage_from_condensed(
+                sf.cpu().numpy(), self.n, linkage=linkage,
+                n_eval_rounds=n_eval_rounds, is_euc_dist=is_euc_dist,
+                optimal_ordering=optimal_ordering, verbose=verbose)
+        if self.world > 1:
+            box = [z]
+            dist.broadcast_object_list(box, src=self._global(dst),
+                                       group=self.group)
+            z = box[0]
+        return z
 
     def _gather(self, t):
         """all-gather of ragged stripes: pad to the widest stripe, trim."""

@@ -42,6 +42,21 @@ class OracleOps(object):
 
 
     # -- consumers: NumPy stand-ins with the device operators' contract -----
+    def squareform_rows(self, d, n, row_begin, out=None):
+        a = d.numpy()
+        runs = [a[r, row_begin + r + 1:] for r in range(a.shape[0])]
+        v = np.concatenate(runs) if runs else np.zeros(0)
+        flags = torch.zeros(1, dtype=torch.int32)
+        if np.isnan(v).any():
+            flags |= 1
+        if any(not (a[r, row_begin + r] == 0) for r in range(a.shape[0])):
+            flags |= 2
+        seg = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64))
+        if out is not None:
+            out.copy_(seg)
+            seg = out
+        return seg, flags
+
     def new_mask(self, n, device):
         return torch.ones(n, dtype=torch.uint8)
 
@@ -238,3 +253,64 @@ def test_two_rank_stripes(n):
     assert got[0][1] == got[1][1]                    # same partition
     assert got[0][2] == got[1][2] == (n, k)          # every rank: all lists
     assert got[0][3] is True
+
+
+def _hclust_worker(rank, world, port, n, p, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.cluster.hierarchy as sch
+        from oracle import hclust_oracle as horc
+        from oracle import sdm_oracle as orc
+        from scedar_b200.stripes import StripedDistanceMatrix
+        xn = np.random.default_rng(4).normal(size=(n, p))
+        x = torch.from_numpy(xn) if rank == 0 else None
+        sdm = StripedDistanceMatrix(x, "euclidean", shape=(n, p),
+                                    device="cpu", ops=OracleOps())
+        d = orc.pdist(xn, "euclidean")
+        want = horc.squareform(d)
+        ok = True
+        for dst in range(world):
+            sf = sdm.condensed(dst=dst)
+            ok &= (sf is None) == (rank != dst)
+            if rank == dst:
+                ok &= bool(np.array_equal(sf.numpy(), want))
+        z = sdm.hclust_linkage(linkage="average")
+        ok &= bool(np.array_equal(z, sch.linkage(want, method="average")))
+        za = sdm.hclust_linkage(linkage="auto", is_euc_dist=True, dst=world - 1)
+        zo, _ = horc.hclust_linkage(d, linkage="auto", is_euc_dist=True)
+        ok &= bool(np.array_equal(za, zo))
+        # what scipy's validity check rejects is raised on every rank, even
+        # though only one rank's stripe holds the NaN
+        sdm.d_stripe = sdm.d_stripe.clone()
+        if rank == world - 1:
+            sdm.d_stripe[-2, -1] = float("nan")
+        try:
+            sdm.condensed()
+            ok = False
+        except ValueError as e:
+            ok &= "symmetric" in str(e)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [260, 130])
+def test_two_rank_condensed_and_linkage(n):
+    """Row-striped condensed form (exact-size send / recv of the ragged
+    segments) and the linkage on top of it (world 2, gloo)."""
+    world, p = 2, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() + n) % 2000
+    procs = [ctx.Process(target=_hclust_worker, args=(r, world, port, n, p, q))
+             for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(g[1] is True for g in got), got

@@ -4,7 +4,8 @@
         --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 
 Row-striped kNN without D (FP64 and tcgen05 fast path), the peer-store
-symmetric D, rare-sample detection and imputation over the ranks are compared
+symmetric D, rare-sample detection, imputation and the condensed D / linkage
+hand-off over the ranks are compared
 with the same computation on one GPU (rank 0 recomputes everything alone).
 Prints one JSON line with timings; exits non-zero on any mismatch."""
 import json
@@ -82,11 +83,21 @@ def main():
         lambda: sdm.impute(xi, idx, k, 5, 6.0, 2))
     out["impute_ms"] = round(t_imp, 2)
     out["impute_stats"] = list(gstats)
+    # condensed D (HClustTree hand-off): ragged segments sent to rank 0
+    sf, t_sf = timed(lambda: sdm.condensed(dst=0))
+    out["condensed_ms"] = round(t_sf, 2)
+    z = sdm.hclust_linkage(linkage="single", dst=world - 1)
+    assert z.shape == (n - 1, 4)
     if rank == 0:
         # the same operators on one GPU, no process group
         cells = dev.Cells.from_dense(x, "euclidean")
         d = cells.pdist_symmetric()
         assert torch.equal(d[sdm.row_begin:sdm.row_end], sdm.d_stripe), "D"
+        sf1, fl = dev.squareform_rows(d, n)
+        assert int(fl.item()) == 0 and torch.equal(sf, sf1), "condensed D"
+        import scipy.cluster.hierarchy as sch
+        assert np.array_equal(z, sch.linkage(sf1.cpu().numpy(), "single"))
+        del sf1
         alive = torch.ones(n, dtype=torch.uint8, device=device)
         lk1 = torch.zeros(n, dtype=torch.int32, device=device)
         kth = dev.masked_kth(d, alive, k)
