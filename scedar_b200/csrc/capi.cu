@@ -417,7 +417,7 @@ int scedar_num_correct_dist_mat(double* d, int64_t ldd, int64_t n, int has_upper
                      static_cast<cudaStream_t>(stream));
 }
 
-// ---- one-shot forms --------------------------------------------------------
+// ---- consumers --------------------------------------------------------------
 int scedar_knn_connectivity_csr(const int64_t* idx, const double* dist, int64_t n, int k,
                                 int64_t* indptr_out, int32_t* indices_out, double* data_out,
                                 void* stream) {
@@ -529,8 +529,23 @@ int scedar_impute_iter(const double* x_curr, int64_t ldx, int64_t n, int64_t p,
                             static_cast<cudaStream_t>(stream));
 }
 
+// ---- one-shot forms --------------------------------------------------------
+// every argument is checked before the first CUDA call, so a bad request costs
+// no device work (and is reported as ERR_ARG even without a device)
+static int check_oneshot(int64_t n, int64_t p, int metric, int precision, int64_t row_begin,
+                         int64_t row_end) {
+  SCEDAR_CHECK(check_metric(metric));
+  SCEDAR_CHECK(check_precision(precision));
+  if (n < 0 || p < 0) return fail(SCEDAR_ERR_ARG, "n and p must be >= 0");
+  if (row_begin < 0 || row_end < row_begin || row_end > n)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n");
+  return SCEDAR_OK;
+}
+
 int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric, int precision,
                        int64_t row_begin, int64_t row_end, double* d_out, void* stream) {
+  SCEDAR_CHECK(check_oneshot(n, p, metric, precision, row_begin, row_end));
+  if (row_end > row_begin && !d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
   scedar_cells_t* c = nullptr;
   SCEDAR_CHECK(scedar_cells_from_dense(x, n, p, p, metric, stream, &c));
   int rc = scedar_pdist_stripe(c, precision, row_begin, row_end, d_out, n, stream);
@@ -543,6 +558,8 @@ int scedar_pdist_dense(const double* x, int64_t n, int64_t p, int metric, int pr
 int scedar_pdist_csr(const void* indptr, int indptr_is_64, const int32_t* indices,
                      const double* data, int64_t n, int64_t p, int metric, int precision,
                      int64_t row_begin, int64_t row_end, double* d_out, void* stream) {
+  SCEDAR_CHECK(check_oneshot(n, p, metric, precision, row_begin, row_end));
+  if (row_end > row_begin && !d_out) return fail(SCEDAR_ERR_ARG, "d_out is NULL");
   scedar_cells_t* c = nullptr;
   SCEDAR_CHECK(scedar_cells_from_csr(indptr, indptr_is_64, indices, data, n, p, metric, stream, &c));
   int rc = scedar_pdist_stripe(c, precision, row_begin, row_end, d_out, n, stream);
@@ -555,6 +572,12 @@ int scedar_pdist_csr(const void* indptr, int indptr_is_64, const int32_t* indice
 int scedar_knn_dense(const double* x, int64_t n, int64_t p, int metric, int precision, int k,
                      int exclude, int64_t row_begin, int64_t row_end, int64_t* idx_out,
                      double* dist_out, void* stream) {
+  SCEDAR_CHECK(check_oneshot(n, p, metric, precision, row_begin, row_end));
+  if (k < 0 || k > n - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
+  if (exclude != SCEDAR_EXCLUDE_FIRST && exclude != SCEDAR_EXCLUDE_SELF)
+    return fail(SCEDAR_ERR_ARG, "exclude must be 0 (first) or 1 (self)");
+  if (k > 0 && row_end > row_begin && (!idx_out || !dist_out))
+    return fail(SCEDAR_ERR_ARG, "NULL buffer");
   scedar_cells_t* c = nullptr;
   SCEDAR_CHECK(scedar_cells_from_dense(x, n, p, p, metric, stream, &c));
   int rc = scedar_knn_stripe(c, precision, k, exclude, row_begin, row_end, idx_out, dist_out, stream);
@@ -646,6 +669,8 @@ int scedar_knn_dense_host(const double* x, int64_t n, int64_t p, int metric, int
   SCEDAR_CHECK(check_precision(precision));
   if (n < 0 || p < 0) return fail(SCEDAR_ERR_ARG, "n and p must be >= 0");
   if (k < 0 || k > n - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
+  if (exclude != SCEDAR_EXCLUDE_FIRST && exclude != SCEDAR_EXCLUDE_SELF)
+    return fail(SCEDAR_ERR_ARG, "exclude must be 0 (first) or 1 (self)");
   if (n == 0 || k == 0) return SCEDAR_OK;
   if (!idx_out || !dist_out || (p > 0 && !x)) return fail(SCEDAR_ERR_ARG, "NULL buffer");
   SCEDAR_CUDA(cudaSetDevice(device));
