@@ -92,3 +92,58 @@ def test_rare_and_impute(ref, seed):
     np.testing.assert_array_equal(np.asarray(out._x), ox)
     key = (k, n_do, 0.2, n_iter, np.median)
     np.testing.assert_array_equal(fi._res_lut[key][1].toarray(), oidc)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_hclust(ref, seed):
+    """oracle/hclust_oracle.py against the live HClustTree (sdm.py:1369-1693)
+    on the reference's own D (bit-identical input, so the linkage matrices
+    must be identical too)."""
+    from oracle import hclust_oracle as horc
+    import scedar.eda as ref_eda
+    SDM, _ = ref
+    H = ref_eda.HClustTree
+    rng = np.random.default_rng(200 + seed)
+    n, p = int(rng.integers(6, 90)), int(rng.integers(2, 30))
+    x = rng.normal(size=(n, p)) + rng.integers(0, 3, size=(n, 1)) * 2.0
+    metric = ("euclidean", "cosine", "correlation")[seed % 3]
+    if metric == "correlation" and p < 3:
+        p = 3
+        x = rng.normal(size=(n, p))
+    d = SDM(x, metric=metric)._d
+    euc = metric == "euclidean"
+    for lt in ("single", "complete", "average", "weighted") + \
+            (("centroid", "median", "ward") if euc else ()):
+        z, _ = horc.hclust_linkage(d, linkage=lt)
+        np.testing.assert_array_equal(z, H.hclust_linkage(d, linkage=lt))
+    rounds = int(rng.integers(-2, 12))
+    for oo in (False, True):
+        z, _ = horc.hclust_linkage(d, linkage="auto", n_eval_rounds=rounds,
+                                   is_euc_dist=euc, optimal_ordering=oo)
+        want = H.hclust_linkage(d, linkage="auto", n_eval_rounds=rounds,
+                                is_euc_dist=euc, optimal_ordering=oo)
+        np.testing.assert_array_equal(z, want)
+    tree = H.hclust_tree(d, linkage="average")
+    z, _ = horc.hclust_linkage(d, linkage="average")
+    assert tree.leaf_ids() == horc.leaf_ids(z)
+    r = int(rng.integers(1, 8))
+    import scipy.cluster.hierarchy as sch
+    assert tree.n_round_bipar_cnt(r) == horc.n_round_bipar_cnt(sch.to_tree(z), r)
+    assert H.sort_x_by_d(x, metric=metric, optimal_ordering=True) == \
+        horc.sort_x_by_d(x, metric=metric, optimal_ordering=True)
+    # the product's host logic (no device involved) on the same linkage
+    from scedar_b200 import hclust as ph
+    assert ph.bipartition_counts(z, r) == tree.n_round_bipar_cnt(r)
+    sf = horc.squareform(d)
+    for oo in (False, True):
+        got = ph.linkage_from_condensed(sf, n, linkage="auto",
+                                        n_eval_rounds=rounds, is_euc_dist=euc,
+                                        optimal_ordering=oo)
+        want = H.hclust_linkage(d, linkage="auto", n_eval_rounds=rounds,
+                                is_euc_dist=euc, optimal_ordering=oo)
+        np.testing.assert_array_equal(got, want)
+    # MultinomialMdl.mdl on count vectors (mdl.py:86-106)
+    from scedar.eda.mdl import MultinomialMdl
+    for c in tree.n_round_bipar_cnt(r) + [[], [4], [2, 2, 2]]:
+        assert horc.multinomial_mdl(c) == MultinomialMdl(np.array(c)).mdl
+        assert ph._multinomial_mdl(np.array(c)) == MultinomialMdl(np.array(c)).mdl
