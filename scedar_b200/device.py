@@ -28,6 +28,26 @@ def _guard():
                            "CPU fallback")
 
 
+# Every tensor the host modules allocate themselves goes through these three,
+# so the package has exactly one place that names the device.
+DEVICE = "cuda"
+
+
+def zeros(shape, dtype):
+    _guard()
+    return torch.zeros(shape, dtype=dtype, device=DEVICE)
+
+
+def ones(shape, dtype):
+    _guard()
+    return torch.ones(shape, dtype=dtype, device=DEVICE)
+
+
+def empty(shape, dtype):
+    _guard()
+    return torch.empty(shape, dtype=dtype, device=DEVICE)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -61,7 +61,7 @@ def _condensed_of(dmat):
         if dmat.dim() != 2 or dmat.shape[0] != dmat.shape[1]:
             raise ValueError("dmat must be a 2D (n_samples, n_samples)"
                              " np array")
-        t = dmat.detach().to(device="cuda", dtype=torch.float64).clone()
+        t = dmat.detach().to(device=dev.DEVICE, dtype=torch.float64).clone()
     else:
         a = np.array(dmat, dtype="float")
         if a.ndim != 2 or a.shape[0] != a.shape[1]:

@@ -80,8 +80,8 @@ class RareSampleDetection(object):
         for i in range(1, n_iter + 1):
             i_d_cutoff = (d_cutoff +
                           (n_iter - i) / n_iter * max(0, d_max - d_cutoff))
-            alive = torch.ones(m, dtype=torch.uint8, device="cuda")
-            scratch = torch.zeros(m, dtype=torch.int32, device="cuda")
+            alive = dev.ones(m, torch.uint8)
+            scratch = dev.zeros(m, torch.int32)
             kept = dev.rare_update(dist[:, k - 1:], i_d_cutoff, i, alive,
                                    scratch, ldk=k)
             sel = dev.compact_alive(alive, kept)
@@ -113,9 +113,9 @@ class RareSampleDetection(object):
         n = sdm._x.shape[0]
         if k > 127:
             raise NotImplementedError("rare-sample detection with k > 127")
-        alive = torch.ones(n, dtype=torch.uint8, device="cuda")
-        last_kept = torch.zeros(n, dtype=torch.int32, device="cuda")
-        kth = torch.empty(n, dtype=torch.float64, device="cuda")
+        alive = dev.ones(n, torch.uint8)
+        last_kept = dev.zeros(n, torch.int32)
+        kth = dev.empty(n, torch.float64)
 
         def kth_of_alive(rank):
             for r0, r1, stripe in sdm._d_stripes():
@@ -225,9 +225,8 @@ class FeatureImputation(object):
         curr = dev.to_device(np.ascontiguousarray(x_host, dtype=np.float64))
         nxt = torch.empty_like(curr)
         knn_dev = dev.to_device(knn)
-        idc = torch.zeros((n_samples, n_features), dtype=torch.int32,
-                          device="cuda")
-        counters = torch.zeros(2, dtype=torch.int64, device="cuda")
+        idc = dev.zeros((n_samples, n_features), torch.int32)
+        counters = dev.zeros(2, torch.int64)
         stats = "Preparation: {:.2f}s\n".format(time.time() - start_time)
         if verbose:
             print(stats)

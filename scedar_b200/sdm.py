@@ -197,7 +197,7 @@ class SampleDistanceMatrix(object):
         out = np.empty(dev.condensed_len(n), dtype=np.float64)
         if n == 0:
             return out
-        flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+        flags = dev.zeros(1, torch.int32)
         for r0, r1, stripe in self._d_stripes():
             seg, _ = dev.squareform_rows(stripe, n, row_begin=r0, flags=flags)
             b0, b1 = dev.condensed_base(r0, n), dev.condensed_base(r1, n)
