@@ -297,11 +297,12 @@ def _hclust_worker(rank, world, port, n, p, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [260, 130])
-def test_two_rank_condensed_and_linkage(n):
+@pytest.mark.parametrize("n,world", [(260, 2), (130, 2), (390, 3)])
+def test_condensed_and_linkage_over_ranks(n, world):
     """Row-striped condensed form (exact-size send / recv of the ragged
-    segments) and the linkage on top of it (world 2, gloo)."""
-    world, p = 2, 7
+    segments) and the linkage on top of it (gloo, world 2 and 3; n = 130
+    leaves the last rank two rows)."""
+    p = 7
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 35500 + (os.getpid() + n) % 2000
