@@ -2,9 +2,6 @@
 (``scedar_pdist_dense``, ``scedar_pdist_csr``, ``scedar_knn_dense``: prepare +
 run + free in one call) against the handle-based path and the oracle.
 
-Written after this round's GPU budget was spent: the wrappers only sequence
-entry points that the other ``-m gpu`` tests exercise, but this file itself had
-not yet run on a B200 when it was committed -- hence collected last.
 Needs a B200: ``pytest -m gpu``."""
 import ctypes
 
