@@ -56,6 +56,20 @@ def test_install_on_live_reference_cpu():
     assert s._d.shape == (0, 0) and s.sids == []
     with pytest.raises(ValueError):
         cls(np.arange(12.0).reshape(4, 3), use_pdist=False)._d
+    # HClustTree: the reference's own hclust_tree reaches the patched
+    # hclust_linkage by name (sdm.py:1671-1678) and keeps its error behaviour
+    # (tests/test_eda/test_dense_sdm.py:1306-1311) -- no device involved
+    import scedar.eda.sdm as ref_sdm_mod
+    tree_cls = ref_sdm_mod.HClustTree
+    orig = tree_cls.__dict__["hclust_linkage"]
+    try:
+        patch.install_hclust(tree_cls)
+        with pytest.raises(ValueError):
+            tree_cls.hclust_tree(np.arange(5))
+        with pytest.raises(ValueError):
+            tree_cls.hclust_tree(np.arange(10).reshape(2, 5))
+    finally:
+        tree_cls.hclust_linkage = orig
 
 
 @pytest.mark.gpu
@@ -110,3 +124,52 @@ def test_patched_hclust_matches_dropin():
         sch.to_tree(want).pre_order(lambda nd: nd.get_id())
     assert a._lazy_load_d is None
     assert np.array_equal(RefTree.hclust_linkage(a._d, linkage="ward"), want)
+
+
+def test_patched_live_reference_on_fake_device(monkeypatch):
+    """The reference's OWN class with the B200 hooks patched in (device
+    operators replaced by the CPU stand-ins of tests/fake_device.py) against
+    the unpatched reference: the wiring of every hook, on the real class, in
+    the build container only."""
+    from oracle.ref_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("live reference only exists in the build container")
+    import warnings
+    warnings.simplefilter("ignore")
+    import fake_device
+    fake_device.install(monkeypatch)
+    ref = load_reference()
+    import scedar.eda.sdm as ref_sdm_mod
+    from scedar_b200 import patch, synth
+    cls = patch.install_sdm(type("RefSub", (ref,), {}))
+    tree = patch.install_hclust(type("TreeSub", (ref_sdm_mod.HClustTree,), {}))
+    x = synth.blobs(90, 14, seed=6, n_blobs=3)
+    for metric in ("cosine", "correlation", "euclidean"):
+        a, b = cls(x, metric=metric), ref(x, metric=metric)
+        np.testing.assert_allclose(a._d, b._d, rtol=1e-10, atol=1e-13)
+        assert a._d is a._lazy_load_d
+        assert a.s_knn_ind_lut(7) == b.s_knn_ind_lut(7)
+        ta, da = a.s_knns(7)
+        tb, db = b.s_knns(7)
+        assert np.array_equal(np.array(ta), np.array(tb))
+        np.testing.assert_allclose(np.array(da), np.array(db), rtol=1e-10)
+        assert np.array_equal(a._col_argsorted_d, b._col_argsorted_d)
+        np.testing.assert_allclose(a.s_ith_nn_d(3), b.s_ith_nn_d(3),
+                                   rtol=1e-10)
+        ca, cb = a.s_knn_connectivity_matrix(4), b.s_knn_connectivity_matrix(4)
+        assert np.array_equal(ca.indices, cb.indices)
+        np.testing.assert_allclose(ca.data, cb.data, rtol=1e-10)
+        # reference methods that were not touched keep working on the patched
+        # class: ind_x slices the D the hooks produced
+        sub = a.ind_x([5, 1, 60])
+        np.testing.assert_allclose(sub._d, b.ind_x([5, 1, 60])._d,
+                                   rtol=1e-10, atol=1e-13)
+        za = tree.hclust_linkage(a, linkage="average")
+        zb = ref_sdm_mod.HClustTree.hclust_linkage(b._d, linkage="average")
+        assert np.array_equal(za[:, [0, 1, 3]], zb[:, [0, 1, 3]])
+        np.testing.assert_allclose(za[:, 2], zb[:, 2], rtol=1e-9)
+    nd_a = cls(x, metric="euclidean", use_pdist=False)
+    nd_b = ref(x, metric="euclidean", use_pdist=False)
+    assert nd_a.s_knn_ind_lut(5) == nd_b.s_knn_ind_lut(5)
+    with pytest.raises(ValueError):
+        nd_a._d
