@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SCEDAR_ABI_VERSION 1
+#define SCEDAR_ABI_VERSION 2
 
 /* metric: SampleDistanceMatrix(metric=...), scedar/eda/sdm.py:1211-1217 */
 enum {
@@ -51,9 +51,18 @@ enum {
 /* precision of the Gram contraction */
 enum {
   SCEDAR_PRECISION_FP64 = 0, /* float64 tensor-core (DMMA) path, <=1e-10 rel */
-  SCEDAR_PRECISION_FAST = 1  /* 3xFP16 tcgen05 path: D to a stated tolerance
+  SCEDAR_PRECISION_FAST = 1, /* 3xFP16 tcgen05 path: D to a stated tolerance
                                 (1e-5 cosine/correlation; 2e-6 max|x|^2 on d^2
                                 euclidean), kNN exact (FP64 re-rank)         */
+  SCEDAR_PRECISION_FP64_I8 = 2,   /* float64-grade Gram as an error-free split
+                                on the INT8 tensor pipe (tcgen05 kind::i8, 7
+                                byte slices, exact INT32 accumulation, float64
+                                epilogue): <=1e-10 rel like FP64, dot products
+                                of integer data exact.  n_features <= 4096,
+                                otherwise the DMMA path runs                  */
+  SCEDAR_PRECISION_FP64_I8S6 = 3  /* the same with 6 slices (21 instead of 28
+                                products): |dD| <= 1e-11 of max|x|^2-scaled
+                                products, see gram_oz.cu                      */
 };
 
 /* which of the k+1 nearest is dropped */
@@ -179,6 +188,12 @@ int scedar_stripe_close(void* peer_ptr);
 int scedar_pdist_lower_rows(const scedar_cells_t* cells, int64_t row_begin,
                             int64_t row_end, double* d, int64_t ldd,
                             void* stream);
+
+/* scedar_pdist_lower_rows with the Gram kernel chosen by `precision`
+ * (SCEDAR_PRECISION_FP64, _FP64_I8 or _FP64_I8S6). */
+int scedar_pdist_lower_rows_prec(const scedar_cells_t* cells, int precision,
+                                 int64_t row_begin, int64_t row_end, double* d,
+                                 int64_t ldd, void* stream);
 
 /* Whole matrix at once, computing only the lower-triangle tiles and writing
  * each tile and its transpose (half the contraction work). */

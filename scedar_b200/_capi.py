@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libscedar_b200.so")
 
 METRIC_IDS = {"cosine": 0, "correlation": 1, "euclidean": 2}
-PRECISION_IDS = {"fp64": 0, "fast": 1}
+PRECISION_IDS = {"fp64": 0, "fast": 1, "fp64_i8": 2, "fp64_i8s6": 3}
 EXCLUDE_FIRST, EXCLUDE_SELF = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, 1, 2, 3, 4
 NCDM_BAD_DIAG, NCDM_ASYMMETRIC = 1, 2
@@ -37,6 +37,8 @@ SIGNATURES = {
                                        c_int64, c_void_p]),
     "scedar_pdist_lower_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p,
                                         c_int64, c_void_p]),
+    "scedar_pdist_lower_rows_prec": (c_int, [c_void_p, c_int, c_int64, c_int64,
+                                             c_void_p, c_int64, c_void_p]),
     "scedar_cells_free": (c_int, [c_void_p]),
     "scedar_cells_n": (c_int64, [c_void_p]),
     "scedar_cells_p": (c_int64, [c_void_p]),
@@ -120,7 +122,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.scedar_abi_version() != 1:
+        if lib.scedar_abi_version() != 2:
             raise ImportError("scedar_b200: ABI version mismatch")
         _lib = lib
     return _lib

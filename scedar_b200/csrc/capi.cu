@@ -73,8 +73,17 @@ int check_metric(int metric) {
 }
 
 int check_precision(int precision) {
-  if (precision == SCEDAR_PRECISION_FP64 || precision == SCEDAR_PRECISION_FAST) return SCEDAR_OK;
-  return fail(SCEDAR_ERR_ARG, "precision must be 0 (fp64) or 1 (fast)");
+  if (precision >= SCEDAR_PRECISION_FP64 && precision <= SCEDAR_PRECISION_FP64_I8S6)
+    return SCEDAR_OK;
+  return fail(SCEDAR_ERR_ARG, "precision must be 0 (fp64), 1 (fast), 2 (fp64_i8) or 3 (fp64_i8s6)");
+}
+
+// slices of the INT8 split path for `precision`, 0 when the DMMA kernel runs
+// (not requested, or rows longer than the split's INT32 accumulators allow)
+int oz_slices(const scedar_cells* c, int precision) {
+  if (precision != SCEDAR_PRECISION_FP64_I8 && precision != SCEDAR_PRECISION_FP64_I8S6) return 0;
+  if (!oz_supported(c)) return 0;
+  return precision == SCEDAR_PRECISION_FP64_I8 ? 7 : 6;
 }
 
 int check_rows(const scedar_cells* c, int64_t row_begin, int64_t row_end) {
@@ -132,7 +141,8 @@ int new_cells(int64_t n, int64_t p, int metric, cudaStream_t s, scedar_cells** o
 //              reaches HBM (k + 1 <= 32); the only form that needs no scratch
 // SCEDAR_B200_KNN_FP64 = symmetric | chunked | fused forces one (testing).
 int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin,
-                    int64_t row_end, int64_t* idx_out, double* dist_out, cudaStream_t s) {
+                    int64_t row_end, int64_t* idx_out, double* dist_out, cudaStream_t s,
+                    int oz_S) {
   const int64_t rows = row_end - row_begin;
   if (k == 0 || rows <= 0) return SCEDAR_OK;
   const int K = k + 1;
@@ -164,7 +174,9 @@ int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin
     mode = CHUNKED;   // measured: 1.2-1.4x over fused at p = 2000, 2x slower at p = 50
   else
     mode = FUSED;
-  if (forced && K <= 32) {
+  // the INT8 split kernel has no fused top-k: D goes through scratch
+  if (oz_S && mode == FUSED) mode = CHUNKED;
+  if (forced && K <= 32 && !oz_S) {
     if (!strcmp(forced, "fused")) mode = FUSED;
     if (!strcmp(forced, "chunked")) mode = CHUNKED;
     if (!strcmp(forced, "symmetric") && rows == n) mode = SYM;
@@ -172,7 +184,8 @@ int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin
   if (mode == SYM) {
     Scratch dbuf;
     if (dbuf.alloc((size_t)d_bytes, s) == SCEDAR_OK) {
-      SCEDAR_CHECK(launch_gram_symmetric(c, dbuf.as<double>(), n, s));
+      SCEDAR_CHECK(oz_S ? launch_oz_symmetric(c, oz_S, dbuf.as<double>(), n, s)
+                        : launch_gram_symmetric(c, dbuf.as<double>(), n, s));
       return launch_topk_from_d(dbuf.as<double>(), n, n, 0, n, k, exclude, idx_out, dist_out, s);
     }
     mode = CHUNKED;   // fragmentation: fall through with a smaller request
@@ -186,16 +199,19 @@ int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin
     chunk = std::min(chunk, round_up(rows, 128));
     Scratch dbuf;
     if (dbuf.alloc(sizeof(double) * (size_t)chunk * (size_t)n, s) == SCEDAR_OK) {
+      // the split kernel takes 128-aligned stripes
+      if (oz_S && row_begin % 128 != 0) oz_S = 0;
       for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk) {
         const int64_t r1 = std::min(row_end, r0 + chunk);
-        SCEDAR_CHECK(launch_gram_stripe(c, r0, r1, dbuf.as<double>(), n, s));
+        SCEDAR_CHECK(oz_S ? launch_oz_stripe(c, oz_S, r0, r1, dbuf.as<double>(), n, s)
+                          : launch_gram_stripe(c, r0, r1, dbuf.as<double>(), n, s));
         SCEDAR_CHECK(launch_topk_from_d(dbuf.as<double>(), n, n, r0, r1, k, exclude,
                                         idx_out + (r0 - row_begin) * k,
                                         dist_out + (r0 - row_begin) * k, s));
       }
       return SCEDAR_OK;
     }
-    if (K > 32) return SCEDAR_ERR_NOMEM;
+    if (K > 32 || oz_S) return SCEDAR_ERR_NOMEM;
   }
   const int splits = gram_topk_splits(c, rows);
   Scratch pd, pi;
@@ -285,9 +301,26 @@ int scedar_pdist_lower_rows(const scedar_cells_t* c, int64_t row_begin, int64_t 
   return launch_gram_lower_rows(c, row_begin, row_end, d, ldd, static_cast<cudaStream_t>(stream));
 }
 
+int scedar_pdist_lower_rows_prec(const scedar_cells_t* c, int precision, int64_t row_begin,
+                                 int64_t row_end, double* d, int64_t ldd, void* stream) {
+  SCEDAR_CHECK(check_rows(c, row_begin, row_end));
+  SCEDAR_CHECK(check_precision(precision));
+  if (precision == SCEDAR_PRECISION_FAST)
+    return fail(SCEDAR_ERR_UNSUPPORTED, "row ranges of the lower triangle are FP64-grade only");
+  const int S = oz_slices(c, precision);
+  if (!S) return scedar_pdist_lower_rows(c, row_begin, row_end, d, ldd, stream);
+  if (row_begin % kRowPad != 0)
+    return fail(SCEDAR_ERR_ARG, "row_begin must be 128-aligned");
+  if (row_end == row_begin) return SCEDAR_OK;
+  if (!d) return fail(SCEDAR_ERR_ARG, "d is NULL");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  return launch_oz_lower_rows(c, S, row_begin, row_end, d, ldd, static_cast<cudaStream_t>(stream));
+}
+
 int scedar_cells_free(scedar_cells_t* c) {
   if (!c) return SCEDAR_OK;
   if (c->fast) fast_state_free(c->fast, c->stream);
+  if (c->oz) oz_state_free(c->oz, c->stream);
   if (c->xw) cudaFreeAsync(c->xw, c->stream);
   if (c->stat) cudaFreeAsync(c->stat, c->stream);
   delete c;
@@ -307,6 +340,10 @@ int scedar_pdist_stripe(const scedar_cells_t* c, int precision, int64_t row_begi
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
   if (precision == SCEDAR_PRECISION_FAST)
     return launch_fast_stripe(c, row_begin, row_end, d_out, ldd, static_cast<cudaStream_t>(stream));
+  // the split kernel takes 128-aligned stripes; ragged ones run on DMMA
+  const bool aligned = row_begin % kRowPad == 0 && (row_end % kRowPad == 0 || row_end == c->n);
+  if (const int S = aligned ? oz_slices(c, precision) : 0)
+    return launch_oz_stripe(c, S, row_begin, row_end, d_out, ldd, static_cast<cudaStream_t>(stream));
   return launch_gram_stripe(c, row_begin, row_end, d_out, ldd, static_cast<cudaStream_t>(stream));
 }
 
@@ -319,6 +356,8 @@ int scedar_pdist_symmetric(const scedar_cells_t* c, int precision, double* d_out
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
   if (precision == SCEDAR_PRECISION_FAST)
     return launch_fast_stripe(c, 0, c->n, d_out, ldd, static_cast<cudaStream_t>(stream), 1);
+  if (const int S = oz_slices(c, precision))
+    return launch_oz_symmetric(c, S, d_out, ldd, static_cast<cudaStream_t>(stream));
   return launch_gram_symmetric(c, d_out, ldd, static_cast<cudaStream_t>(stream));
 }
 
@@ -327,10 +366,13 @@ int scedar_pdist_stripe_p2p(const scedar_cells_t* c, int precision, int rank, in
                             int64_t ldd, void* stream) {
   if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
   SCEDAR_CHECK(check_precision(precision));
-  if (precision != SCEDAR_PRECISION_FP64)
-    return fail(SCEDAR_ERR_UNSUPPORTED, "peer-store stripes are FP64 only");
+  if (precision == SCEDAR_PRECISION_FAST)
+    return fail(SCEDAR_ERR_UNSUPPORTED, "peer-store stripes are FP64-grade only");
   if (!stripe_begin || !stripe_ptr) return fail(SCEDAR_ERR_ARG, "NULL stripe table");
   if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (const int S = oz_slices(c, precision))
+    return launch_oz_stripe_p2p(c, S, rank, world, stripe_begin, stripe_ptr, ldd,
+                                static_cast<cudaStream_t>(stream));
   return launch_gram_stripe_p2p(c, rank, world, stripe_begin, stripe_ptr, ldd,
                                 static_cast<cudaStream_t>(stream));
 }
@@ -394,7 +436,8 @@ int scedar_knn_stripe(const scedar_cells_t* c, int precision, int k, int exclude
   // the tensor-core pass proposes 32 candidates per cell; larger k runs FP64
   if (precision == SCEDAR_PRECISION_FAST && k <= fast_knn_max_k())
     return launch_fast_knn(c, k, exclude, row_begin, row_end, idx_out, dist_out, s);
-  return knn_stripe_fp64(c, k, exclude, row_begin, row_end, idx_out, dist_out, s);
+  return knn_stripe_fp64(c, k, exclude, row_begin, row_end, idx_out, dist_out, s,
+                         oz_slices(c, precision));
 }
 
 int scedar_col_sort(const double* d, int64_t ldd, int64_t rows, int64_t n_cols,

@@ -66,6 +66,7 @@ struct scedar_cells {
   double* stat = nullptr;  // [n_pad] sqrt(1/|x|^2) (0 for zero rows) or |x|^2
   cudaStream_t stream = nullptr;  // creation stream: the frees are ordered on it
   void* fast = nullptr;  // FastState of the tensor-core path (gram_tc.cu), lazy
+  void* oz = nullptr;    // OzState of the INT8 split path (gram_oz.cu), lazy
   CUtensorMap xmap;      // TMA view of xw: boxes of 128 rows x 16 doubles, 128B swizzle
 };
 
@@ -113,10 +114,24 @@ int launch_fast_stripe(const scedar_cells* c, int64_t row_begin, int64_t row_end
 int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin,
                     int64_t row_end, int64_t* idx_out, double* dist_out,
                     cudaStream_t s);
-// capi.cu: the FP64 kNN of a row range (fused when k+1 <= 32)
+// gram_oz.cu (FP64-grade Gram as an error-free split on the INT8 tensor pipe;
+// S = 6 or 7 slices)
+void oz_state_free(void* oz, cudaStream_t s);
+bool oz_supported(const scedar_cells* c);
+int launch_oz_stripe(const scedar_cells* c, int S, int64_t row_begin, int64_t row_end,
+                     double* d_out, int64_t ldd, cudaStream_t s);
+int launch_oz_symmetric(const scedar_cells* c, int S, double* d_out, int64_t ldd,
+                        cudaStream_t s);
+int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
+                         const int64_t* stripe_begin, double* const* stripe_ptr,
+                         int64_t ldd, cudaStream_t s);
+int launch_oz_lower_rows(const scedar_cells* c, int S, int64_t row_begin, int64_t row_end,
+                         double* d_full, int64_t ldd, cudaStream_t s);
+// capi.cu: the FP64 kNN of a row range (fused when k+1 <= 32); oz_S = 6 / 7
+// computes the distances with the INT8 split kernel instead of DMMA
 int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin,
                     int64_t row_end, int64_t* idx_out, double* dist_out,
-                    cudaStream_t s);
+                    cudaStream_t s, int oz_S = 0);
 
 // topk.cu
 int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols,

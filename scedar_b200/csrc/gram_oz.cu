@@ -1,0 +1,733 @@
+// K2 (FP64-grade path on the tcgen05 tensor cores) -- Gram contraction X.Xt as
+// an error-free split over the INT8 tensor pipe (tcgen05.mma.kind::i8, exact
+// INT32 accumulation in TMEM, operands streamed by TMA), with the float64 metric
+// epilogue of gram_f64.cu fused.  Selected by SCEDAR_PRECISION_FP64_I8 (7
+// slices) / SCEDAR_PRECISION_FP64_I8S6 (6 slices).
+//
+// Replaces the same reference arithmetic as gram_f64.cu: np.dot(x, x.T)
+// (scedar/eda/sdm.py:1245-1247), the cosine / correlation scaling (1249-1266),
+// sklearn's euclidean formula (1216) and num_correct_dist_mat's clean-up
+// (215-221).  tcgen05 has no f64 kind; the DMMA kernel sits at 0.92 of a
+// 37 TFLOP/s pipe, the INT8 pipe is two orders of magnitude wider.
+//
+// Split (Ozaki scheme, fixed point per row).  Row i of the working copy is
+// scaled by 2^-e_i (2^e_i > max|x_i|) and truncated to F = 7 + 8(S-1)
+// fractional bits: q = floor(x 2^(F - e_i)), a two's-complement integer that is
+// cut into S bytes, most significant first.  The top byte is stored
+// offset-binary (a_0 + 128), so EVERY slice is an unsigned byte and the slices
+// of the column operand can be stacked along N: one MMA of N = 64 m columns
+// multiplies slice s of the row tile with slices t0..t0+m-1 of the column tile
+// and lands on the accumulators of the diagonals s+t0 .. s+t0+m-1, which sit
+// side by side in TMEM (diagonal d = columns [64 d, 64 d + 64)).  Only the
+// pairs with s + t < S are formed (S(S+1)/2 products in 8 (S=6) / 10 (S=7)
+// instructions per 32-byte K step); the dropped pairs are below 2^-(8S-2) of
+// the row scales.  The offset of the top bytes contributes 128 (R_d[i] +
+// R_d[j]) (+ 2^14 K on diagonal 0) with R_d the byte sums of a row; the
+// epilogue subtracts it exactly in 64-bit integers, converts the two halves of
+// the weighted sum to float64 (each conversion exact) and joins them with one
+// FMA: P = 2^(e_i + e_j - 30) (hi + lo 2^(-8(S-3))).  Integer input (counts)
+// therefore gives the exact dot product, identical rows give P_ij == P_ii ==
+// P_jj bit for bit (the statistic comes from the same integers), and for S = 7
+// the truncation (<= 6 p 2^-56 of the row scales, a few 1e-15 of |x_i||x_j| on
+// log counts) is of the size of DGEMM's own rounding.
+//
+// Kernel (persistent, one CTA per SM, 320 threads):
+//   warp 0     TMA producer: per 64-byte K slab S boxes of 128 rows (row-tile
+//              slices) + S boxes of 64 rows (column-tile slices), 64B swizzle,
+//              ring of 2 (S=7) / 3 (S=6) stages, full/empty mbarriers
+//   warp 1     MMA issuer (elected lane), descriptors = stage base + constant
+//   warps 2-9  epilogue: TMEM lane quarter = warp % 4, column half = (warp-2)/4;
+//              4 columns at a time: S x tcgen05.ld.x4 -> integers -> float64 ->
+//              finish_entry -> mirrored store straight from registers (lanes =
+//              consecutive rows: coalesced), row-major store through a 9 KB
+//              staging tile
+// TMEM holds S x 64 columns (448 of 512 for S = 7): no second accumulator set,
+// so the epilogue (a few % of a tile at p = 2000) is not overlapped with the
+// next tile's MMAs; the producer does run ahead into the next tile.
+// Tiles (128 rows x 64 columns) come from a host-built list in L2-friendly
+// order, dealt round-robin to the CTAs; the list also carries what to store
+// (tile / mirrored tile), so the whole-matrix, row-stripe, peer-store and
+// row-range forms are one kernel.
+// Roofline: INT8 tensor pipe; executed MACs = S(S+1)/2 x the algorithmic ones.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "tc_sm100.cuh"
+#include "topk_list.cuh"
+
+namespace scedar {
+namespace {
+
+constexpr int OM = 128;            // tile rows = TMEM lanes
+constexpr int ON = 64;             // tile columns (per slice diagonal)
+constexpr int OKB = 64;            // K bytes per slab (one 64B-swizzle row)
+constexpr int A_SLAB = OM * OKB;   // 8 KB
+constexpr int B_SLAB = ON * OKB;   // 4 KB
+constexpr int oz_stage_bytes(int S) { return S * (A_SLAB + B_SLAB); }
+constexpr int oz_stages(int S) { return S <= 6 ? 3 : 2; }
+constexpr int STG_LD = 9;          // staging row stride in doubles (8 columns + 1)
+constexpr int STG_BYTES = OM * STG_LD * 8;
+constexpr int OZ_BAR_BYTES = 256;
+constexpr int oz_smem(int S) {
+  return 1024 + oz_stages(S) * oz_stage_bytes(S) + STG_BYTES + OZ_BAR_BYTES;
+}
+static_assert(oz_smem(6) <= 227 * 1024 && oz_smem(7) <= 227 * 1024, "shared memory budget");
+constexpr int OZ_EPI_WARPS = 8;
+constexpr int OZ_EPI_THREADS = 32 * OZ_EPI_WARPS;
+constexpr int OZ_THREADS = 64 + OZ_EPI_THREADS;
+constexpr int OZ_KMAX = 4096;      // K columns: 7 * 255^2 * 4096 < 2^31
+constexpr int kOzPeers = 16;
+constexpr int TILE_DIRECT = 1, TILE_MIRROR = 2;
+
+struct OzTile {
+  int32_t I, J;      // row tile (128 rows), column tile (64 columns)
+  int32_t flags;     // TILE_DIRECT: store D[I rows][J cols]; TILE_MIRROR: store the transpose
+  int32_t pad;
+};
+
+struct OzArgs {
+  const double* sc;        // 2^(e_i - 15)
+  const long long* hi;     // offset corrections of the two halves of the weighted sum
+  const long long* lo;
+  const double* stat;      // sqrt(1/P_ii) (0 for zero rows) or P_ii, from the same integers
+  long long c0;            // 2^14 K << 16: the offset x offset term of diagonal 0
+  int64_t n, n_pl;         // cells; rows per slice plane
+  int64_t row_lo, row_hi;  // rows of D this launch may store
+  int kslabs;
+  int euclid;
+  const OzTile* tiles;
+  int n_tiles;
+  int64_t ldd;
+  int world;                              // output stripes (1 for a single buffer)
+  int64_t stripe_begin[kOzPeers + 1];     // row ranges of the stripes
+  double* stripe_ptr[kOzPeers];
+};
+
+// weighted sum of the diagonal accumulators minus the offset terms -> float64
+template <int S>
+__device__ __forceinline__ double oz_value(const uint32_t (&acc)[S], long long hi_corr,
+                                           long long lo_corr) {
+  long long hi = ((long long)acc[0] << 16) + ((long long)acc[1] << 8) + (long long)acc[2];
+  long long lo = 0;
+#pragma unroll
+  for (int d = 3; d < S; ++d) lo = (lo << 8) + (long long)acc[d];
+  hi -= hi_corr;
+  lo -= lo_corr;
+  constexpr double w = 1.0 / (double)(1ull << (8 * (S - 3)));
+  return fma((double)lo, w, (double)hi);
+}
+
+// ---- K1': slices, scales, offset corrections and the Gram diagonal -----------
+template <int S>
+__global__ void __launch_bounds__(256)
+oz_slice_kernel(const double* __restrict__ xw, int64_t n, int64_t p, int64_t p_pad, int64_t p_oz,
+                int64_t n_pl, int64_t row_begin, int euclid, long long c0,
+                uint8_t* __restrict__ planes, double* __restrict__ sc, long long* __restrict__ hi,
+                long long* __restrict__ lo, double* __restrict__ stat) {
+  constexpr int F = 7 + 8 * (S - 1);
+  const int64_t row = row_begin + blockIdx.x;
+  const bool real = row < n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double smax[8];
+  __shared__ long long sred[8][2 * S];
+  const double* __restrict__ xr = xw + row * p_pad;
+  double m = 0.0;
+  if (real)
+    for (int64_t k = tid; k < p; k += 256) m = fmax(m, fabs(xr[k]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) smax[warp] = m;
+  __syncthreads();
+  m = smax[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmax(m, smax[w]);
+  int e = 0;
+  if (m > 0.0) frexp(m, &e);   // m = f 2^e, f in [0.5, 1): |x| < 2^e
+  long long R[S], dg[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) R[s] = dg[s] = 0;
+  for (int64_t k4 = (int64_t)tid * 4; k4 < p_oz; k4 += 1024) {
+    uint32_t pack[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) pack[s] = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t k = k4 + u;
+      const double x = (real && k < p) ? xr[k] : 0.0;
+      const long long q = __double2ll_rd(scalbn(x, F - e));
+      int dgt[S];
+      const int top = (int)(q >> (8 * (S - 1)));   // [-128, 127]
+      dgt[0] = top + 128;
+      R[0] += top;
+#pragma unroll
+      for (int s = 1; s < S; ++s) {
+        dgt[s] = (int)((q >> (8 * (S - 1 - s))) & 255);
+        R[s] += dgt[s];
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) pack[s] |= (uint32_t)dgt[s] << (8 * u);
+      // what the tensor core accumulates for the pair (row, row)
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int t = 0; s + t < S; ++t) dg[s + t] += (long long)(dgt[s] * dgt[t]);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      *reinterpret_cast<uint32_t*>(planes + ((int64_t)s * n_pl + row) * p_oz + k4) = pack[s];
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    for (int o = 16; o > 0; o >>= 1) {
+      R[s] += __shfl_xor_sync(0xffffffffu, R[s], o);
+      dg[s] += __shfl_xor_sync(0xffffffffu, dg[s], o);
+    }
+    if (lane == 0) {
+      sred[warp][s] = R[s];
+      sred[warp][S + s] = dg[s];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t acc[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      long long r = 0, g = 0;
+      for (int w = 0; w < 8; ++w) {
+        r += sred[w][s];
+        g += sred[w][S + s];
+      }
+      R[s] = r;
+      acc[s] = (uint32_t)g;
+    }
+    const long long hi_i = 128 * ((R[0] << 16) + (R[1] << 8) + R[2]);
+    long long lo_i = 0;
+#pragma unroll
+    for (int d = 3; d < S; ++d) lo_i = (lo_i << 8) + R[d];
+    lo_i *= 128;
+    const double sci = scalbn(1.0, e - 15);
+    sc[row] = sci;
+    hi[row] = hi_i;
+    lo[row] = lo_i;
+    const double v = oz_value<S>(acc, 2 * hi_i + c0, 2 * lo_i);
+    const double P = __dmul_rn(v, __dmul_rn(sci, sci));
+    double sv = 0.0;
+    if (real) sv = euclid ? P : __dsqrt_rn(P != 0.0 ? __ddiv_rn(1.0, P) : 0.0);
+    stat[row] = sv;
+  }
+}
+
+// ---- K2: the tile kernel -------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const OzArgs a) {
+  constexpr int NST = oz_stages(S);
+  constexpr int STAGE = oz_stage_bytes(S);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  double* stg = reinterpret_cast<double*>(gbase + NST * STAGE);
+  const uint32_t bars = base + NST * STAGE + STG_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 32, tfull = bars + 64, tempty = bars + 72;
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(gbase + NST * STAGE + STG_BYTES + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KS = a.kslabs;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, OZ_EPI_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc512(bars + 128);
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer ----------------------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        const OzTile tl = a.tiles[t];
+        const int i0 = tl.I * OM, j0 = tl.J * ON;
+        for (int ks = 0; ks < KS; ++ks, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, STAGE);
+          const uint32_t st = base + s * STAGE;
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl)
+            tma_load_2d(st + sl * A_SLAB, &map_a, ks * OKB, (int)(sl * a.n_pl) + i0,
+                        full0 + 8 * s);
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl)
+            tma_load_2d(st + S * A_SLAB + sl * B_SLAB, &map_b, ks * OKB,
+                        (int)(sl * a.n_pl) + j0, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer --------------------------------------------------------------
+    const bool el = tc::elect_one();
+    uint32_t it = 0, tcount = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tcount) {
+      mbar_wait(tempty, (tcount & 1) ^ 1);   // the epilogue has drained the accumulators
+      tc::fence_after();
+      for (int ks = 0; ks < KS; ++ks, ++it) {
+        const uint32_t s = it % NST, ph = (it / NST) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc::fence_after();
+        const uint32_t st = base + s * STAGE;
+        const uint64_t da = tc::desc_sw64(st), db = tc::desc_sw64(st + S * A_SLAB);
+#pragma unroll
+        for (int kk = 0; kk < OKB / 32; ++kk) {
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl) {
+            // slice sl of the row tile x slices [0, S - sl) of the column tile, at
+            // most four (N <= 256) per instruction; slice 0 goes first in a tile:
+            // it covers every diagonal, so its first K step zero-initialises them
+#pragma unroll
+            for (int t0 = 0; t0 < S - sl; t0 += 4) {
+              const int m = (S - sl - t0) < 4 ? (S - sl - t0) : 4;
+              const uint32_t acc = (ks | kk | sl) != 0;
+              if (el)
+                tc::mma_i8(tmem_base + (uint32_t)((sl + t0) * ON),
+                           da + (uint64_t)((sl * A_SLAB + kk * 32) >> 4),
+                           db + (uint64_t)((t0 * B_SLAB + kk * 32) >> 4), tc::idesc_u8(ON * m),
+                           acc);
+            }
+          }
+        }
+        if (el) tc::commit(empty0 + 8 * s);   // stage reusable once these MMAs retire
+        __syncwarp();
+      }
+      if (el) tc::commit(tfull);              // accumulators complete
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue warps 2..9 -----------------------------------------------------
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int h = (warp - 2) >> 2;            // column half
+    const int r = q * 32 + lane;              // tile row
+    const int et = threadIdx.x - 64;          // 0..255
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tcount) {
+      const OzTile tl = a.tiles[t];
+      const int64_t i0 = (int64_t)tl.I * OM, j0 = (int64_t)tl.J * ON;
+      const int64_t gi = i0 + r;
+      const bool row_ok = gi < a.n;
+      double sci = 0.0, sti = 0.0;
+      long long hii = 0, loi = 0;
+      if (row_ok) {
+        sci = __ldg(a.sc + gi);
+        sti = __ldg(a.stat + gi);
+        hii = __ldg(a.hi + gi);
+        loi = __ldg(a.lo + gi);
+      }
+      // output stripes of the tile's rows and of its (mirrored) columns
+      int od = 0, om = 0;
+      while (od + 1 < a.world && i0 >= a.stripe_begin[od + 1]) ++od;
+      while (om + 1 < a.world && j0 >= a.stripe_begin[om + 1]) ++om;
+      double* __restrict__ dbase = a.stripe_ptr[od] + (i0 - a.stripe_begin[od]) * a.ldd + j0;
+      double* __restrict__ mbase = a.stripe_ptr[om] + (j0 - a.stripe_begin[om]) * a.ldd + i0;
+      const bool direct = tl.flags & TILE_DIRECT, mirror = tl.flags & TILE_MIRROR;
+
+      mbar_wait(tfull, tcount & 1);
+      tc::fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 32; c0 += 4) {
+        uint32_t v[S][4];
+#pragma unroll
+        for (int d = 0; d < S; ++d)
+          tc::tmem_ld4_async(lane_base + (uint32_t)(d * ON + h * 32 + c0), v[d]);
+#pragma unroll
+        for (int d = 0; d < S; ++d) tc::tmem_wait4(v[d]);
+        if (c0 == 28) {
+          // last read of this tile: the accumulators may be overwritten
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = h * 32 + c0 + cc;
+          const int64_t gj = j0 + c;
+          double dv = 0.0;
+          if (gj < a.n) {
+            uint32_t acc[S];
+#pragma unroll
+            for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
+            const double val = oz_value<S>(acc, hii + __ldg(a.hi + gj) + a.c0,
+                                           loi + __ldg(a.lo + gj));
+            const double P = __dmul_rn(val, __dmul_rn(sci, __ldg(a.sc + gj)));
+            const double stj = __ldg(a.stat + gj);
+            const bool lower = gi >= gj;
+            dv = finish_entry(P, lower ? sti : stj, lower ? stj : sti, gi == gj, a.euclid);
+            // column c of the tile is row j0 + c of D: lanes are consecutive entries
+            if (mirror && row_ok && gj >= a.row_lo && gj < a.row_hi)
+              __stcs(mbase + (int64_t)c * a.ldd + r, dv);
+          }
+          stg[r * STG_LD + h * 4 + cc] = dv;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
+        if (direct) {
+          // 128 rows x (2 x 4 columns): 32-byte runs, 4 rows per warp instruction
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int row = pass * 32 + (et >> 3), seg = (et >> 2) & 1, cc = et & 3;
+            const int64_t gi2 = i0 + row, gj = j0 + seg * 32 + c0 + cc;
+            if (gi2 >= a.row_lo && gi2 < a.row_hi && gj < a.n)
+              __stcs(dbase + (int64_t)row * a.ldd + seg * 32 + c0 + cc,
+                     stg[row * STG_LD + seg * 4 + cc]);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_free512(tmem_base);
+}
+
+int oz_group_rows() {
+  // row tiles per L2 group: 16 panels of S x 128 x p bytes stay in L2 while the
+  // column panels stream once per group
+  const char* e = getenv("SCEDAR_B200_OZ_GROUP");
+  const int g = e ? atoi(e) : 16;
+  return g >= 1 ? g : 16;
+}
+
+}  // namespace
+
+// working set of the INT8 split of a cells handle (created on first use)
+struct OzState {
+  int S = 0;
+  uint8_t* planes = nullptr;    // [S][n_pl][p_oz]
+  double* sc = nullptr;         // [n_pl]
+  long long* hi = nullptr;
+  long long* lo = nullptr;
+  double* stat = nullptr;
+  int64_t n_pl = 0, p_oz = 0;
+  bool sliced_all = false;
+  OzTile* tiles = nullptr;      // device tile list (grown on demand)
+  size_t tiles_cap = 0;
+  std::vector<OzTile> host_tiles;
+  // key of the list currently on the device
+  int key_mode = -1;
+  int64_t key_a = -1, key_b = -1, key_c = -1, key_d = -1;
+  CUtensorMap map_a, map_b;
+};
+
+void oz_state_free(void* p, cudaStream_t s) {
+  OzState* o = static_cast<OzState*>(p);
+  if (!o) return;
+  if (o->planes) cudaFreeAsync(o->planes, s);
+  if (o->sc) cudaFreeAsync(o->sc, s);
+  if (o->hi) cudaFreeAsync(o->hi, s);
+  if (o->lo) cudaFreeAsync(o->lo, s);
+  if (o->stat) cudaFreeAsync(o->stat, s);
+  if (o->tiles) cudaFreeAsync(o->tiles, s);
+  delete o;
+}
+
+bool oz_supported(const scedar_cells* c) {
+  return c->p > 0 && round_up(c->p, OKB) <= OZ_KMAX;
+}
+
+namespace {
+
+int oz_encode(CUtensorMap* m, const uint8_t* ptr, int64_t rows, int64_t cols, int box_rows) {
+  return encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ptr, rows, cols, box_rows, OKB,
+                           CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+int oz_alloc(const scedar_cells* c, int S, cudaStream_t s, OzState** out) {
+  scedar_cells* mc = const_cast<scedar_cells*>(c);
+  OzState* o = static_cast<OzState*>(mc->oz);
+  if (o && o->S == S) {
+    *out = o;
+    return SCEDAR_OK;
+  }
+  if (o) {
+    oz_state_free(o, s);
+    mc->oz = nullptr;
+  }
+  if (!oz_supported(c))
+    return fail(SCEDAR_ERR_UNSUPPORTED, "the INT8 split path takes 1 <= n_features <= 4096");
+  o = new OzState();
+  o->S = S;
+  o->n_pl = c->n_pad;
+  o->p_oz = round_up(c->p, OKB);
+  cudaError_t e = cudaMallocAsync(&o->planes, (size_t)S * o->n_pl * o->p_oz, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&o->sc, sizeof(double) * o->n_pl, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&o->hi, sizeof(long long) * o->n_pl, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&o->lo, sizeof(long long) * o->n_pl, s);
+  if (e == cudaSuccess) e = cudaMallocAsync(&o->stat, sizeof(double) * o->n_pl, s);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    oz_state_free(o, s);
+    return fail(SCEDAR_ERR_NOMEM, std::string("INT8 slice planes: ") + cudaGetErrorString(e));
+  }
+  int rc = oz_encode(&o->map_a, o->planes, (int64_t)S * o->n_pl, o->p_oz, OM);
+  if (rc == SCEDAR_OK) rc = oz_encode(&o->map_b, o->planes, (int64_t)S * o->n_pl, o->p_oz, ON);
+  if (rc != SCEDAR_OK) {
+    oz_state_free(o, s);
+    return rc;
+  }
+  mc->oz = o;
+  *out = o;
+  return SCEDAR_OK;
+}
+
+long long oz_c0(const OzState* o) { return ((long long)16384 * o->p_oz) << 16; }
+
+// slices / scales / statistic of the cells [row_begin, row_end) (padding rows allowed)
+int oz_slice_rows(const scedar_cells* c, OzState* o, int64_t row_begin, int64_t row_end,
+                  cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  const int euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
+  const unsigned grid = (unsigned)(row_end - row_begin);
+  if (o->S == 6)
+    oz_slice_kernel<6><<<grid, 256, 0, s>>>(c->xw, c->n, c->p, c->p_pad, o->p_oz, o->n_pl,
+                                            row_begin, euclid, oz_c0(o), o->planes, o->sc, o->hi,
+                                            o->lo, o->stat);
+  else
+    oz_slice_kernel<7><<<grid, 256, 0, s>>>(c->xw, c->n, c->p, c->p_pad, o->p_oz, o->n_pl,
+                                            row_begin, euclid, oz_c0(o), o->planes, o->sc, o->hi,
+                                            o->lo, o->stat);
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
+int ensure_oz(const scedar_cells* c, int S, cudaStream_t s, OzState** out) {
+  SCEDAR_CHECK(oz_alloc(c, S, s, out));
+  if (!(*out)->sliced_all) {
+    SCEDAR_CHECK(oz_slice_rows(c, *out, 0, c->n_pad, s));
+    (*out)->sliced_all = true;
+  }
+  return SCEDAR_OK;
+}
+
+bool oz_have_tiles(const OzState* o, int mode, int64_t ka, int64_t kb, int64_t kc, int64_t kd) {
+  return o->key_mode == mode && o->key_a == ka && o->key_b == kb && o->key_c == kc &&
+         o->key_d == kd;
+}
+
+// upload the host tile list unless the same list is already on the device
+int oz_put_tiles(OzState* o, int mode, int64_t ka, int64_t kb, int64_t kc, int64_t kd,
+                 cudaStream_t s) {
+  if (oz_have_tiles(o, mode, ka, kb, kc, kd)) return SCEDAR_OK;
+  const size_t need = o->host_tiles.size();
+  if (need > o->tiles_cap) {
+    if (o->tiles) cudaFreeAsync(o->tiles, s);
+    o->tiles = nullptr;
+    o->tiles_cap = 0;
+    SCEDAR_CUDA(cudaMallocAsync(&o->tiles, sizeof(OzTile) * need, s));
+    o->tiles_cap = need;
+  }
+  if (need)
+    SCEDAR_CUDA(cudaMemcpyAsync(o->tiles, o->host_tiles.data(), sizeof(OzTile) * need,
+                                cudaMemcpyHostToDevice, s));
+  // the copy from pageable memory is staged before the call returns
+  o->key_mode = mode;
+  o->key_a = ka;
+  o->key_b = kb;
+  o->key_c = kc;
+  o->key_d = kd;
+  return SCEDAR_OK;
+}
+
+int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
+  a.sc = o->sc;
+  a.hi = o->hi;
+  a.lo = o->lo;
+  a.stat = o->stat;
+  a.c0 = oz_c0(o);
+  a.n = c->n;
+  a.n_pl = o->n_pl;
+  a.kslabs = (int)(o->p_oz / OKB);
+  a.euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
+  a.tiles = o->tiles;
+  a.n_tiles = (int)o->host_tiles.size();
+  if (a.n_tiles == 0) return SCEDAR_OK;
+  const int grid = std::min(a.n_tiles, num_sms());
+  if (o->S == 6) {
+    SCEDAR_CUDA(cudaFuncSetAttribute(gram_oz_kernel<6>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem(6)));
+    gram_oz_kernel<6><<<grid, OZ_THREADS, oz_smem(6), s>>>(o->map_a, o->map_b, a);
+  } else {
+    SCEDAR_CUDA(cudaFuncSetAttribute(gram_oz_kernel<7>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem(7)));
+    gram_oz_kernel<7><<<grid, OZ_THREADS, oz_smem(7), s>>>(o->map_a, o->map_b, a);
+  }
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
+// Tiles of the row tiles [rt0, rt1) in L2-friendly order.  `want(I, Jr)` decides
+// for the pair (row tile I, row tile Jr = J / 2 holding the 64 columns) whether
+// this launch computes it and what it stores.
+template <typename Want>
+void oz_list(std::vector<OzTile>& out, int64_t rt0, int64_t rt1, int64_t n, Want want) {
+  out.clear();
+  const int64_t CT = (n + ON - 1) / ON;
+  const int G = oz_group_rows();
+  for (int64_t g0 = rt0; g0 < rt1; g0 += G) {
+    const int64_t g1 = std::min<int64_t>(rt1, g0 + G);
+    for (int64_t J = 0; J < CT; ++J)
+      for (int64_t I = g0; I < g1; ++I) {
+        const int f = want(I, J);
+        if (f) out.push_back(OzTile{(int32_t)I, (int32_t)J, f, 0});
+      }
+  }
+}
+
+}  // namespace
+
+int launch_oz_stat(const scedar_cells* c, int S, const double** stat_out, cudaStream_t s) {
+  OzState* o = nullptr;
+  SCEDAR_CHECK(ensure_oz(c, S, s, &o));
+  *stat_out = o->stat;
+  return SCEDAR_OK;
+}
+
+// rows [row_begin, row_end) of D -> d_out [rows, n]; tile pairs that lie wholly
+// inside the stripe's own square block are computed once and mirrored
+int launch_oz_stripe(const scedar_cells* c, int S, int64_t row_begin, int64_t row_end,
+                     double* d_out, int64_t ldd, cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  if (row_begin % OM != 0 || (row_end % OM != 0 && row_end != c->n))
+    return fail(SCEDAR_ERR_UNSUPPORTED, "INT8 split stripes must be 128-row aligned");
+  OzState* o = nullptr;
+  SCEDAR_CHECK(ensure_oz(c, S, s, &o));
+  const int64_t n = c->n;
+  const int64_t rt0 = row_begin / OM, rt1 = (row_end + OM - 1) / OM;
+  // row tiles wholly inside the stripe (the stripe may start / end mid-tile)
+  auto inside = [&](int64_t T) {
+    return T * OM >= row_begin && std::min<int64_t>((T + 1) * OM, n) <= row_end;
+  };
+  if (!oz_have_tiles(o, 0, row_begin, row_end, oz_group_rows(), 0))
+  oz_list(o->host_tiles, rt0, rt1, n, [&](int64_t I, int64_t J) -> int {
+    const int64_t Jr = J / 2;
+    if (inside(I) && inside(Jr)) {
+      if (Jr > I) return 0;                     // produced as a mirror
+      return Jr == I ? TILE_DIRECT : TILE_DIRECT | TILE_MIRROR;
+    }
+    return TILE_DIRECT;
+  });
+  SCEDAR_CHECK(oz_put_tiles(o, 0, row_begin, row_end, oz_group_rows(), 0, s));
+  OzArgs a{};
+  a.ldd = ldd;
+  a.world = 1;
+  // rows outside [row_begin, row_end) are never stored: the stripe table maps
+  // row `row_begin` to d_out and the per-row guards below keep the rest out
+  a.stripe_begin[0] = row_begin;
+  a.stripe_begin[1] = row_end;
+  a.stripe_ptr[0] = d_out;
+  a.row_lo = row_begin;
+  a.row_hi = row_end;
+  return oz_launch(c, o, a, s);
+}
+
+int launch_oz_symmetric(const scedar_cells* c, int S, double* d_out, int64_t ldd,
+                        cudaStream_t s) {
+  return launch_oz_stripe(c, S, 0, c->n, d_out, ldd, s);
+}
+
+// Peer-store form: every tile pair of the whole matrix is computed by one rank
+// -- the owner of one of its two row tiles, alternating with the parity of the
+// pair so the ranks' tile counts balance -- and stored into both owners'
+// stripes (its own HBM or the peer's over NVLink).  Only owned tiles are
+// enumerated: no CTA is launched to find out that it has nothing to do.
+int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
+                         const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
+                         cudaStream_t s) {
+  if (world < 1 || world > kOzPeers) return fail(SCEDAR_ERR_ARG, "world must be in 1..16");
+  if (rank < 0 || rank >= world) return fail(SCEDAR_ERR_ARG, "rank out of range");
+  const int64_t n = c->n;
+  for (int r = 0; r <= world; ++r) {
+    const int64_t b = stripe_begin[r];
+    if (!(b % OM == 0 || b == n) || (r > 0 && b < stripe_begin[r - 1]))
+      return fail(SCEDAR_ERR_ARG, "stripes must be ascending and 128-row aligned");
+  }
+  if (stripe_begin[0] != 0 || stripe_begin[world] != n)
+    return fail(SCEDAR_ERR_ARG, "stripes must cover [0, n)");
+  OzState* o = nullptr;
+  SCEDAR_CHECK(ensure_oz(c, S, s, &o));
+  const int64_t RT = (n + OM - 1) / OM;
+  auto owner = [&](int64_t T) {
+    int r = 0;
+    while (r + 1 < world && T * OM >= stripe_begin[r + 1]) ++r;
+    return r;
+  };
+  if (!oz_have_tiles(o, 1, rank, world, stripe_begin[rank], oz_group_rows()))
+  oz_list(o->host_tiles, 0, RT, n, [&](int64_t I, int64_t J) -> int {
+    const int64_t Jr = J / 2;
+    if (Jr > I) return 0;
+    if (Jr == I) return owner(I) == rank ? TILE_DIRECT : 0;
+    const int64_t by = ((I + Jr) & 1) == 0 ? I : Jr;
+    return owner(by) == rank ? TILE_DIRECT | TILE_MIRROR : 0;
+  });
+  SCEDAR_CHECK(oz_put_tiles(o, 1, rank, world, stripe_begin[rank], oz_group_rows(), s));
+  OzArgs a{};
+  a.ldd = ldd;
+  a.world = world;
+  for (int r = 0; r < world; ++r) {
+    a.stripe_begin[r] = stripe_begin[r];
+    a.stripe_ptr[r] = stripe_ptr[r];
+  }
+  a.stripe_begin[world] = stripe_begin[world];
+  a.row_lo = 0;
+  a.row_hi = n;
+  return oz_launch(c, o, a, s);
+}
+
+// Rows [row_begin, row_end) of the lower triangle of the WHOLE matrix d_full
+// (row 0 first), mirrored: needs only the cells [0, row_end), so D can be
+// produced range by range while later cells are still being uploaded.
+int launch_oz_lower_rows(const scedar_cells* c, int S, int64_t row_begin, int64_t row_end,
+                         double* d_full, int64_t ldd, cudaStream_t s) {
+  if (row_end <= row_begin) return SCEDAR_OK;
+  if (row_begin % OM != 0) return fail(SCEDAR_ERR_ARG, "row_begin must be 128-aligned");
+  OzState* o = nullptr;
+  SCEDAR_CHECK(oz_alloc(c, S, s, &o));
+  const int64_t n = c->n;
+  // this range's cells were just filled: slice them (the last range also the padding)
+  const int64_t pad_end = row_end == n ? c->n_pad : round_up(row_end, OM);
+  SCEDAR_CHECK(oz_slice_rows(c, o, row_begin, std::min<int64_t>(pad_end, c->n_pad), s));
+  if (row_begin == 0 && row_end == n) o->sliced_all = true;
+  const int64_t rt0 = row_begin / OM, rt1 = (row_end + OM - 1) / OM;
+  oz_list(o->host_tiles, rt0, rt1, std::min<int64_t>(n, rt1 * OM), [&](int64_t I, int64_t J) -> int {
+    const int64_t Jr = J / 2;
+    if (Jr > I) return 0;
+    return Jr == I ? TILE_DIRECT : TILE_DIRECT | TILE_MIRROR;
+  });
+  SCEDAR_CHECK(oz_put_tiles(o, 2, row_begin, row_end, oz_group_rows(), 0, s));
+  OzArgs a{};
+  a.ldd = ldd;
+  a.world = 1;
+  a.stripe_begin[0] = 0;
+  a.stripe_begin[1] = n;
+  a.stripe_ptr[0] = d_full;
+  a.row_lo = 0;
+  a.row_hi = n;
+  return oz_launch(c, o, a, s);
+}
+
+}  // namespace scedar

@@ -113,12 +113,12 @@ class Cells(object):
             self._h, _ptr(x_rows), max(ldx, self.p), int(row_begin),
             int(row_begin) + x_rows.shape[0], _stream()))
 
-    def pdist_lower_rows(self, row_begin, row_end, out):
+    def pdist_lower_rows(self, row_begin, row_end, out, precision="fp64"):
         """Rows [row_begin, row_end) of the lower triangle of the whole
         matrix ``out`` [n, n], mirrored; needs the cells [0, row_end) only."""
-        _capi.check(_capi.load().scedar_pdist_lower_rows(
-            self._h, int(row_begin), int(row_end), _ptr(out),
-            out.stride(0) if self.n > 1 else self.n, _stream()))
+        _capi.check(_capi.load().scedar_pdist_lower_rows_prec(
+            self._h, PRECISION_IDS[precision], int(row_begin), int(row_end),
+            _ptr(out), out.stride(0) if self.n > 1 else self.n, _stream()))
         return out
 
     @classmethod
@@ -327,6 +327,7 @@ class PeerStripes(object):
 
 
 def pdist_stripe_p2p(cells, peers, rank, precision="fp64"):
+    # precision: "fp64" (DMMA) or "fp64_i8" / "fp64_i8s6" (INT8 split)
     """Rank ``rank``'s share of the balanced symmetric contraction: its tiles
     go to its own stripe, their transposes to the peers' stripes.  All ranks
     must barrier before reading (stripes.StripedDistanceMatrix does)."""
@@ -516,7 +517,8 @@ def upload_ranges(n, first=2048):
     return out
 
 
-def pdist_symmetric_from_host(x_host, metric, out=None, x_dev=None):
+def pdist_symmetric_from_host(x_host, metric, out=None, x_dev=None,
+                              precision="fp64"):
     """FP64 distance matrix of a pinned HOST matrix with the upload hidden
     behind the contraction: x is copied range by range on a second stream,
     each range is prepared (K1 + diagonal) as it lands and the rows of the
@@ -541,7 +543,7 @@ def pdist_symmetric_from_host(x_host, metric, out=None, x_dev=None):
             landed.record(copy)
         main.wait_event(landed)
         cells.fill_rows(x_dev[b:e], b)
-        cells.pdist_lower_rows(b, e, out)
+        cells.pdist_lower_rows(b, e, out, precision=precision)
     return cells, out
 
 

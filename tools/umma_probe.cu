@@ -1,0 +1,436 @@
+// Probe for the INT8 tensor path (tcgen05.mma.kind::i8, INT32 accumulators in
+// TMEM) that the error-free-split Gram kernel (scedar_b200/csrc/gram_oz.cu) is
+// built on.  Two questions, both answered by measurement on a B200:
+//   check   is the operand plumbing right?  TMA (64-byte swizzle) of a uint8
+//           matrix -> K-major smem descriptors -> kind::i8 with every
+//           signed/unsigned operand combination, cta_group 1 and 2, against a
+//           CPU int64 dot product.
+//   rate    cycles per MMA for M = 128 x cta_group, N in {32..256}, kind i8 and
+//           f16, issued in the slice-pair pattern of the split Gram (S slices,
+//           one accumulator per diagonal s + t) -- is N = 64 paced by the
+//           tensor pipe (N/2 cycles) or by the shared-memory operand reads?
+// Build: make -C tools umma_probe      Run (GPU box): tools/umma_probe
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../scedar_b200/csrc/ptx_sm100.cuh"
+
+using namespace scedar;
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                     \
+    }                                                                              \
+  } while (0)
+
+static int encode_u8_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int box_rows,
+                         int box_cols) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<encode_fn>(fn)(
+      m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
+    return 1;
+  }
+  return 0;
+}
+
+// ---- device helpers (same forms as gram_tc.cu) -------------------------------
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;   // 8-row atoms of 64-byte rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;            // SWIZZLE_64B
+  return d;
+}
+template <int CG, int KIND>   // KIND 0 = i8, 1 = f16
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc,
+                                     uint32_t acc) {
+  if (CG == 1 && KIND == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+  if (CG == 2 && KIND == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+  if (CG == 1 && KIND == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+  if (CG == 2 && KIND == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(a), "l"(b), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void commit(uint32_t bar) {
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void csync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+__device__ __forceinline__ void tma_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                         uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ uint32_t tmem_setup(uint32_t slot_addr, volatile uint32_t* slot, int warp) {
+  if (warp == 0) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CG == 2) csync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *slot;
+}
+template <int CG>
+__device__ __forceinline__ void tmem_teardown(uint32_t tmem_base, int warp) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CG == 2) csync();
+  if (warp == 0) {
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                   : "memory");
+  }
+}
+
+// idesc of kind::i8: D = S32 (2 << 4), A/B format 0 = u8, 1 = s8, K-major both
+static uint32_t idesc_i8(int M, int N, int a_signed, int b_signed) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+static uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- check: one 128*CG x N tile, K = 64 bytes (two MMAs) -----------------------
+// matrix g: rows [0, 256) are A rows, rows [256, 256 + N) are B rows, 64 columns
+template <int CG>
+__global__ void __launch_bounds__(128, 1)
+check_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+             int N, uint32_t idesc, int32_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  const uint32_t sa = base, sb = base + 8192;
+  const uint32_t bars = base + 8192 + 16384;
+  const uint32_t full = bars, done = bars + 8;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(g + 8192 + 16384 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? ctarank() : 0;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  const uint32_t tmem_base = tmem_setup<CG>(bars + 64, slot, warp);
+  const int nb = N / CG;   // B rows staged by this CTA
+  if (threadIdx.x == 0) {
+    if (CG == 1) {
+      mbar_expect_tx(full, 8192 + nb * 64);
+      tma_load_2d(sa, &map_a, 0, 0, full);
+      tma_load_2d(sb, &map_b, 0, 256, full);
+    } else {
+      if (rank == 0) mbar_expect_tx(full, 2 * (8192 + nb * 64));
+      const uint32_t lbar = mapa(full, 0);
+      tma_pair(sa, &map_a, 0, (int)rank * 128, lbar);
+      tma_pair(sb, &map_b, 0, 256 + (int)rank * nb, lbar);
+    }
+    if (rank == 0) {
+      mbar_wait(full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int kk = 0; kk < 2; ++kk)
+        umma<CG, 0>(tmem_base, umma_desc64(sa + kk * 32), umma_desc64(sb + kk * 32), idesc, kk != 0);
+      commit<CG>(done);
+    }
+  }
+  __syncthreads();
+  mbar_wait(done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = (int)rank * 128 + warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    for (int c = 0; c < 32; ++c) out[row * N + c0 + c] = (int32_t)v[c];
+  }
+  tmem_teardown<CG>(tmem_base, warp);
+}
+
+// ---- rate: S slices of A and B resident in smem, the slice-pair pattern -------
+// mode 0: pairs (s, t), s + t < S, accumulator s + t (needs S * N <= 512)
+// mode 1: plain GEMM pattern: A slice (i % S), B slice (i % S), accumulators 0/1
+template <int CG, int KIND>
+__global__ void __launch_bounds__(128, 1)
+rate_kernel(int N, int S, int iters, int mode, uint32_t idesc, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  const int nb = N / CG;
+  const uint32_t a_bytes = 8192, b_bytes = (uint32_t)nb * 64;
+  const uint32_t sa = base, sb = base + S * a_bytes;
+  const uint32_t bars = sb + S * ((b_bytes + 1023u) & ~1023u);
+  const uint32_t done = bars;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(g + (bars - base) + 64);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = CG == 2 ? ctarank() : 0;
+  // small integers / small halves: no NaNs, no denormal slow paths
+  for (uint32_t i = threadIdx.x; i < (bars - base) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(g)[i] = KIND == 0 ? 0x01020301u : 0x3c003c00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  const uint32_t tmem_base = tmem_setup<CG>(bars + 64, slot, warp);
+  const uint32_t bstride = (b_bytes + 1023u) & ~1023u;
+  if (threadIdx.x == 0 && rank == 0) {
+    const long long t0 = clock64();
+    long long n_mma = 0;
+    for (int it = 0; it < iters; ++it) {
+      for (int kk = 0; kk < 2; ++kk) {
+        if (mode == 0) {
+          for (int s = 0; s < S; ++s)
+            for (int t = 0; s + t < S; ++t) {
+              umma<CG, KIND>(tmem_base + (s + t) * N, umma_desc64(sa + s * a_bytes + kk * 32),
+                             umma_desc64(sb + t * bstride + kk * 32), idesc, 1);
+              ++n_mma;
+            }
+        } else {
+          for (int s = 0; s < S; ++s) {
+            umma<CG, KIND>(tmem_base + (s & 1) * N, umma_desc64(sa + s * a_bytes + kk * 32),
+                           umma_desc64(sb + s * bstride + kk * 32), idesc, 1);
+            ++n_mma;
+          }
+        }
+      }
+    }
+    commit<CG>(done);
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    out[2 * (blockIdx.x / CG)] = (unsigned long long)(t1 - t0);
+    out[2 * (blockIdx.x / CG) + 1] = (unsigned long long)n_mma;
+  }
+  if (CG == 2 && rank == 1 && threadIdx.x == 0) mbar_wait(done, 0);
+  tmem_teardown<CG>(tmem_base, warp);
+}
+
+template <int CG>
+static int run_check(int N, int a_signed, int b_signed) {
+  const int rows = 256 + 256, cols = 64;
+  std::vector<uint8_t> h((size_t)rows * cols);
+  srand(1234 + N + 2 * a_signed + b_signed);
+  for (auto& v : h) v = (uint8_t)(rand() & 0xff);
+  uint8_t* d;
+  int32_t* out;
+  CK(cudaMalloc(&d, h.size()));
+  CK(cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&out, sizeof(int32_t) * 256 * N));
+  CK(cudaMemset(out, 0xff, sizeof(int32_t) * 256 * N));
+  CUtensorMap ma, mb;
+  if (encode_u8_map(&ma, d, rows, cols, 128, 64)) return 1;
+  if (encode_u8_map(&mb, d, rows, cols, N / CG, 64)) return 1;
+  const int smem = 1024 + 8192 + 16384 + 256;
+  auto kern = check_kernel<CG>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CG);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = CG;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, ma, mb, N, idesc_i8(128 * CG, N, a_signed, b_signed), out));
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> got((size_t)256 * N);
+  CK(cudaMemcpy(got.data(), out, got.size() * 4, cudaMemcpyDeviceToHost));
+  long bad = 0;
+  const int M = 128 * CG;
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < N; ++j) {
+      long long acc = 0;
+      for (int k = 0; k < cols; ++k) {
+        const uint8_t ab = h[(size_t)i * cols + k], bb = h[(size_t)(256 + j) * cols + k];
+        const int av = a_signed ? (int)(int8_t)ab : (int)ab;
+        const int bv = b_signed ? (int)(int8_t)bb : (int)bb;
+        acc += (long long)av * bv;
+      }
+      if ((long long)got[(size_t)i * N + j] != acc) {
+        if (bad < 5)
+          printf("  mismatch (%d,%d): got %d want %lld\n", i, j, got[(size_t)i * N + j], acc);
+        ++bad;
+      }
+    }
+  printf("check cg=%d N=%d A=%s B=%s: %s (%ld of %d wrong)\n", CG, N, a_signed ? "s8" : "u8",
+         b_signed ? "s8" : "u8", bad ? "FAIL" : "ok", bad, M * N);
+  cudaFree(d);
+  cudaFree(out);
+  return bad != 0;
+}
+
+template <int CG, int KIND>
+static void run_rate(int N, int S, int mode) {
+  const int units = 148 / CG;
+  const int nb = N / CG;
+  const int smem = 1024 + S * 8192 + S * ((nb * 64 + 1023) & ~1023) + 256;
+  if (smem > 227 * 1024) return;
+  if (mode == 0 && S * N > 512) return;
+  if (mode == 1 && 2 * N > 512) return;
+  unsigned long long* out;
+  CK(cudaMalloc(&out, sizeof(unsigned long long) * 2 * units));
+  auto kern = rate_kernel<CG, KIND>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = CG;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  const uint32_t idesc = KIND == 0 ? idesc_i8(128 * CG, N, 1, 0) : idesc_f16(128 * CG, N);
+  const int iters = 200;
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaLaunchKernelEx(&cfg, kern, N, S, iters, mode, idesc, out));
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<unsigned long long> h(2 * units);
+  CK(cudaMemcpy(h.data(), out, sizeof(unsigned long long) * 2 * units, cudaMemcpyDeviceToHost));
+  std::vector<double> per;
+  for (int u = 0; u < units; ++u) per.push_back((double)h[2 * u] / (double)h[2 * u + 1]);
+  std::sort(per.begin(), per.end());
+  const double med = per[per.size() / 2];
+  // MACs per cycle per SM: each SM contracts 128 x N x (32 bytes of K) per MMA
+  const double k_el = KIND == 0 ? 32.0 : 16.0;
+  printf("rate kind=%s cg=%d N=%3d S=%d mode=%d: %.1f cyc/MMA (min %.1f max %.1f; floor N/2 = %d) "
+         "-> %.0f MAC/cyc/SM, smem operand bytes/cyc/SM %.0f\n",
+         KIND == 0 ? "i8 " : "f16", CG, N, S, mode, med, per.front(), per.back(), N / 2,
+         128.0 * N * k_el / med, (128.0 * 32 + nb * 32.0) / med);
+  cudaFree(out);
+}
+
+int main() {
+  int dev = 0;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device: %s, %d SMs, clock %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
+  int fails = 0;
+  for (int as = 0; as < 2; ++as)
+    for (int bs = 0; bs < 2; ++bs) {
+      fails += run_check<1>(64, as, bs);
+      fails += run_check<2>(64, as, bs);
+    }
+  fails += run_check<1>(128, 1, 0);
+  fails += run_check<2>(128, 1, 0);
+  fails += run_check<1>(256, 1, 0);
+  fails += run_check<2>(256, 1, 0);
+  fails += run_check<1>(32, 1, 0);
+  fails += run_check<2>(32, 1, 0);
+  const int Ns[] = {32, 64, 96, 128, 160, 256};
+  for (int N : Ns) {
+    run_rate<1, 0>(N, 7, 0);
+    run_rate<1, 0>(N, 6, 0);
+    run_rate<2, 0>(N, 7, 0);
+    run_rate<2, 0>(N, 6, 0);
+    run_rate<1, 0>(N, 4, 1);
+    run_rate<2, 0>(N, 4, 1);
+    run_rate<1, 1>(N, 4, 1);
+    run_rate<2, 1>(N, 4, 1);
+  }
+  // three accumulators (two-pass split): S = 3 pattern at N = 128 / 160
+  run_rate<1, 0>(128, 3, 0);
+  run_rate<2, 0>(128, 3, 0);
+  run_rate<1, 0>(160, 3, 0);
+  run_rate<2, 0>(160, 3, 0);
+  printf("probe done: %d check failures\n", fails);
+  return fails ? 1 : 0;
+}
