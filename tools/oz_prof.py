@@ -1,0 +1,27 @@
+"""One shape of the INT8 split Gram for ncu: python tools/oz_prof.py [n] [p] [precision] [reps]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from scedar_b200 import device as dev, synth          # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+p = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+prec = sys.argv[3] if len(sys.argv) > 3 else "fp64_i8"
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+torch.cuda.set_device(0)
+x = torch.from_numpy(synth.log_counts(n, p, seed=n)).cuda()
+cells = dev.Cells.from_dense(x, "correlation")
+d = torch.empty((n, n), dtype=torch.float64, device="cuda")
+ts = []
+for _ in range(reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    cells.pdist_symmetric(out=d, precision=prec)
+    b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+print("n={} p={} {}: ms {}".format(n, p, prec, ["%.3f" % t for t in ts]))
