@@ -62,6 +62,34 @@ conn_csr_kernel(const int64_t* __restrict__ idx, const double* __restrict__ dist
   }
 }
 
+// any k: one block per cell, the cell's neighbour indices in shared memory when
+// they fit (k <= 12,288), else read from global memory
+__global__ void __launch_bounds__(256)
+conn_csr_big_kernel(const int64_t* __restrict__ idx, const double* __restrict__ dist, int64_t n,
+                    int k, int in_smem, int64_t* __restrict__ indptr,
+                    int32_t* __restrict__ indices, double* __restrict__ data) {
+  extern __shared__ int s_big[];
+  const int64_t row = blockIdx.x;
+  if (threadIdx.x == 0) indptr[row] = row * k;  // row == n writes the end pointer
+  if (row == n) return;
+  const int64_t* __restrict__ mine = idx + row * k;
+  if (in_smem) {
+    for (int e = threadIdx.x; e < k; e += blockDim.x) s_big[e] = (int)mine[e];
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    const int me = in_smem ? s_big[e] : (int)mine[e];
+    int rank = 0;
+    for (int m = 0; m < k; ++m) {
+      const int o = in_smem ? s_big[m] : (int)mine[m];
+      rank += (o < me) || (o == me && m < e);
+    }
+    const double v = dist[row * k + e];
+    indices[row * k + rank] = me;
+    data[row * k + rank] = v == 0.0 ? neg_inf() : v;
+  }
+}
+
 // max over max(w, 0) with -inf -> 0: all candidates are >= 0, so the IEEE bit
 // pattern orders like the value
 __global__ void __launch_bounds__(256)
@@ -127,6 +155,68 @@ masked_kth_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols, int
   }
   L.refresh(K);
   if (lane == 0) kth_out[row] = L.td;
+}
+
+// Any rank: one block per row, most-significant-byte-first radix selection on
+// the order-preserving integer image of the distances (8 passes over the row,
+// the first from HBM, the rest from L2).  Same result as the list kernel: the
+// value at 0-based `rank` among the live columns, +inf when fewer are alive.
+__device__ __forceinline__ unsigned long long ord_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__global__ void __launch_bounds__(256)
+masked_kth_radix_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols,
+                        int64_t row_begin, const uint8_t* __restrict__ alive, int rank,
+                        double* __restrict__ kth_out) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned s_rank;
+  __shared__ int s_short;
+  const int64_t row = blockIdx.x;
+  if (!alive[row_begin + row]) {
+    if (threadIdx.x == 0) kth_out[row] = pos_inf();
+    return;
+  }
+  const double* __restrict__ src = d + row * ldd;
+  if (threadIdx.x == 0) {
+    s_prefix = 0;
+    s_rank = (unsigned)rank;
+    s_short = 0;
+  }
+  for (int pass = 7; pass >= 0; --pass) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const unsigned long long mask = pass == 7 ? 0ULL : (~0ULL << (8 * (pass + 1)));
+    for (int64_t c = threadIdx.x; c < n_cols; c += blockDim.x) {
+      if (!alive[c]) continue;
+      const unsigned long long key = ord_key(src[c]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned r = s_rank, cum = 0;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (cum + hist[b] > r) break;
+        cum += hist[b];
+      }
+      if (b == 256) {
+        s_short = 1;   // fewer live columns than rank + 1
+        b = 255;
+      }
+      s_rank = r - cum;
+      s_prefix = prefix | ((unsigned long long)b << (8 * pass));
+    }
+    __syncthreads();
+    if (s_short) break;
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long key = s_prefix;
+    const unsigned long long bits = (key >> 63) ? (key & 0x7fffffffffffffffULL) : ~key;
+    kth_out[row] = s_short ? pos_inf() : __longlong_as_double((long long)bits);
+  }
 }
 
 // counters[0] = cells kept, counters[1] = bits of max(kth) over the kept cells
@@ -321,9 +411,14 @@ impute_stats_kernel(const int32_t* __restrict__ idc, int64_t ldi, int64_t n, int
 
 int launch_conn_csr(const int64_t* idx, const double* dist, int64_t n, int k, int64_t* indptr,
                     int32_t* indices, double* data, cudaStream_t s) {
-  if (k > CONN_MAXK) return fail(SCEDAR_ERR_UNSUPPORTED, "connectivity CSR: k must be <= 128");
-  conn_csr_kernel<<<(unsigned)((n + 1 + 7) / 8), 256, 0, s>>>(idx, dist, n, k, indptr, indices,
-                                                             data);
+  if (k > CONN_MAXK) {
+    const int in_smem = k <= 12288;
+    conn_csr_big_kernel<<<(unsigned)(n + 1), 256, in_smem ? sizeof(int) * k : 0, s>>>(
+        idx, dist, n, k, in_smem, indptr, indices, data);
+  } else {
+    conn_csr_kernel<<<(unsigned)((n + 1 + 7) / 8), 256, 0, s>>>(idx, dist, n, k, indptr, indices,
+                                                               data);
+  }
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
   return SCEDAR_OK;
@@ -358,7 +453,8 @@ int launch_masked_kth(const double* d, int64_t ldd, int64_t n_cols, int64_t row_
   else if (K <= 32 * kMaxR)
     masked_kth_kernel<4><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, alive, rank, kth_out);
   else
-    return fail(SCEDAR_ERR_UNSUPPORTED, "masked k-th: rank must be < 128");
+    masked_kth_radix_kernel<<<(unsigned)rows, 256, 0, s>>>(d, ldd, n_cols, row_begin, alive, rank,
+                                                          kth_out);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
   return SCEDAR_OK;

@@ -17,7 +17,7 @@ import torch
 
 from . import device as dev
 from ._capi import EXCLUDE_SELF
-from .sdm import SampleDistanceMatrix
+from .sdm import MAX_TOPK, SampleDistanceMatrix
 
 
 def _as_list(v):
@@ -48,17 +48,31 @@ class RareSampleDetection(object):
         if param_key in self._res_lut:
             return self._res_lut[param_key]
         sdm = self._sdm
-        if use_pca or use_hnsw or index_params or query_params:
-            # same refusals as SampleDistanceMatrix.s_knns
+        metric = sdm._metric if metric is None else metric
+        if (use_pca or use_hnsw or index_params or query_params
+                or not SampleDistanceMatrix._on_b200_path(metric)):
+            # PCA-space / HNSW / foreign-metric searches: the reference's own
+            # loop when this is a patched scedar class, else the refusals of
+            # SampleDistanceMatrix.s_knns
+            ref = getattr(type(self), "_ref__no_pdist_rare_s_detect", None)
+            if ref is not None:
+                return ref(self, k, d_cutoff, n_iter, metric=metric,
+                           use_pca=use_pca, use_hnsw=use_hnsw,
+                           index_params=index_params,
+                           query_params=query_params)
             sdm.s_knns(k, metric=metric, use_pca=use_pca, use_hnsw=use_hnsw,
                        index_params=index_params, query_params=query_params)
-        metric = sdm._metric if metric is None else metric
+            if use_pca:
+                raise NotImplementedError(
+                    "rare-sample detection over PCA coordinates: build the "
+                    "SampleDistanceMatrix on the PCs instead")
         sdm._check_metric(metric)
         x = sdm._x.toarray() if spsp.issparse(sdm._x) else sdm._x
         x_dev = dev.to_device(np.ascontiguousarray(x, dtype=np.float64))
         precision = getattr(sdm, "precision", "fp64")
 
         def kth_nn(xd):
+            """Distance to the k-th neighbour of every cell: tensor [m, 1]."""
             m = xd.shape[0]
             if k + 1 > m:
                 raise ValueError(
@@ -66,15 +80,21 @@ class RareSampleDetection(object):
                     "{}, n_samples_fit = {}".format(k, m))
             cells = dev.Cells.from_dense(xd, metric)
             try:
+                if k > MAX_TOPK:
+                    # beyond the list kernels: sorted D stripes in HBM
+                    _, dist = sdm._knn_by_full_sort(sdm._stripes_of(cells),
+                                                    m, k)
+                    return dev.to_device(
+                        np.ascontiguousarray(dist[:, k - 1:k]))
                 _, dist = cells.knn_stripe(k, EXCLUDE_SELF,
                                            precision=precision)
             finally:
                 cells.close()
-            return dist
+            return dist[:, k - 1:k].contiguous()
 
         dist = kth_nn(x_dev)
         m = x_dev.shape[0]
-        d_max = dev.masked_max(dist[:, k - 1:], None, ldv=k, n=m)
+        d_max = dev.masked_max(dist, None, ldv=1, n=m)
         curr_s_inds = np.arange(m)
         progress_list = [curr_s_inds.tolist()]
         for i in range(1, n_iter + 1):
@@ -82,8 +102,8 @@ class RareSampleDetection(object):
                           (n_iter - i) / n_iter * max(0, d_max - d_cutoff))
             alive = dev.ones(m, torch.uint8)
             scratch = dev.zeros(m, torch.int32)
-            kept = dev.rare_update(dist[:, k - 1:], i_d_cutoff, i, alive,
-                                   scratch, ldk=k)
+            kept = dev.rare_update(dist, i_d_cutoff, i, alive, scratch,
+                                   ldk=1)
             sel = dev.compact_alive(alive, kept)
             curr_s_inds = curr_s_inds[sel.cpu().numpy()]
             progress_list.append(curr_s_inds.tolist())
@@ -111,8 +131,6 @@ class RareSampleDetection(object):
         sdm = self._sdm
         sdm._validate_pdist()
         n = sdm._x.shape[0]
-        if k > 127:
-            raise NotImplementedError("rare-sample detection with k > 127")
         alive = dev.ones(n, torch.uint8)
         last_kept = dev.zeros(n, torch.int32)
         kth = dev.empty(n, torch.float64)
@@ -340,8 +358,14 @@ class FeatureImputation(object):
                 self._res_lut[param_tup] = res_tup
             res_list[res_list_run_inds[i]] = res_tup
         kpu_sdm_list = []
+        # the class of the wrapped object: a patched scedar installation gets
+        # scedar.eda.SampleDistanceMatrix back (with its tsne / plots /
+        # to_classified), the stand-alone package its own class
+        sdm_cls = getattr(self, "_result_cls", None) or type(self._sdm)
+        if not (isinstance(sdm_cls, type) and hasattr(sdm_cls, "s_knns")):
+            sdm_cls = SampleDistanceMatrix
         for res in res_list:
-            kpu_sdm = SampleDistanceMatrix(
+            kpu_sdm = sdm_cls(
                 res[0], metric=self._sdm._metric, sids=self._sdm.sids,
                 fids=self._sdm.fids, nprocs=self._sdm._nprocs)
             kpu_sdm_list.append(kpu_sdm)

@@ -225,6 +225,19 @@ class SampleDistanceMatrix(object):
         return self.ind_x(s, f)
 
     # ------------------------------------------------------- device helpers
+    @staticmethod
+    def _on_b200_path(metric):
+        """cosine / correlation / euclidean run on the device; every other
+        metric is sklearn's (sdm.py:1215-1217) and is none of this path's
+        business."""
+        return isinstance(metric, str) and metric in METRIC_IDS
+
+    def _ref_hook(self, name):
+        """The reference's own implementation of a patched hook, kept by
+        ``patch.install_sdm`` as ``_ref_<name>`` (None on the stand-alone
+        drop-in class, which has nothing to fall back to)."""
+        return getattr(type(self), "_ref_" + name, None)
+
     def _check_metric(self, metric):
         if not isinstance(metric, str) or metric not in METRIC_IDS:
             raise ValueError(
@@ -364,6 +377,13 @@ class SampleDistanceMatrix(object):
         """sdm.py:1193-1221: lazy, memoised in ``_lazy_load_d``.  D may
         already be resident in HBM (an earlier kNN accessor); the host copy is
         made on first access."""
+        if (self._lazy_load_d is None and self._use_pdist
+                and not self._on_b200_path(self._metric)
+                and self._ref_hook("_d") is not None):
+            # a metric the device path does not own: the reference's own
+            # (sklearn) route, untouched; the accessors below then work on
+            # the matrix it leaves in _lazy_load_d
+            return self._ref_hook("_d").fget(self)
         self._validate_pdist()
         if self._lazy_load_d is None:
             n = self._x.shape[0]
@@ -371,21 +391,30 @@ class SampleDistanceMatrix(object):
             for r0, r1, stripe in self._d_stripes():
                 dev.to_host(stripe, out[r0:r1])
             self._lazy_load_d = out
+            self._d_own = out
         return self._lazy_load_d
 
     # ------------------------------------------------------ sorted columns
     def _col_sort(self, want_sorted, want_arg):
+        if self._use_pdist and not self._on_b200_path(self._metric):
+            self._d                      # the reference's route fills the slot
         self._validate_pdist()
         n = self._x.shape[0]
         srt = np.empty((n, n), dtype=np.float64) if want_sorted else None
         arg = np.empty((n, n), dtype=np.int64) if want_arg else None
         if n:
+            # the sort writes up to two more [rows, n] arrays: a resident D is
+            # sorted in row blocks, not in one piece
+            block = max(128, (STRIPE_BYTES // (8 * n)) // 128 * 128)
             for r0, r1, stripe in self._d_stripes():
-                s, a = dev.col_sort(stripe, want_sorted, want_arg)
-                if want_sorted:
-                    dev.to_host(s, srt[r0:r1])
-                if want_arg:
-                    dev.to_host(a, arg[r0:r1])
+                for b0 in range(r0, r1, block):
+                    b1 = min(r1, b0 + block)
+                    s, a = dev.col_sort(stripe[b0 - r0:b1 - r0], want_sorted,
+                                        want_arg)
+                    if want_sorted:
+                        dev.to_host(s, srt[b0:b1])
+                    if want_arg:
+                        dev.to_host(a, arg[b0:b1])
         # cell-major -> the reference's (rank, cell) orientation (a view)
         return (srt.T if want_sorted else None, arg.T if want_arg else None)
 
@@ -421,13 +450,21 @@ class SampleDistanceMatrix(object):
         fused = (self._lazy_load_d is None and self._d_dev is None
                  and k <= 31 and n * n * 8 > DEVICE_D_CACHE_BYTES)
         # a tensor-core D is approximate: exact neighbours come from the
-        # candidate + float64 re-rank kernel, never from that matrix
-        exact_fast = (self.precision == "fast" and not self._d_user
-                      and k <= FAST_MAX_K)
+        # candidate + float64 re-rank kernel (k <= 55) or the FP64 kernels
+        # (larger k), never from that matrix.  Only a D this object computed
+        # itself may be bypassed like this -- one that was handed in (the
+        # constructor, to_classified, a restored cache) is the caller's truth.
+        own_d = (self._lazy_load_d is None
+                 or self._lazy_load_d is getattr(self, "_d_own", None))
+        exact_fast = (self.precision == "fast" and own_d
+                      and not getattr(self, "_d_user", False)
+                      and self._on_b200_path(self._metric))
         if fused or exact_fast:
             # D is not needed (or would not fit): fused Gram -> top-k
             i, dd = self._cells(self._metric).knn_stripe(
-                k, exclude, precision=self.precision)
+                k, exclude, precision=(
+                    self.precision if k <= FAST_MAX_K or not exact_fast
+                    else "fp64"))
             self._knn_dev = (k, exclude, self._metric, i, dd)
             return i.cpu().numpy(), dd.cpu().numpy()
         parts = []
@@ -480,9 +517,16 @@ class SampleDistanceMatrix(object):
         if k < 1:
             raise ValueError("k should >= 1")
         if use_hnsw:
-            raise NotImplementedError(
-                "approximate HNSW search (nmslib) is outside the B200 path; "
-                "the exact brute-force path is use_hnsw=False")
+            # approximate search (nmslib, sdm.py:949-1051) is the reference's
+            # own: a patched class keeps it, the stand-alone class has none
+            ref = self._ref_hook("s_knns")
+            if ref is None:
+                raise NotImplementedError(
+                    "approximate HNSW search (nmslib) is outside the B200 "
+                    "path; the exact brute-force path is use_hnsw=False")
+            return ref(self, k, metric=metric, use_pca=use_pca,
+                       use_hnsw=use_hnsw, index_params=index_params,
+                       query_params=query_params, verbose=verbose)
         if index_params is not None:
             raise ValueError("index_params are not used with use_hnsw=False.")
         if query_params is not None:
@@ -493,20 +537,60 @@ class SampleDistanceMatrix(object):
         self._last_knns = (targets, distances)
         return targets, distances
 
+    def _knn_by_full_sort(self, stripes, n, k):
+        """k + 1 <= n nearest of every cell by the full stable sort of its row
+        of D (any k; the list kernels keep at most 128 entries), self dropped
+        by sklearn's rule.  ``stripes`` yields (r0, r1, device stripe)."""
+        idx = np.empty((n, k), dtype=np.int64)
+        dist = np.empty((n, k), dtype=np.float64)
+        for r0, r1, stripe in stripes:
+            block = max(128, (STRIPE_BYTES // (8 * n)) // 128 * 128)
+            for b0 in range(r0, r1, block):
+                b1 = min(r1, b0 + block)
+                srt, arg = dev.col_sort(stripe[b0 - r0:b1 - r0], True, True)
+                a = arg[:, :k + 1].cpu().numpy()
+                v = srt[:, :k + 1].cpu().numpy()
+                keep = a != np.arange(b0, b1)[:, None]
+                keep[keep.all(axis=1), 0] = False
+                idx[b0:b1] = a[keep].reshape(b1 - b0, k)
+                dist[b0:b1] = v[keep].reshape(b1 - b0, k)
+        return idx, dist
+
     def _s_knns_skl(self, k, metric=None, use_pca=False, verbose=False):
         """sdm.py:1053-1083 (the slot sklearn's NearestNeighbors filled)."""
         if metric is None:
             metric = self._metric
-        if use_pca:
-            raise NotImplementedError(
-                "PCA-space kNN needs scedar's PCA (sdm.py:1313-1334), which "
-                "is outside the B200 path; pass the PCs as x instead")
+        if not self._on_b200_path(metric) or (
+                self._is_sparse and metric == "correlation"):
+            ref = self._ref_hook("_s_knns_skl")
+            if ref is not None:
+                return ref(self, k, metric=metric, use_pca=use_pca,
+                           verbose=verbose)
+            self._check_metric(metric)          # raises
         n = self._x.shape[0]
         k = int(k)
         if k + 1 > n:
             raise ValueError("Expected n_neighbors < n_samples_fit, but "
                              "n_neighbors = {}, n_samples_fit = {}".format(
                                  k, n))
+        if use_pca:
+            # sdm.py:1060-1065: the same search over the PCA coordinates
+            # (the reference's own _pca_x on a patched class)
+            if verbose:
+                print("Construct {} distance KNN graph on PCA.".format(metric))
+            pcs = np.ascontiguousarray(self._pca_x, dtype=np.float64)
+            cells = dev.Cells.from_dense(dev.to_device(pcs), metric)
+            try:
+                if k > MAX_TOPK:
+                    idx, dist = self._knn_by_full_sort(
+                        self._stripes_of(cells), n, k)
+                else:
+                    i, dd = cells.knn_stripe(k, EXCLUDE_SELF,
+                                             precision=self.precision)
+                    idx, dist = i.cpu().numpy(), dd.cpu().numpy()
+            finally:
+                cells.close()
+            return list(idx), list(dist)
         if verbose:
             print("Construct {} distance KNN graph on raw data.".format(
                 metric))
@@ -520,23 +604,33 @@ class SampleDistanceMatrix(object):
                 dist = srt[keep].reshape(n, k)
             else:
                 idx, dist = self._knn_from_pdist(k, EXCLUDE_SELF)
+        elif k > MAX_TOPK:
+            # more neighbours than the list kernels keep: D row stripes are
+            # formed in HBM and sorted there; the matrix never exists whole
+            idx, dist = self._knn_by_full_sort(
+                self._stripes_of(self._cells(metric)), n, k)
         else:
-            if k > MAX_TOPK:
-                raise NotImplementedError("k > {} without pdist".format(
-                    MAX_TOPK))
             i, dd = self._cells(metric).knn_stripe(k, EXCLUDE_SELF,
                                                    precision=self.precision)
             self._knn_dev = (k, EXCLUDE_SELF, metric, i, dd)
             idx, dist = i.cpu().numpy(), dd.cpu().numpy()
         return list(idx), list(dist)
 
+    def _stripes_of(self, cells):
+        """(r0, r1, D stripe in HBM) of prepared cells, a few GB at a time;
+        exact kernels only (these stripes are searched, not returned)."""
+        n = cells.n
+        rows = max(128, (STRIPE_BYTES // (8 * max(n, 1))) // 128 * 128)
+        prec = self.precision if self.precision != "fast" else "fp64"
+        for r0 in range(0, n, rows):
+            r1 = min(n, r0 + rows)
+            yield r0, r1, cells.pdist_stripe(r0, r1, precision=prec)
+
     def s_knn_connectivity_matrix(self, k, metric=None, use_pca=False,
                                   use_hnsw=False, index_params=None,
                                   query_params=None, verbose=False):
         """sdm.py:872-947: CSR, entry (i, j) = distance when j is one of i's
         kNN; exact-zero distances stored as -inf."""
-        if k > 128:
-            raise NotImplementedError("connectivity matrix with k > 128")
         self._knn_dev = None
         targets, distances = self.s_knns(
             k=k, metric=metric, use_pca=use_pca, use_hnsw=use_hnsw,
@@ -580,6 +674,17 @@ class SampleDistanceMatrix(object):
             knn_conn_mat, aff_scale)
         return ig.Graph(edges=list(zip(s_.tolist(), t_.tolist())),
                         directed=False, edge_attrs={"weight": w})
+
+    # ------------------------------------------------------------------ PCA
+    @property
+    def _pca_x(self):
+        """sdm.py:1313-1334: the samples in the space of the first
+        ``min(100, n, p)`` principal components (dense) or singular vectors
+        (sparse, ``min(100, p - 1)``), memoised in ``_lazy_load_pca_x``."""
+        if getattr(self, "_lazy_load_pca_x", None) is None:
+            from . import pca as _pca
+            self._lazy_load_pca_x = _pca.pca_x(self._x)
+        return self._lazy_load_pca_x
 
     # ------------------------------------------------------------- read-only
     @property

@@ -70,8 +70,8 @@ class _DeviceOps(object):
         from . import device
         return device.Cells.from_csr(indptr, indices, data, shape, metric)
 
-    def pdist_stripe(self, cells, r0, r1, out=None):
-        return cells.pdist_stripe(r0, r1, out=out)
+    def pdist_stripe(self, cells, r0, r1, out=None, precision="fp64"):
+        return cells.pdist_stripe(r0, r1, out=out, precision=precision)
 
     def knn_from_d(self, d, k, exclude, row_begin):
         from . import device
@@ -81,9 +81,9 @@ class _DeviceOps(object):
         from . import device
         return device.PeerStripes(stripes, n, rank=rank, group=group)
 
-    def pdist_stripe_p2p(self, cells, peers, rank):
+    def pdist_stripe_p2p(self, cells, peers, rank, precision="fp64"):
         from . import device
-        device.pdist_stripe_p2p(cells, peers, rank)
+        device.pdist_stripe_p2p(cells, peers, rank, precision=precision)
 
     def knn_stripe(self, cells, k, exclude, r0, r1, precision="fp64"):
         return cells.knn_stripe(k, exclude, r0, r1, precision=precision)
@@ -130,7 +130,7 @@ class StripedDistanceMatrix(object):
 
     @classmethod
     def from_host(cls, x_host, metric="correlation", out=None, x_dev=None,
-                  ops=None):
+                  ops=None, precision="fp64"):
         """Single-GPU form for a pinned HOST matrix: the upload of x is hidden
         behind the contraction (``device.pdist_symmetric_from_host``); on
         return the cells are prepared and D (float64, symmetric) is already
@@ -145,10 +145,11 @@ class StripedDistanceMatrix(object):
         self.group, self.distributed, self.rank, self.world = None, False, 0, 1
         self.n, self.p = x_host.shape
         self.metric = metric
+        self.precision = precision
         self.stripes = partition(self.n, 1)
         self.row_begin, self.row_end = self.stripes[0]
         self.cells, self.d_stripe = device.pdist_symmetric_from_host(
-            x_host, metric, out=out, x_dev=x_dev)
+            x_host, metric, out=out, x_dev=x_dev, precision=precision)
         self.d_device = self.d_stripe.device
         return self
 
@@ -177,6 +178,7 @@ class StripedDistanceMatrix(object):
         self.n, self.p = n, p
         self.d_device = csr[2].device
         self.metric = metric
+        self.precision = "fp64"
         self.stripes = partition(self.n, self.world)
         self.row_begin, self.row_end = self.stripes[self.rank]
         self.cells = self.ops.prepare_csr(csr[0], csr[1], csr[2], (n, p), metric)
@@ -184,8 +186,12 @@ class StripedDistanceMatrix(object):
         return self
 
     def __init__(self, x, metric="correlation", shape=None, group=None,
-                 src=0, device=None, ops=None, broadcast=True):
+                 src=0, device=None, ops=None, broadcast=True,
+                 precision="fp64"):
+        """``precision``: Gram kernel of the D stripes -- "fp64" (DMMA) or
+        "fp64_i8" / "fp64_i8s6" (INT8 split on tcgen05, same 1e-10 bar)."""
         self.ops = ops or _DeviceOps()
+        self.precision = precision
         self.group = group
         self.distributed = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(group) if self.distributed else 0
@@ -219,14 +225,16 @@ class StripedDistanceMatrix(object):
         owner's stripe over NVLink.  The two barriers fence the peer writes:
         nobody may still be reading a stripe when the stores start, and every
         store must have landed before anyone reads."""
+        extra = {} if self.precision == "fp64" else {
+            "precision": self.precision}
         if peers is not None and self.world > 1:
             self._fence()
-            self.ops.pdist_stripe_p2p(self.cells, peers, self.rank)
+            self.ops.pdist_stripe_p2p(self.cells, peers, self.rank, **extra)
             self._fence()
             self.d_stripe = peers.tensor(self.rank)
             return self.d_stripe
         self.d_stripe = self.ops.pdist_stripe(self.cells, self.row_begin,
-                                              self.row_end, out=out)
+                                              self.row_end, out=out, **extra)
         return self.d_stripe
 
     def _fence(self):

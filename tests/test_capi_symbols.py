@@ -38,7 +38,7 @@ def test_binding_table_matches_header(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.scedar_abi_version() == 1
+    assert lib.scedar_abi_version() == 2
     assert lib.scedar_max_k() == 127
     assert isinstance(lib.scedar_last_error(), bytes)
 
@@ -134,7 +134,7 @@ def test_argument_errors_of_every_family(lib):
         "pdist_dense bad rows": lambda: lib.scedar_pdist_dense(
             one, 4, 4, 0, 0, 2, 5, one, None),
         "pdist_csr bad precision": lambda: lib.scedar_pdist_csr(
-            one, 1, one, one, 4, 4, 0, 3, 0, 4, one, None),
+            one, 1, one, one, 4, 4, 0, 9, 0, 4, one, None),
         "knn_dense k > n-1": lambda: lib.scedar_knn_dense(
             one, 4, 4, 0, 0, 4, 0, 0, 4, one, one, None),
         "knn_dense bad exclude": lambda: lib.scedar_knn_dense(

@@ -152,3 +152,38 @@ def test_config5_streaming_topk_1m_x_50(b200):
     np.testing.assert_allclose(sd.cpu().numpy(), rdist, rtol=1e-10,
                                atol=1e-12)
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_config1_ties_full_shape(b200, metric):
+    """C1-ties: 3,005 x 19,972 raw Poisson(0.5) counts.
+    Dot products of integer counts are exact in float64, so equal distances
+    are real ties (thousands of them among the 16 nearest) and the whole
+    result must reproduce the oracle BIT FOR BIT: D itself, the full stable
+    column argsort and the k = 15 look-up table under the lowest-index-wins
+    rule."""
+    from oracle import sdm_oracle as orc
+    from scedar_b200 import synth
+    n, p, k = 3005, 19972, 15
+    x = synth.raw_counts(n, p, seed=3005)
+    want = orc.pdist(x, metric)
+    sdm = b200.SampleDistanceMatrix(x, metric=metric)
+    got = sdm._d
+    assert np.array_equal(got, want)
+    # the data really ties: many equal distances among the nearest
+    srt = np.sort(want, axis=1)[:, :k + 2]
+    if metric == "euclidean":
+        assert (np.diff(srt, axis=1) == 0).sum() > 1000
+    lut = sdm.s_knn_ind_lut(k)
+    ref = orc.knn_ind_lut(want, k)
+    assert all(lut[i] == ref[i] for i in range(n))
+    assert np.array_equal(sdm._col_argsorted_d, orc.col_argsorted_d(want))
+    assert np.array_equal(sdm._col_sorted_d, orc.col_sorted_d(want))
+    # the kNN accessor without D (fused kernel) and sklearn's rule
+    nd = b200.SampleDistanceMatrix(x, metric=metric, use_pdist=False)
+    idx, dist = nd.s_knns(k)
+    ridx, rdist = orc.knns_precomputed(want, k)
+    assert np.array_equal(np.array(idx), ridx)
+    assert np.array_equal(np.array(dist), rdist)
+    sdm.release_device()
+    nd.release_device()

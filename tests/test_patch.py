@@ -173,3 +173,74 @@ def test_patched_live_reference_on_fake_device(monkeypatch):
     assert nd_a.s_knn_ind_lut(5) == nd_b.s_knn_ind_lut(5)
     with pytest.raises(ValueError):
         nd_a._d
+
+
+def test_patch_keeps_what_the_device_path_does_not_own(monkeypatch):
+    """Installing the patch must not remove anything from a working scedar:
+    metrics outside cosine / correlation / euclidean keep the reference's own
+    sklearn route (sdm.py:1215-1217, 1064-1079), the sorted-column accessors
+    then work on the matrix it leaves behind, ``use_pca=True`` searches the
+    reference's own PCA coordinates, and ``use_hnsw=True`` reaches the
+    reference's HNSW code (cluster.Community's defaults,
+    scedar/cluster/community.py:117)."""
+    from oracle.ref_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("live reference only exists in the build container")
+    import warnings
+    warnings.simplefilter("ignore")
+    import fake_device
+    fake_device.install(monkeypatch)
+    ref = load_reference()
+    import scedar.knn as ref_knn
+    from scedar_b200 import patch, synth
+    cls = patch.install_sdm(type("RefSub2", (ref,), {}))
+    x = synth.blobs(60, 9, seed=11, n_blobs=3)
+    for metric in ("cityblock", "chebyshev"):
+        a, b = cls(x, metric=metric), ref(x, metric=metric)
+        assert np.array_equal(a._d, b._d)
+        assert a.s_knn_ind_lut(4) == b.s_knn_ind_lut(4)
+        assert np.array_equal(a._col_argsorted_d, b._col_argsorted_d)
+        ta, _ = a.s_knns(4)
+        tb, _ = b.s_knns(4)
+        assert np.array_equal(np.array(ta), np.array(tb))
+        na = cls(x, metric=metric, use_pdist=False)
+        nb = ref(x, metric=metric, use_pdist=False)
+        assert na.s_knn_ind_lut(4) == nb.s_knn_ind_lut(4)
+    # PCA-space search: the reference's PCA, the path's kNN
+    a, b = cls(x, metric="euclidean"), ref(x, metric="euclidean")
+    ta, da = a.s_knns(5, use_pca=True)
+    tb, db = b.s_knns(5, use_pca=True)
+    assert np.array_equal(np.array(ta), np.array(tb))
+    np.testing.assert_allclose(np.array(da), np.array(db), rtol=1e-9)
+    # HNSW goes to the reference's own method (nmslib is a stub in this image:
+    # reaching it is what is checked)
+    seen = {}
+
+    def fake_hnsw(self, k, **kw):
+        seen["k"] = k
+        return [np.zeros(k, dtype=int)] * 60, [np.zeros(k)] * 60
+
+    monkeypatch.setattr(cls, "_s_knns_hnsw", fake_hnsw, raising=False)
+    a.s_knns(3, use_hnsw=True)
+    assert seen == {"k": 3}
+    # the kNN consumers: the reference's own wrappers, serial, device runners
+    rare_cls = type("RareSub", (ref_knn.RareSampleDetection,), {})
+    imp_cls = type("ImpSub", (ref_knn.FeatureImputation,), {})
+    patch.install_knn(rare_cls, imp_cls)
+    a, b = cls(x, metric="euclidean"), ref(x, metric="euclidean")
+    ra = rare_cls(a).detect_rare_samples(3, 6.0, 2, nprocs=4)
+    rb = ref_knn.RareSampleDetection(b).detect_rare_samples(3, 6.0, 2)
+    assert ra == rb
+    xi = np.where(x > np.median(x), x, 0.0)
+    ia = imp_cls(cls(xi, metric="euclidean")).impute_features(4, 2, 1, 1,
+                                                              nprocs=3)
+    ib = ref_knn.FeatureImputation(ref(xi, metric="euclidean")).impute_features(
+        4, 2, 1, 1)
+    assert isinstance(ia[0], ref)          # the reference's class comes back
+    assert np.array_equal(ia[0]._x, ib[0]._x)
+    # a statistic other than the median is the reference's own loop
+    ia = imp_cls(cls(xi, metric="euclidean")).impute_features(
+        4, 2, 1, 1, statistic_fun=np.mean)
+    ib = ref_knn.FeatureImputation(ref(xi, metric="euclidean")).impute_features(
+        4, 2, 1, 1, statistic_fun=np.mean)
+    np.testing.assert_allclose(ia[0]._x, ib[0]._x)
