@@ -12,15 +12,28 @@ whole path: prepare cells (centre rows, Gram diagonal) -> Gram + metric
 epilogue into this rank's D stripe -> row-wise top-k from the stripe ->
 all-gather of the kNN lists.
 
+The Gram kernel is the FP64-grade INT8 split on the tcgen05 tensor cores
+(`--precision fp64_i8`, gram_oz.cu: 7 byte slices, exact INT32 accumulation in
+TMEM, float64 epilogue; same 1e-10 bar as the DMMA kernel, which is timed
+beside it as `dmma_path`).  Every run ends with a parity gate: every rank
+compares rows of ITS OWN D stripe (including the tiles a peer computed and
+stored over NVLink) and of the gathered kNN lists with a float64 NumPy
+evaluation and exits non-zero on any mismatch.
+
 `value` times the step with x already resident in HBM; `e2e` times it through
 the public API from pinned HOST memory (at N=1 x is uploaded range by range on
 a copy stream while the contraction of the rows already there runs; at N>1
 every rank uploads its 1/N row shard over its own PCIe link and the shards are
 all-gathered over NVLink -- all inside the timed region) to the kNN lists back
-on the host.  The reference arm
-(--impl reference) times the CPU oracle port of the reference's own path
-(oracle/sdm_oracle.py: pdist + full stable argsort, what s_knn_ind_lut costs)
-on a bounded row sample with all host threads.
+on the host; `e2e_api` (N=1) is the plugin call a scedar user makes,
+`SampleDistanceMatrix(x_numpy, metric).s_knn_ind_lut(k)`: pageable upload,
+allocation of D, the Python dict of lists.  The reference arm
+(--impl reference) times the reference's own CPU path -- the live class where
+/root/reference is importable (kind "live"), else the oracle port pinned to it
+(oracle/sdm_oracle.py, kind "port") -- on a row sample with all host threads:
+20,000 cells when the requested steps fit a few
+minutes, fewer otherwise, plus one 20,000-cell pass that times `_d`,
+`_col_argsorted_d`, `s_knns(k)` and `s_knn_ind_lut(k)` separately.
 """
 import argparse
 import json
@@ -28,6 +41,11 @@ import os
 import sys
 import threading
 import time
+
+# BLAS / OpenMP threads of the CPU arm and of the parity gate: all host cores,
+# also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(os.cpu_count() or 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -47,9 +65,20 @@ def parse():
     ap.add_argument("--p", type=int, default=2000)
     ap.add_argument("--k", type=int, default=15)
     ap.add_argument("--metric", default="correlation")
-    ap.add_argument("--cpu-sample", type=int, default=6000,
-                    help="rows of the workload the CPU arm is timed on")
+    ap.add_argument("--precision", default=os.environ.get(
+        "SCEDAR_BENCH_PRECISION", "fp64_i8"),
+        choices=["fp64", "fp64_i8", "fp64_i8s6"],
+        help="Gram kernel of the headline path (all FP64-grade, 1e-10)")
+    ap.add_argument("--cpu-sample", type=int, default=20000,
+                    help="rows of the workload the CPU arm is timed on "
+                         "(SURVEY.md section 8d: 20,000)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0,
+                    help="--impl reference: wall time the warm-up + timed "
+                         "steps may take; the sample shrinks to fit")
+    ap.add_argument("--check-rows", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the dmma_path / fast_path / e2e_api extras")
     return ap.parse_args()
 
 
@@ -60,55 +89,149 @@ def workload_name(a):
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's path on a bounded sample
+# CPU arm: the reference's own path on a bounded row sample
 # ---------------------------------------------------------------------------
-def cpu_pass(xs, metric, k):
-    from oracle import sdm_oracle as orc
-    t0 = time.perf_counter()
-    d = orc.pdist(xs, metric)          # SampleDistanceMatrix._d
-    lut = orc.knn_ind_lut(d, k)        # s_knn_ind_lut: full stable argsort
-    t1 = time.perf_counter()
-    assert len(lut) == xs.shape[0]
-    return t1 - t0
+def host_threads():
+    """Pin the BLAS pools to all host cores and describe them."""
+    info = []
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
+        info = [{k: d.get(k) for k in ("user_api", "internal_api",
+                                       "num_threads", "version")}
+                for d in threadpoolctl.threadpool_info()]
+    except Exception as e:                       # pragma: no cover
+        info = [{"error": repr(e)}]
+    return info
 
 
-def cpu_sample(a):
+class CpuArm(object):
+    """The four accessors the reference's users pay for, as callables on a
+    sample: the live class when the checkout is importable, else the port."""
+
+    def __init__(self, metric, k):
+        self.metric, self.k = metric, k
+        self.kind, self.cls = "port", None
+        try:
+            from oracle import ref_loader
+            if ref_loader.reference_available():
+                import warnings
+                warnings.simplefilter("ignore")
+                self.cls = ref_loader.load_reference()
+                self.kind = "live"
+        except Exception:
+            self.cls, self.kind = None, "port"
+        from oracle import sdm_oracle
+        self.orc = sdm_oracle
+
+    def e2e(self, xs):
+        """SampleDistanceMatrix(x, metric).s_knn_ind_lut(k): _d + the full
+        stable column argsort + the dict of lists."""
+        t0 = time.perf_counter()
+        if self.cls is not None:
+            lut = self.cls(xs, metric=self.metric,
+                           nprocs=os.cpu_count()).s_knn_ind_lut(self.k)
+        else:
+            lut = self.orc.knn_ind_lut(self.orc.pdist(xs, self.metric), self.k)
+        dt = time.perf_counter() - t0
+        assert len(lut) == xs.shape[0]
+        return dt
+
+    def breakdown(self, xs):
+        """_d, _col_argsorted_d, s_knns(k) (on the cached D) timed one by
+        one, then the end-to-end call on a fresh object."""
+        out = {}
+        if self.cls is not None:
+            sdm = self.cls(xs, metric=self.metric, nprocs=os.cpu_count())
+            t0 = time.perf_counter()
+            sdm._d
+            out["d_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            sdm._col_argsorted_d
+            out["col_argsorted_d_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            sdm.s_knns(self.k)
+            out["s_knns_s"] = time.perf_counter() - t0
+            del sdm
+        else:
+            t0 = time.perf_counter()
+            d = self.orc.pdist(xs, self.metric)
+            out["d_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            self.orc.col_argsorted_d(d)
+            out["col_argsorted_d_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            self.orc.knns_precomputed(d, self.k)
+            out["s_knns_s"] = time.perf_counter() - t0
+            del d
+        out["s_knn_ind_lut_s"] = self.e2e(xs)
+        n = xs.shape[0]
+        out["rows"] = n
+        out["d_pairs_per_s"] = n * n / out["d_s"]
+        out["e2e_pairs_per_s"] = n * n / out["s_knn_ind_lut_s"]
+        return out
+
+
+def cpu_sample(a, rows=None):
     from scedar_b200 import synth
-    ns = min(a.cpu_sample, a.n)
+    ns = min(a.cpu_sample if rows is None else rows, a.n)
     return synth.log_counts(ns, a.p, seed=a.n)
 
 
-def cpu_baseline(a, reps=1):
+def cpu_baseline(a):
+    """cpu_baseline leg of the default run: one 20,000-cell pass, every
+    accessor timed (about a minute or two of CPU work)."""
+    threads = host_threads()
+    arm = CpuArm(a.metric, a.k)
     xs = cpu_sample(a)
     ns = xs.shape[0]
-    ts = [cpu_pass(xs, a.metric, a.k) for _ in range(reps)]
-    t = min(ts)
-    return {"value": ns * ns / t, "unit": UNIT, "cores": os.cpu_count(),
-            "kind": "port",
+    br = arm.breakdown(xs)
+    return {"value": br["e2e_pairs_per_s"], "unit": UNIT,
+            "cores": os.cpu_count(), "kind": arm.kind,
             "sample": "first {} of {} cells x {} genes, same generator; "
-                      "pdist + s_knn_ind_lut(k={}) (full stable argsort), "
-                      "{:.2f} s per pass; BLAS threads = all host cores, "
-                      "NumPy sort single-threaded".format(
-                          ns, a.n, a.p, a.k, t)}
+                      "SampleDistanceMatrix(x, {!r}).s_knn_ind_lut({}) "
+                      "end to end (pdist + num_correct_dist_mat + full stable "
+                      "column argsort), one pass; BLAS threads = all host "
+                      "cores, NumPy sort single-threaded".format(
+                          ns, a.n, a.p, a.metric, a.k),
+            "breakdown": br, "threadpools": threads}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    xs = cpu_sample(a)
-    ns = xs.shape[0]
-    for _ in range(min(a.warmup, 1)):       # one warm-up is enough on CPU
-        cpu_pass(xs, a.metric, a.k)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        cpu_pass(xs, a.metric, a.k)
-    dt = (time.perf_counter() - t0) / a.steps
+    threads = host_threads()
+    arm = CpuArm(a.metric, a.k)
+    x_full = cpu_sample(a)
+    # sample size: 20,000 cells if (warm-up + steps) passes fit the budget,
+    # else as many as do; calibrated on a small pass (the cost grows like
+    # n^2 log n: pairs/s is NOT size-invariant, so the sample is reported)
+    n_cal = min(3000, x_full.shape[0])
+    t_cal = arm.e2e(x_full[:n_cal])
+    warm = min(a.warmup, 1)                 # one warm-up is enough on CPU
+    per_step = a.cpu_budget_s / max(a.steps + warm, 1)
+    ns = int(n_cal * (per_step / max(t_cal, 1e-3)) ** 0.5 * 0.9)
+    ns = max(1000, min(x_full.shape[0], ns // 100 * 100))
+    xs = x_full[:ns]
+    for _ in range(warm):
+        arm.e2e(xs)
+    ts = [arm.e2e(xs) for _ in range(a.steps)]
+    dt = sum(ts) / len(ts)
     value = ns * ns / dt
     base = {"value": value, "unit": UNIT, "cores": os.cpu_count(),
-            "kind": "port",
-            "sample": "first {} of {} cells x {} genes per step".format(
-                ns, a.n, a.p)}
+            "kind": arm.kind,
+            "sample": "first {} of {} cells x {} genes per step "
+                      "(SampleDistanceMatrix(x, {!r}).s_knn_ind_lut({}) end "
+                      "to end); best step {:.2f} s".format(
+                          ns, a.n, a.p, a.metric, a.k, min(ts)),
+            "best_value": ns * ns / min(ts), "threadpools": threads}
+    if ns < x_full.shape[0]:
+        # the 20,000-cell figures of SURVEY.md section 8d, one pass, outside
+        # the timed steps
+        base["breakdown_20k"] = arm.breakdown(x_full)
+    else:
+        base["breakdown_20k"] = arm.breakdown(xs)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -239,6 +362,8 @@ def run_b200(a):
     dist_host = torch.empty((n, k), dtype=torch.float64).pin_memory()
     phase_events = []
 
+    prec = a.precision
+
     def step(x, broadcast, timed_kernel=False):
         """One pass of the hot path.  With timed_kernel, CUDA events bracket
         the phases on the launching stream (read after the region ends)."""
@@ -248,7 +373,8 @@ def run_b200(a):
         if ev:
             ev[0].record()
         sdm = StripedDistanceMatrix(x, a.metric, shape=(n, p), device=dev,
-                                    broadcast=broadcast)   # K1 + Gram diagonal
+                                    broadcast=broadcast,
+                                    precision=prec)        # K1 + Gram diagonal
         if ev:
             ev[1].record()
         if trace:
@@ -328,7 +454,7 @@ def run_b200(a):
             # on a copy stream, each range is prepared and the rows of the
             # lower triangle it completes are contracted at once
             sdm = StripedDistanceMatrix.from_host(x_host, a.metric, out=d_buf,
-                                                  x_dev=x_dev)
+                                                  x_dev=x_dev, precision=prec)
             idx, dd = sdm.knn(k, EXCLUDE_FIRST)
             sdm.close()
         else:
@@ -347,6 +473,60 @@ def run_b200(a):
     sync_all()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / a.steps)
     e2e_value = float(n) * n / e2e_s
+
+    # ---- parity gate on the result of the last end-to-end step (not timed) ---
+    # Every rank checks rows of ITS OWN stripe of D -- all columns, so at N > 1
+    # also the tiles a peer computed and stored over NVLink -- and the same
+    # rows of the gathered kNN lists against float64 NumPy; any mismatch ends
+    # the run with a non-zero exit code on every rank.
+    gate = parity_gate(a, rank, world, r0, r1, x_dev, d_buf, idx, dd)
+    ok = torch.tensor([1.0 if gate["ok"] else 0.0], dtype=torch.float64,
+                      device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) != 1.0:
+        print("bench parity gate FAILED on rank {}: {}".format(rank, gate),
+              file=sys.stderr, flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        raise SystemExit(3)
+
+    # ---- secondary: the DMMA kernel and the tcgen05 fast path, same workload --
+    dmma = None
+    if not a.no_secondary and prec != "fp64":
+        ev_d = []
+
+        def dmma_step():
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            sdm = StripedDistanceMatrix(x_dev, a.metric, shape=(n, p),
+                                        device=dev, broadcast=False)
+            e[0].record()
+            sdm.compute_d(out=d_buf, peers=peers)
+            e[1].record()
+            ev_d.append(e)
+            i2, d2 = sdm.knn(k, EXCLUDE_FIRST)
+            sdm.close()
+            return i2, d2
+        dmma_step()
+        sync_all()
+        ev_d.clear()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        reps = min(a.steps, 3)
+        g0.record()
+        for _ in range(reps):
+            i2, d2 = dmma_step()
+        g1.record()
+        sync_all()
+        dm_ms = max_over_ranks(g0.elapsed_time(g1)) / reps
+        dm_gram = sum(e[0].elapsed_time(e[1]) for e in ev_d) / len(ev_d)
+        dmma = {"what": "same step with the DMMA Gram kernel "
+                        "(mma.sync.m8n8k4.f64, round 1's headline)",
+                "ms_per_step": dm_ms, "value": float(n) * n / (dm_ms * 1e-3),
+                "unit": UNIT, "gram_ms": dm_gram,
+                "knn_indices_identical_to_headline": bool(torch.equal(i2, idx)),
+                "max_abs_knn_distance_difference": float(
+                    (d2 - dd).abs().max())}
 
     # ---- secondary: the tcgen05 fast path on the same workload --------------
     # (D within 1e-4*max(D) of the FP64 matrix, kNN exact after the FP64
@@ -374,7 +554,7 @@ def run_b200(a):
         return fi, fd
 
     fast = None
-    if k <= 55:
+    if k <= 55 and not a.no_secondary:
         for _ in range(a.warmup):
             fast_step()
         sync_all()
@@ -420,20 +600,31 @@ def run_b200(a):
         peers.close()
         peers = None
 
-    # ---- self-check of the last step's result on 64 rows (not timed) -------
-    if rank == 0 and a.metric == "correlation":
-        rows = np.arange(0, n, max(1, n // 64))[:64]
-        xs = x_host.numpy()
-        xc = xs - xs.mean(axis=1, keepdims=True)
-        nrm = np.sqrt(np.einsum("ij,ij->i", xc, xc))
-        dref = 1.0 - (xc[rows] @ xc.T) / nrm[rows, None] / nrm[None, :]
-        dref[np.arange(len(rows)), rows] = -1.0        # self sorts first
-        ref = np.argsort(dref, kind="mergesort", axis=1)[:, 1:k + 1]
-        got = idx_host[rows].numpy()
-        mism = int((ref != got).any(axis=1).sum())
-        if mism:
-            raise SystemExit("bench self-check failed: {} of {} sampled rows "
-                             "disagree with NumPy".format(mism, len(rows)))
+    # ---- e2e_api (N = 1): the plugin call a scedar user makes ----------------
+    api = None
+    if world == 1 and not a.no_secondary:
+        import scedar_b200
+        del d_buf
+        torch.cuda.empty_cache()
+        x_np = x_host.numpy()                     # pageable from torch's view
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            s_api = scedar_b200.SampleDistanceMatrix(x_np, metric=a.metric)
+            lut = s_api.s_knn_ind_lut(k)
+            ts.append(time.perf_counter() - t0)
+            api_ok = all(lut[int(i)] == idx_host[int(i)].tolist()
+                         for i in gate["rows"])
+            s_api.release_device()
+            del s_api, lut
+        api = {"what": "SampleDistanceMatrix(x_numpy, metric={!r})."
+                       "s_knn_ind_lut({}) through the drop-in class: upload "
+                       "of x from pageable host memory, allocation of the "
+                       "{:.0f} GB D, Gram, top-k, download, Python dict of "
+                       "lists".format(a.metric, k, 8e-9 * n * n),
+               "s_per_call": min(ts), "first_call_s": ts[0],
+               "value": float(n) * n / min(ts), "unit": UNIT,
+               "lists_identical_to_headline_on_gate_rows": bool(api_ok)}
 
     if rank != 0:
         if world > 1:
@@ -445,19 +636,58 @@ def run_b200(a):
     # evenly over the ranks (every tile pair once), n(n+1)/2 in total
     entries = (n * (n + 1.0) / 2.0) * rows_here / n
     alg_flops = 2.0 * p * entries          # n(n+1)p/N
-    fp64_peak = fp64_peak_tflops()
-    achieved = alg_flops / (gram_avg_ms * 1e-3) * 1e-12
     peaks = measured_peaks()
+    achieved = alg_flops / (gram_avg_ms * 1e-3) * 1e-12
+    if prec == "fp64":
+        peak = fp64_peak_tflops()
+        roof = {
+            "kernel": "gram_f64_kernel<STORE> (DMMA m8n8k4 + fused metric "
+                      "epilogue, lower tiles mirrored)",
+            "bound": "tensor", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "FP64 DMMA probe tools/fp64_peak.cu measured on "
+                           "this pool (profiles/r01_fp64_peak.json); "
+                           "MEASURED_PEAKS.json has no FP64 figure"}
+    else:
+        slices = 7 if prec == "fp64_i8" else 6
+        products = slices * (slices + 1) // 2
+        p_oz = (p + 63) // 64 * 64
+        executed = achieved * products * p_oz / p     # INT8 TOP/s on the pipe
+        bf16 = peaks.get("bf16_tflops_sustained") or peaks.get(
+            "bf16_tflops") or 1400.0
+        peak = 2.0 * bf16
+        roof = {
+            "kernel": "gram_oz_kernel<{}> (tcgen05.mma kind::i8, {} byte "
+                      "slices, {} products, TMA-fed, INT32 TMEM accumulators, "
+                      "float64 metric epilogue, lower tiles mirrored)".format(
+                          slices, slices, products),
+            "bound": "tensor", "achieved": executed, "peak": peak,
+            "unit": "TOP/s (INT8, executed)", "frac": executed / peak,
+            "algorithmic_tflops": achieved,
+            "executed_over_algorithmic": products * p_oz / p,
+            "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained "
+                           "({}; the kernel is timed inside a seconds-long "
+                           "step): kind::i8 issues at twice the rate of "
+                           "kind::f16 on this part (tools/umma_probe.cu, "
+                           "profiles/r02_umma_probe.log: 8,173 vs 4,087 "
+                           "MAC/cycle/SM); of measured".format(bf16),
+            "frac_of_burst_peak": executed / (2.0 * peaks.get(
+                "bf16_tflops", 1640.9)),
+            "vs_fp64_dmma_peak": achieved / fp64_peak_tflops()}
+    roof.update({"algorithmic_flops_per_launch": alg_flops,
+                 "ms_per_launch": gram_avg_ms,
+                 "share_of_step": gram_avg_ms / ms_per_step,
+                 "traffic": recorded_traffic(prec) if world == 1 else None})
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "n_cells": n, "n_genes": p,
-                   "k": k, "metric": a.metric,
+                   "k": k, "metric": a.metric, "gram_kernel": prec,
                    "sharding": "row stripes x{}{}".format(
-                       world, ", symmetric tile pairs mirrored into the "
-                       "owner's stripe by peer stores over NVLink"
+                       world, ", symmetric tile pairs stored into both "
+                       "owners' stripes (peer stores over NVLink)"
                        if world > 1 else ", lower tiles mirrored"),
                    "l2": "inputs larger than L2 (x {:.1f} GB, D stripe "
                          "{:.1f} GB per GPU)".format(
@@ -475,22 +705,12 @@ def run_b200(a):
                           "x row-sharded over the {} ranks' pinned host "
                           "buffers, uploaded in parallel, all-gathered over "
                           "NVLink".format(world))},
+        "e2e_api": api,
         "gpu_launches": int(launches),
-        "roofline": {
-            "kernel": "gram_f64_kernel<STORE> (DMMA m8n8k4 + fused metric "
-                      "epilogue, lower tiles mirrored)",
-            "bound": "tensor", "achieved": achieved, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "peak_source": "FP64 DMMA probe tools/fp64_peak.cu measured on "
-                           "this pool (profiles/r01_fp64_peak.json); "
-                           "MEASURED_PEAKS.json has no FP64 figure "
-                           "(bf16 {} TF/s is not the pipe this kernel "
-                           "uses)".format(peaks.get("bf16_tflops")),
-            "algorithmic_flops_per_launch": alg_flops,
-            "ms_per_launch": gram_avg_ms,
-            "share_of_step": gram_avg_ms / ms_per_step,
-            "traffic": recorded_traffic()},
+        "roofline": roof,
+        "parity_gate": {kk: vv for kk, vv in gate.items() if kk != "rows"},
         "clocks": clock_info,
+        "dmma_path": dmma,
         "fast_path": fast,
     }
     if world == 1 and not a.no_cpu_baseline:
@@ -498,6 +718,68 @@ def run_b200(a):
     os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_gate(a, rank, world, r0, r1, x_dev, d_stripe, idx, dd):
+    """Rows of this rank's stripe of D and of the gathered kNN lists against a
+    float64 NumPy evaluation of the metric over all cells (plain NumPy: the
+    oracle package stays test infrastructure).  Tolerance 1e-10 of max(D);
+    indices must equal the stable (distance, index) order, a mismatch being
+    tolerated only between distances within 4 ulp (none is expected)."""
+    import numpy as np
+    import torch
+    n, k = a.n, a.k
+    m = min(a.check_rows, r1 - r0)
+    if m <= 0:
+        return {"ok": True, "rows_checked": 0, "rows": []}
+    rows = np.unique(np.linspace(r0, r1 - 1, m).astype(np.int64))
+    x = x_dev.cpu().numpy()
+    if a.metric == "euclidean":
+        sq = np.einsum("ij,ij->i", x, x)
+        d2 = -2.0 * (x[rows] @ x.T)
+        d2 += sq[rows, None]
+        d2 += sq[None, :]
+        ref = np.sqrt(np.maximum(d2, 0.0))
+    else:
+        xc = x - x.mean(axis=1, keepdims=True) if a.metric == "correlation" \
+            else x
+        nrm = np.sqrt(np.einsum("ij,ij->i", xc, xc))
+        inv = np.where(nrm > 0, 1.0 / np.where(nrm > 0, nrm, 1.0), 0.0)
+        ref = 1.0 - (xc[rows] @ xc.T) * inv[rows, None] * inv[None, :]
+        np.maximum(ref, 0.0, out=ref)
+    ref[np.arange(len(rows)), rows] = 0.0
+    rt = torch.from_numpy(rows - r0).to(d_stripe.device)
+    got = d_stripe[rt].cpu().numpy()
+    err = float(np.abs(got - ref).max() / ref.max())
+    diag_ok = not got[np.arange(len(rows)), rows].any()
+    # columns == rows inside the stripe's own square block (bit-symmetry)
+    blk = d_stripe[:, r0:r1]
+    sym_ok = bool(torch.equal(blk[:2048, :2048], blk[:2048, :2048].T))
+    # kNN lists of the same rows: rank 0 of the stable order is dropped
+    # (s_knn_ind_lut, sdm.py:764)
+    order = np.argsort(ref, kind="mergesort", axis=1)[:, 1:k + 1]
+    gi = idx[torch.from_numpy(rows).to(idx.device)].cpu().numpy()
+    gd = dd[torch.from_numpy(rows).to(dd.device)].cpu().numpy()
+    bad = np.nonzero((order != gi).any(axis=1))[0]
+    near_ties = 0
+    hard = 0
+    for r in bad:
+        dw, dg = ref[r, order[r]], ref[r, gi[r]]
+        if np.abs(dw - dg).max() <= 4 * np.spacing(max(dw.max(), 1e-300)):
+            near_ties += 1
+        else:
+            hard += 1
+    derr = float(np.abs(gd - np.take_along_axis(ref, gi, axis=1)).max()
+                 / ref.max())
+    ok = (err <= 1e-10 and diag_ok and sym_ok and hard == 0 and near_ties == 0
+          and derr <= 1e-10)
+    return {"ok": bool(ok), "rows_checked": int(len(rows)),
+            "stripe": [int(r0), int(r1)], "max_rel_err_d": err,
+            "zero_diagonal": bool(diag_ok), "bit_symmetric_block": sym_ok,
+            "knn_rows_differing": int(len(bad)), "knn_near_ties": near_ties,
+            "knn_max_rel_err_dist": derr,
+            "reference": "float64 NumPy over all {} cells, rank-local".format(n),
+            "rows": rows.tolist()}
 
 
 def measured_peaks():
@@ -517,11 +799,13 @@ def fp64_peak_tflops():
         return 37.1
 
 
-def recorded_traffic():
+def recorded_traffic(prec="fp64"):
     """DRAM bytes per launch of the Gram kernel from the committed ncu
-    capture, when one exists for this workload (else null)."""
+    capture of this workload on ONE GPU, when one exists (else null)."""
+    name = {"fp64": "r01_gram_traffic.json"}.get(
+        prec, "r02_gram_oz_traffic_{}.json".format(prec))
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_gram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             return json.load(f).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         return None

@@ -32,18 +32,29 @@
 // log counts) is of the size of DGEMM's own rounding.
 //
 // Kernel (persistent, one CTA per SM, 320 threads):
-//   warp 0     TMA producer: per 64-byte K slab S boxes of 128 rows (row-tile
-//              slices) + S boxes of 64 rows (column-tile slices), 64B swizzle,
-//              ring of 2 (S=7) / 3 (S=6) stages, full/empty mbarriers
-//   warp 1     MMA issuer (elected lane), descriptors = stage base + constant
-//   warps 2-9  epilogue: TMEM lane quarter = warp % 4, column half = (warp-2)/4;
-//              4 columns at a time: S x tcgen05.ld.x4 -> integers -> float64 ->
-//              finish_entry -> mirrored store straight from registers (lanes =
-//              consecutive rows: coalesced), row-major store through a 9 KB
-//              staging tile
+//   warp 0     TMA producer, 128-byte K slabs (128B swizzle; with 64-byte box rows
+//              the TMA unit of one SM delivers ~52 B/cycle, with 128-byte rows
+//              73-105 -- tools/tma_probe.cu -- and this kernel needs 47): the S
+//              slices of the row tile (16 KB each) sit in S single slots that
+//              are re-filled slice by slice as the MMAs of a slice retire, the
+//              S slices of the column tile (8 KB each, stacked) are double
+//              buffered; full / empty mbarriers per slot
+//   warp 1     MMA issuer (elected lane), slice-major inside a slab, descriptors
+//              = slot base + constant
+//   warps 2-9  epilogue: TMEM lane quarter = warp % 4, column half = (warp-2)/4.
+//              Phase 1 drains the accumulators (S x tcgen05.ld.x4 per 4 columns,
+//              the next 4 in flight) into 32 float64 dot products per thread and
+//              hands TMEM back; phase 2 (under the next tile's MMAs) applies
+//              finish_entry and stores: the mirrored tile straight from the
+//              registers (lanes = consecutive entries of a row of D), the tile
+//              itself in 32-byte runs (st.global.v4.f64)
 // TMEM holds S x 64 columns (448 of 512 for S = 7): no second accumulator set,
-// so the epilogue (a few % of a tile at p = 2000) is not overlapped with the
-// next tile's MMAs; the producer does run ahead into the next tile.
+// so phase 1 (~8 k cycles of an ~80 k cycle tile at p = 2000) is not overlapped.
+// Measured cost model of the MMA stream (SCEDAR_B200_OZ_DEBUG=1 prints per-tile
+// cycle counters): an instruction of N = 64 m columns takes ~128 cycles for
+// m = 3, 4 and ~96 for m = 1, 2 (ideal 32 m): the 128 x 32-byte row operand is
+// re-read from shared memory by every instruction, so the triangular product
+// set (runs of 7, 6, ... 1 slices) runs at ~0.79 of the pipe's rate.
 // Tiles (128 rows x 64 columns) come from a host-built list in L2-friendly
 // order, dealt round-robin to the CTAs; the list also carries what to store
 // (tile / mirrored tile), so the whole-matrix, row-stripe, peer-store and
@@ -65,17 +76,17 @@ namespace {
 
 constexpr int OM = 128;            // tile rows = TMEM lanes
 constexpr int ON = 64;             // tile columns (per slice diagonal)
-constexpr int OKB = 64;            // K bytes per slab (one 64B-swizzle row)
-constexpr int A_SLAB = OM * OKB;   // 8 KB
-constexpr int B_SLAB = ON * OKB;   // 4 KB
-constexpr int oz_stage_bytes(int S) { return S * (A_SLAB + B_SLAB); }
-constexpr int oz_stages(int S) { return S <= 6 ? 3 : 2; }
-constexpr int STG_LD = 9;          // staging row stride in doubles (8 columns + 1)
-constexpr int STG_BYTES = OM * STG_LD * 8;
+constexpr int OKB = 128;           // K bytes per slab (one 128B-swizzle row: the TMA unit of an
+                                   // SM moves ~1 box row per cycle, so 64-byte rows cap it at
+                                   // ~52 B/cycle -- tools/tma_probe.cu -- against the 47 this
+                                   // kernel needs; 128-byte rows reach 73-105)
+constexpr int A_SLAB = OM * OKB;   // 16 KB: one slice of the row tile, one K slab
+constexpr int B_SLAB = ON * OKB;   // 8 KB
+// shared memory: the S row-tile slices of ONE slab, each slot re-filled as soon
+// as the MMAs of its slice have retired (the MMA loop runs slice-major), and
+// TWO slabs of column-tile slices (all S are needed from the first slice on)
 constexpr int OZ_BAR_BYTES = 256;
-constexpr int oz_smem(int S) {
-  return 1024 + oz_stages(S) * oz_stage_bytes(S) + STG_BYTES + OZ_BAR_BYTES;
-}
+constexpr int oz_smem(int S) { return 1024 + S * A_SLAB + 2 * S * B_SLAB + OZ_BAR_BYTES; }
 static_assert(oz_smem(6) <= 227 * 1024 && oz_smem(7) <= 227 * 1024, "shared memory budget");
 constexpr int OZ_EPI_WARPS = 8;
 constexpr int OZ_EPI_THREADS = 32 * OZ_EPI_WARPS;
@@ -103,6 +114,8 @@ struct OzArgs {
   const OzTile* tiles;
   int n_tiles;
   int64_t ldd;
+  unsigned long long* dbg;                // SCEDAR_B200_OZ_DEBUG: 8 cycle counters per CTA
+  int vec_ok;                             // rows of D are 32-byte aligned (ldd % 4 == 0)
   int world;                              // output stripes (1 for a single buffer)
   int64_t stripe_begin[kOzPeers + 1];     // row ranges of the stripes
   double* stripe_ptr[kOzPeers];
@@ -222,108 +235,177 @@ oz_slice_kernel(const double* __restrict__ xw, int64_t n, int64_t p, int64_t p_p
 }
 
 // ---- K2: the tile kernel -------------------------------------------------------
+// 32-byte store of four consecutive doubles (evict-first: D is write-once)
+__device__ __forceinline__ void st_cs_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c),
+               "d"(d)
+               : "memory");
+}
+
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const OzArgs a) {
-  constexpr int NST = oz_stages(S);
-  constexpr int STAGE = oz_stage_bytes(S);
+  constexpr int A_STAGE = S * A_SLAB, B_STAGE = S * B_SLAB;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  double* stg = reinterpret_cast<double*>(gbase + NST * STAGE);
-  const uint32_t bars = base + NST * STAGE + STG_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 32, tfull = bars + 64, tempty = bars + 72;
+  const uint32_t ring_a = base, ring_b = base + A_STAGE;
+  const uint32_t bars = ring_b + 2 * B_STAGE;
+  // barrier slots (8 bytes each): fullA[S], emptyA[S], fullB[2], emptyB[2], tfull, tempty
+  const uint32_t full_a = bars, empty_a = bars + 64, full_b = bars + 128, empty_b = bars + 144,
+                 tfull = bars + 160, tempty = bars + 168;
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(gbase + NST * STAGE + STG_BYTES + 128);
+      reinterpret_cast<volatile uint32_t*>(gbase + (bars - base) + 192);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = a.kslabs;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_a + 8 * s, 1);
+      mbar_init(empty_a + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_b + 8 * s, 1);
+      mbar_init(empty_b + 8 * s, 1);
     }
     mbar_init(tfull, 1);
     mbar_init(tempty, OZ_EPI_WARPS);
     mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc512(bars + 128);
+  if (warp == 1) tc::tmem_alloc512(bars + 192);
   tc::fence_before();
   __syncthreads();
   tc::fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ---- TMA producer ----------------------------------------------------------
+    // ---- TMA producer.  Slab `it` of this CTA's stream needs slice slots
+    // A_0..A_S-1 (use number `it` of each slot) and column buffer it & 1.  The
+    // requests go out in the order the slots come free: the slices of slab
+    // it + 1 one by one while slab it is contracted, then the columns of slab
+    // it + 2 -- each a full slab period ahead of its use.
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-        const OzTile tl = a.tiles[t];
-        const int i0 = tl.I * OM, j0 = tl.J * ON;
-        for (int ks = 0; ks < KS; ++ks, ++it) {
-          const uint32_t s = it % NST, ph = (it / NST) & 1;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_expect_tx(full0 + 8 * s, STAGE);
-          const uint32_t st = base + s * STAGE;
-#pragma unroll
-          for (int sl = 0; sl < S; ++sl)
-            tma_load_2d(st + sl * A_SLAB, &map_a, ks * OKB, (int)(sl * a.n_pl) + i0,
-                        full0 + 8 * s);
-#pragma unroll
-          for (int sl = 0; sl < S; ++sl)
-            tma_load_2d(st + S * A_SLAB + sl * B_SLAB, &map_b, ks * OKB,
-                        (int)(sl * a.n_pl) + j0, full0 + 8 * s);
+      int my_tiles = 0;
+      for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) ++my_tiles;
+      const int total = my_tiles * KS;
+      int c_i0 = 0, c_j0 = 0, c_tile = -1;
+      auto coords = [&](int it, int& i0, int& j0, int& ks) {
+        const int tl_i = it / KS;
+        ks = it - tl_i * KS;
+        if (tl_i != c_tile) {
+          const OzTile tl = a.tiles[blockIdx.x + (long long)tl_i * gridDim.x];
+          c_i0 = tl.I * OM;
+          c_j0 = tl.J * ON;
+          c_tile = tl_i;
         }
+        i0 = c_i0;
+        j0 = c_j0;
+      };
+      auto load_a = [&](int it) {
+        int i0, j0, ks;
+        coords(it, i0, j0, ks);
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl) {
+          mbar_wait(empty_a + 8 * sl, (uint32_t)((it & 1) ^ 1));
+          mbar_expect_tx(full_a + 8 * sl, A_SLAB);
+          tma_load_2d(ring_a + sl * A_SLAB, &map_a, ks * OKB, (int)(sl * a.n_pl) + i0,
+                      full_a + 8 * sl);
+        }
+      };
+      auto load_b = [&](int it) {
+        int i0, j0, ks;
+        coords(it, i0, j0, ks);
+        const uint32_t buf = (uint32_t)(it & 1), ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(empty_b + 8 * buf, ph ^ 1);
+        mbar_expect_tx(full_b + 8 * buf, B_STAGE);
+        const uint32_t st = ring_b + buf * B_STAGE;
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl)
+          tma_load_2d(st + sl * B_SLAB, &map_b, ks * OKB, (int)(sl * a.n_pl) + j0,
+                      full_b + 8 * buf);
+      };
+      if (total > 0) load_b(0);
+      if (total > 1) load_b(1);
+      if (total > 0) load_a(0);
+      for (int it = 0; it < total; ++it) {
+        if (it + 1 < total) load_a(it + 1);
+        if (it + 2 < total) load_b(it + 2);
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer --------------------------------------------------------------
+    // ---- MMA issuer: slice-major inside a slab, so that a row-tile slice is
+    // done with (and its slot re-filled) after its four K steps
     const bool el = tc::elect_one();
     uint32_t it = 0, tcount = 0;
+    long long w_tempty = 0, w_full = 0;
+    const long long t_begin = clock64();
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tcount) {
+      long long c0 = a.dbg ? clock64() : 0;
       mbar_wait(tempty, (tcount & 1) ^ 1);   // the epilogue has drained the accumulators
+      if (a.dbg) w_tempty += clock64() - c0;
       tc::fence_after();
       for (int ks = 0; ks < KS; ++ks, ++it) {
-        const uint32_t s = it % NST, ph = (it / NST) & 1;
-        mbar_wait(full0 + 8 * s, ph);
-        tc::fence_after();
-        const uint32_t st = base + s * STAGE;
-        const uint64_t da = tc::desc_sw64(st), db = tc::desc_sw64(st + S * A_SLAB);
+        const uint32_t buf = it & 1;
+        c0 = a.dbg ? clock64() : 0;
+        mbar_wait(full_b + 8 * buf, (it >> 1) & 1);
+        if (a.dbg) w_full += clock64() - c0;
+        const uint64_t db = tc::desc_sw128(ring_b + buf * B_STAGE);
 #pragma unroll
-        for (int kk = 0; kk < OKB / 32; ++kk) {
+        for (int sl = 0; sl < S; ++sl) {
+          c0 = a.dbg ? clock64() : 0;
+          mbar_wait(full_a + 8 * sl, it & 1);
+          if (a.dbg) w_full += clock64() - c0;
+          tc::fence_after();
+          const uint64_t da = tc::desc_sw128(ring_a + sl * A_SLAB);
 #pragma unroll
-          for (int sl = 0; sl < S; ++sl) {
-            // slice sl of the row tile x slices [0, S - sl) of the column tile, at
-            // most four (N <= 256) per instruction; slice 0 goes first in a tile:
-            // it covers every diagonal, so its first K step zero-initialises them
-#pragma unroll
-            for (int t0 = 0; t0 < S - sl; t0 += 4) {
-              const int m = (S - sl - t0) < 4 ? (S - sl - t0) : 4;
-              const uint32_t acc = (ks | kk | sl) != 0;
-              if (el)
-                tc::mma_i8(tmem_base + (uint32_t)((sl + t0) * ON),
-                           da + (uint64_t)((sl * A_SLAB + kk * 32) >> 4),
-                           db + (uint64_t)((t0 * B_SLAB + kk * 32) >> 4), tc::idesc_u8(ON * m),
-                           acc);
+          for (int kk = 0; kk < OKB / 32; ++kk) {
+            // slice sl of the row tile x slices [0, S - sl) of the column tile in one
+            // instruction (N = 64 m <= 256) or two.  An instruction costs
+            // max(N / 2, ~100) cycles -- the 4 KB row operand is read from shared
+            // memory at ~41 B/cycle whatever N is (measured: the S = 6 and S = 7
+            // tile times fit this model to 2 %) -- so a run of 5 or 6 slices is cut
+            // into two instructions of <= 192 columns (100 + 100 cycles), not 256 +
+            // a short one (128 + 100).  Slice 0 goes first in a tile: it covers
+            // every diagonal, so its first K step zero-initialises them.
+            constexpr int kFullRun = 4;
+            const int run = S - sl;
+            const int first = run <= kFullRun ? run : (run + 1) / 2;
+            const uint32_t acc = (ks | kk | sl) != 0;
+            if (el) {
+              tc::mma_i8(tmem_base + (uint32_t)(sl * ON), da + (uint64_t)((kk * 32) >> 4),
+                         db + (uint64_t)((kk * 32) >> 4), tc::idesc_u8(ON * first), acc);
+              if (run > first)
+                tc::mma_i8(tmem_base + (uint32_t)((sl + first) * ON),
+                           da + (uint64_t)((kk * 32) >> 4),
+                           db + (uint64_t)((first * B_SLAB + kk * 32) >> 4),
+                           tc::idesc_u8(ON * (run - first)), acc);
             }
           }
+          if (el) tc::commit(empty_a + 8 * sl);   // slot reusable once these MMAs retire
+          __syncwarp();
         }
-        if (el) tc::commit(empty0 + 8 * s);   // stage reusable once these MMAs retire
+        if (el) tc::commit(empty_b + 8 * buf);
         __syncwarp();
       }
       if (el) tc::commit(tfull);              // accumulators complete
       __syncwarp();
+    }
+    if (a.dbg && lane == 0) {
+      a.dbg[8 * blockIdx.x + 0] = (unsigned long long)w_tempty;
+      a.dbg[8 * blockIdx.x + 1] = (unsigned long long)w_full;
+      a.dbg[8 * blockIdx.x + 2] = (unsigned long long)(clock64() - t_begin);
+      a.dbg[8 * blockIdx.x + 7] = tcount;
     }
   } else {
     // ---- epilogue warps 2..9 -----------------------------------------------------
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int h = (warp - 2) >> 2;            // column half
     const int r = q * 32 + lane;              // tile row
-    const int et = threadIdx.x - 64;          // 0..255
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tcount = 0;
+    long long e_wait = 0, e_p1 = 0, e_p2 = 0;
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tcount) {
       const OzTile tl = a.tiles[t];
       const int64_t i0 = (int64_t)tl.I * OM, j0 = (int64_t)tl.J * ON;
@@ -341,61 +423,104 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int od = 0, om = 0;
       while (od + 1 < a.world && i0 >= a.stripe_begin[od + 1]) ++od;
       while (om + 1 < a.world && j0 >= a.stripe_begin[om + 1]) ++om;
-      double* __restrict__ dbase = a.stripe_ptr[od] + (i0 - a.stripe_begin[od]) * a.ldd + j0;
-      double* __restrict__ mbase = a.stripe_ptr[om] + (j0 - a.stripe_begin[om]) * a.ldd + i0;
-      const bool direct = tl.flags & TILE_DIRECT, mirror = tl.flags & TILE_MIRROR;
+      // this thread's run of 32 entries of row gi, and column 0 of its mirror
+      double* __restrict__ drow =
+          a.stripe_ptr[od] + (gi - a.stripe_begin[od]) * a.ldd + j0 + h * 32;
+      double* __restrict__ mcol =
+          a.stripe_ptr[om] + (j0 + h * 32 - a.stripe_begin[om]) * a.ldd + gi;
+      const bool direct = (tl.flags & TILE_DIRECT) && gi >= a.row_lo && gi < a.row_hi;
+      const bool mirror = (tl.flags & TILE_MIRROR) && row_ok;
 
+      long long ec0 = a.dbg ? clock64() : 0;
       mbar_wait(tfull, tcount & 1);
+      long long ec1 = a.dbg ? clock64() : 0;
       tc::fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 32; c0 += 4) {
-        uint32_t v[S][4];
+      // phase 1: drain the accumulators into raw dot products held in registers
+      // (32 per thread), four columns at a time, the next four in flight while
+      // these are combined; then hand TMEM back so the next tile's MMAs run
+      // under phase 2
+      double pv[32];
+      uint32_t va[S][4], vb[S][4];
+      auto drain = [&](uint32_t (&v)[S][4], int c0) {
 #pragma unroll
         for (int d = 0; d < S; ++d)
           tc::tmem_ld4_async(lane_base + (uint32_t)(d * ON + h * 32 + c0), v[d]);
+      };
+      auto settle = [&](uint32_t (&v)[S][4]) {
 #pragma unroll
         for (int d = 0; d < S; ++d) tc::tmem_wait4(v[d]);
-        if (c0 == 28) {
-          // last read of this tile: the accumulators may be overwritten
-          tc::fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
-        }
+      };
+      auto combine = [&](const uint32_t (&v)[S][4], int c0) {
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int c = h * 32 + c0 + cc;
-          const int64_t gj = j0 + c;
-          double dv = 0.0;
+          const int64_t gj = j0 + h * 32 + c0 + cc;
+          double P = 0.0;
           if (gj < a.n) {
             uint32_t acc[S];
 #pragma unroll
             for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
             const double val = oz_value<S>(acc, hii + __ldg(a.hi + gj) + a.c0,
                                            loi + __ldg(a.lo + gj));
-            const double P = __dmul_rn(val, __dmul_rn(sci, __ldg(a.sc + gj)));
+            P = __dmul_rn(val, __dmul_rn(sci, __ldg(a.sc + gj)));
+          }
+          pv[c0 + cc] = P;
+        }
+      };
+      drain(va, 0);
+      settle(va);
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 8) {
+        drain(vb, c0 + 4);
+        combine(va, c0);
+        settle(vb);
+        if (c0 + 8 < 32) drain(va, c0 + 8);
+        combine(vb, c0 + 4);
+        if (c0 + 8 < 32) settle(va);
+      }
+      tc::fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);   // the accumulators may be overwritten
+      long long ec2 = a.dbg ? clock64() : 0;
+      // phase 2 (under the next tile's MMAs): metric epilogue and the two stores.
+      // The mirrored tile is written straight from the registers -- lanes are
+      // consecutive entries of a row of D; the tile itself in 32-byte runs
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 4) {
+        double dv[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = c0 + cc;
+          const int64_t gj = j0 + h * 32 + c;
+          dv[cc] = 0.0;
+          if (gj < a.n) {
             const double stj = __ldg(a.stat + gj);
             const bool lower = gi >= gj;
-            dv = finish_entry(P, lower ? sti : stj, lower ? stj : sti, gi == gj, a.euclid);
-            // column c of the tile is row j0 + c of D: lanes are consecutive entries
-            if (mirror && row_ok && gj >= a.row_lo && gj < a.row_hi)
-              __stcs(mbase + (int64_t)c * a.ldd + r, dv);
+            dv[cc] = finish_entry(pv[c], lower ? sti : stj, lower ? stj : sti, gi == gj,
+                                  a.euclid);
+            if (mirror && gj >= a.row_lo && gj < a.row_hi) __stcs(mcol + (int64_t)c * a.ldd, dv[cc]);
           }
-          stg[r * STG_LD + h * 4 + cc] = dv;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
         if (direct) {
-          // 128 rows x (2 x 4 columns): 32-byte runs, 4 rows per warp instruction
+          const int64_t gj0 = j0 + h * 32 + c0;
+          if (a.vec_ok && gj0 + 3 < a.n) {
+            st_cs_v4(drow + c0, dv[0], dv[1], dv[2], dv[3]);
+          } else {
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int row = pass * 32 + (et >> 3), seg = (et >> 2) & 1, cc = et & 3;
-            const int64_t gi2 = i0 + row, gj = j0 + seg * 32 + c0 + cc;
-            if (gi2 >= a.row_lo && gi2 < a.row_hi && gj < a.n)
-              __stcs(dbase + (int64_t)row * a.ldd + seg * 32 + c0 + cc,
-                     stg[row * STG_LD + seg * 4 + cc]);
+            for (int cc = 0; cc < 4; ++cc)
+              if (gj0 + cc < a.n) __stcs(drow + c0 + cc, dv[cc]);
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_THREADS) : "memory");
       }
+      if (a.dbg) {
+        e_wait += ec1 - ec0;
+        e_p1 += ec2 - ec1;
+        e_p2 += clock64() - ec2;
+      }
+    }
+    if (a.dbg && threadIdx.x == 64) {
+      a.dbg[8 * blockIdx.x + 3] = (unsigned long long)e_p1;
+      a.dbg[8 * blockIdx.x + 4] = (unsigned long long)e_p2;
+      a.dbg[8 * blockIdx.x + 5] = (unsigned long long)e_wait;
     }
   }
   tc::fence_before();
@@ -452,7 +577,7 @@ namespace {
 
 int oz_encode(CUtensorMap* m, const uint8_t* ptr, int64_t rows, int64_t cols, int box_rows) {
   return encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ptr, rows, cols, box_rows, OKB,
-                           CU_TENSOR_MAP_SWIZZLE_64B);
+                           CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 int oz_alloc(const scedar_cells* c, int S, cudaStream_t s, OzState** out) {
@@ -565,7 +690,19 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
   a.tiles = o->tiles;
   a.n_tiles = (int)o->host_tiles.size();
   if (a.n_tiles == 0) return SCEDAR_OK;
-  const int grid = std::min(a.n_tiles, num_sms());
+  Scratch dbg;
+  const bool debug = getenv("SCEDAR_B200_OZ_DEBUG") != nullptr;
+  a.dbg = nullptr;
+  if (debug) {
+    SCEDAR_CHECK(dbg.alloc(sizeof(unsigned long long) * 8 * num_sms(), s));
+    SCEDAR_CUDA(cudaMemsetAsync(dbg.ptr, 0, sizeof(unsigned long long) * 8 * num_sms(), s));
+    a.dbg = dbg.as<unsigned long long>();
+  }
+  a.vec_ok = a.ldd % 4 == 0;
+  for (int r = 0; r < a.world; ++r)
+    if (reinterpret_cast<uintptr_t>(a.stripe_ptr[r]) % 32 != 0) a.vec_ok = 0;
+  int grid = std::min(a.n_tiles, num_sms());
+  if (const char* e = getenv("SCEDAR_B200_OZ_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
   if (o->S == 6) {
     SCEDAR_CUDA(cudaFuncSetAttribute(gram_oz_kernel<6>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, oz_smem(6)));
@@ -577,6 +714,23 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
   }
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
+  if (debug) {
+    std::vector<unsigned long long> h(8 * (size_t)grid);
+    SCEDAR_CUDA(cudaMemcpyAsync(h.data(), dbg.ptr, sizeof(unsigned long long) * h.size(),
+                                cudaMemcpyDeviceToHost, s));
+    SCEDAR_CUDA(cudaStreamSynchronize(s));
+    double sum[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int q = 0; q < 8; ++q) sum[q] += (double)h[8 * b + q];
+    const double tiles = sum[7] > 0 ? sum[7] : 1;
+    fprintf(stderr,
+            "oz debug: S=%d tiles/CTA %.1f | per tile cycles: total %.0f, MMA warp waits: "
+            "tempty %.0f full %.0f | epilogue: wait tfull %.0f phase1 %.0f phase2 %.0f | "
+            "ideal MMA %.0f\n",
+            o->S, tiles / grid, sum[2] / tiles, sum[0] / tiles, sum[1] / tiles, sum[5] / tiles,
+            sum[3] / tiles, sum[4] / tiles,
+            (double)a.kslabs * (OKB / 32) * (o->S * (o->S + 1) / 2) * 32.0);
+  }
   return SCEDAR_OK;
 }
 

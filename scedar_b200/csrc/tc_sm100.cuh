@@ -25,6 +25,18 @@ __device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr) {
   return d;
 }
 
+// The same for 128B-swizzled tiles: rows of 128 bytes, 8-row atoms 1024 bytes
+// apart.  A K step of 32 bytes inside the row advances the start address by 32.
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+
 // instruction descriptor of kind::i8: D = S32, A and B unsigned 8-bit, both
 // K-major, M = 128 (cta_group::1)
 __host__ __device__ constexpr uint32_t idesc_u8(int n) {

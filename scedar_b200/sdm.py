@@ -396,8 +396,10 @@ class SampleDistanceMatrix(object):
 
     # ------------------------------------------------------ sorted columns
     def _col_sort(self, want_sorted, want_arg):
-        if self._use_pdist and not self._on_b200_path(self._metric):
-            self._d                      # the reference's route fills the slot
+        if self._use_pdist:
+            # np.sort(self._d, ...) (sdm.py:1293, 1302): the reference fills
+            # _lazy_load_d on the way, and to_classified hands that slot on
+            self._d
         self._validate_pdist()
         n = self._x.shape[0]
         srt = np.empty((n, n), dtype=np.float64) if want_sorted else None
