@@ -95,6 +95,8 @@ def host_threads():
     """Pin the BLAS pools to all host cores and describe them."""
     info = []
     try:
+        import numpy  # noqa: F401  (loads the BLAS the pools belong to)
+        import scipy.linalg  # noqa: F401
         import threadpoolctl
         threadpoolctl.threadpool_limits(limits=os.cpu_count())
         info = [{k: d.get(k) for k in ("user_api", "internal_api",

@@ -69,8 +69,6 @@ class RareSampleDetection(object):
         sdm._check_metric(metric)
         x = sdm._x.toarray() if spsp.issparse(sdm._x) else sdm._x
         x_dev = dev.to_device(np.ascontiguousarray(x, dtype=np.float64))
-        precision = getattr(sdm, "precision", "fp64")
-
         def kth_nn(xd):
             """Distance to the k-th neighbour of every cell: tensor [m, 1]."""
             m = xd.shape[0]
@@ -86,8 +84,9 @@ class RareSampleDetection(object):
                                                     m, k)
                     return dev.to_device(
                         np.ascontiguousarray(dist[:, k - 1:k]))
-                _, dist = cells.knn_stripe(k, EXCLUDE_SELF,
-                                           precision=precision)
+                _, dist = cells.knn_stripe(
+                    k, EXCLUDE_SELF,
+                    precision=sdm._gram_precision(m, xd.shape[1]))
             finally:
                 cells.close()
             return dist[:, k - 1:k].contiguous()

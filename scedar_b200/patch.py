@@ -22,6 +22,7 @@ SDM_HOOKS = (
     "_validate_pdist", "_check_metric", "_cells", "_device_d", "_d_stripes",
     "_col_sort", "_knn_from_pdist", "release_device", "_is_sparse",
     "d_block", "_condensed_d", "_ref_hook", "_knn_by_full_sort", "_stripes_of",
+    "_gram_precision",
 )
 SDM_STATIC_HOOKS = (
     "cosine_pdist", "correlation_pdist", "num_correct_dist_mat", "_static_pdist",
@@ -54,6 +55,8 @@ def install_sdm(cls):
         setattr(cls, name, staticmethod(getattr(fast, name)))
     if not hasattr(cls, "precision"):
         cls.precision = fast.precision
+    cls.I8_MIN_CELLS = fast.I8_MIN_CELLS
+    cls.I8_MAX_FEATURES = fast.I8_MAX_FEATURES
     if not hasattr(cls, "_pca_x"):
         cls._pca_x = fast.__dict__["_pca_x"]
 

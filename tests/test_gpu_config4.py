@@ -104,7 +104,7 @@ def check_knn(idx_rows, got_rows, c4):
     assert np.array_equal(own, idx_rows)
 
 
-@pytest.mark.parametrize("precision", ["fp64", "fp64_i8"])
+@pytest.mark.parametrize("precision", ["fp64_dmma", "fp64_i8"])
 def test_config4_through_the_dropin(b200, c4, precision):
     """SampleDistanceMatrix(x, metric='correlation'): D resident in HBM
     (whole-matrix form of the kernel), then s_knn_ind_lut(15)."""
