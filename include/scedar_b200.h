@@ -201,6 +201,31 @@ int scedar_pdist_symmetric(const scedar_cells_t* cells, int precision,
                            double* d_out, int64_t ldd, void* stream);
 
 /* ------------------------------------------------------------------------
+ * PCA / truncated-SVD producer of the kNN path (scedar/eda/sdm.py:1313-1334,
+ * sklearn PCA(svd_solver="auto", random_state=17) / TruncatedSVD): the n^2- and
+ * n p^2-sized pieces.  The p x p (or n x n) symmetric eigenproblem in between
+ * is the caller's (cuSOLVER through torch in scedar_b200/pca.py).
+ * ---------------------------------------------------------------------- */
+/* mean of every column over the real rows of the working copy: mean_out [p] */
+int scedar_cells_col_means(const scedar_cells_t* cells, double* mean_out,
+                           void* stream);
+/* working copy -= shift[column] (column centring), in place */
+int scedar_cells_shift_cols(scedar_cells_t* cells, const double* shift,
+                            void* stream);
+/* new handle holding the transposed working copy (rows = features, columns =
+ * samples), optionally minus shift[feature]; metric as given (no statistic) */
+int scedar_cells_transposed(const scedar_cells_t* cells, const double* shift,
+                            void* stream, scedar_cells_t** out);
+/* bare Gram matrix of the prepared rows, out [n, n] (for transposed cells: the
+ * scatter matrix XtX), FP64 tensor-core kernel, lower tiles mirrored */
+int scedar_gram_raw(const scedar_cells_t* cells, double* out, int64_t ldd,
+                    void* stream);
+/* bare cross products A.Bt of two handles with the same column count:
+ * out [n_a, n_b] */
+int scedar_gram_raw_cross(const scedar_cells_t* a, const scedar_cells_t* b,
+                          double* out, int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------
  * k nearest neighbours of rows [row_begin, row_end) without materialising D:
  * Gram tile -> metric epilogue -> streaming top-(k+1) per row, ordered by
  * (distance, index) -- the order of np.argsort(kind="mergesort")

@@ -39,6 +39,13 @@ SIGNATURES = {
                                         c_int64, c_void_p]),
     "scedar_pdist_lower_rows_prec": (c_int, [c_void_p, c_int, c_int64, c_int64,
                                              c_void_p, c_int64, c_void_p]),
+    "scedar_cells_col_means": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "scedar_cells_shift_cols": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "scedar_cells_transposed": (c_int, [c_void_p, c_void_p, c_void_p,
+                                        POINTER(c_void_p)]),
+    "scedar_gram_raw": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "scedar_gram_raw_cross": (c_int, [c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p]),
     "scedar_cells_free": (c_int, [c_void_p]),
     "scedar_cells_n": (c_int64, [c_void_p]),
     "scedar_cells_p": (c_int64, [c_void_p]),

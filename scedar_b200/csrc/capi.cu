@@ -377,6 +377,50 @@ int scedar_pdist_stripe_p2p(const scedar_cells_t* c, int precision, int rank, in
                                 static_cast<cudaStream_t>(stream));
 }
 
+// ---- PCA producer pieces ------------------------------------------------------
+int scedar_cells_col_means(const scedar_cells_t* c, double* mean_out, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (c->p > 0 && !mean_out) return fail(SCEDAR_ERR_ARG, "mean_out is NULL");
+  return launch_col_means(c, mean_out, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_cells_shift_cols(scedar_cells_t* c, const double* shift, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (c->p > 0 && !shift) return fail(SCEDAR_ERR_ARG, "shift is NULL");
+  return launch_shift_cols(c, shift, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_cells_transposed(const scedar_cells_t* c, const double* shift, void* stream,
+                            scedar_cells_t** out) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SCEDAR_CHECK(new_cells(c->p, c->n, c->metric, s, out));
+  int rc = launch_transpose_cells(c, shift, *out, s);
+  if (rc != SCEDAR_OK) {
+    scedar_cells_free(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int scedar_gram_raw(const scedar_cells_t* c, double* out, int64_t ldd, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (c->n == 0) return SCEDAR_OK;
+  if (!out) return fail(SCEDAR_ERR_ARG, "out is NULL");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  return launch_gram_raw_symmetric(c, out, ldd, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_gram_raw_cross(const scedar_cells_t* a, const scedar_cells_t* b, double* out,
+                          int64_t ldd, void* stream) {
+  if (!a || !b) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (a->p != b->p) return fail(SCEDAR_ERR_ARG, "operands differ in their column count");
+  if (a->n == 0 || b->n == 0) return SCEDAR_OK;
+  if (!out) return fail(SCEDAR_ERR_ARG, "out is NULL");
+  if (ldd < b->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= the row count of b");
+  return launch_gram_raw_cross(a, b, out, ldd, static_cast<cudaStream_t>(stream));
+}
+
 // ---- peer-mapped stripes (one process per GPU, same node) ------------------
 int scedar_stripe_alloc(size_t bytes, void** dev_ptr) {
   if (!dev_ptr) return fail(SCEDAR_ERR_ARG, "dev_ptr is NULL");

@@ -99,6 +99,14 @@ int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,
 int launch_gram_gathered(const scedar_cells* c, const double* g, const int64_t* row_ids,
                          int64_t m, int64_t m_pad, double* d_out, int64_t ldd,
                          cudaStream_t s);
+int launch_gram_raw_symmetric(const scedar_cells* c, double* out, int64_t ldd, cudaStream_t s);
+int launch_gram_raw_cross(const scedar_cells* ca, const scedar_cells* cb, double* out,
+                          int64_t ldd, cudaStream_t s);
+// pca.cu (column means, column shift, transposed working copy)
+int launch_col_means(const scedar_cells* c, double* mean_out, cudaStream_t s);
+int launch_shift_cols(scedar_cells* c, const double* shift, cudaStream_t s);
+int launch_transpose_cells(const scedar_cells* c, const double* shift, scedar_cells* out,
+                           cudaStream_t s);
 // fused Gram -> top-K; part_d/part_i: [splits, rows, K] partial lists
 int gram_topk_splits(const scedar_cells* c, int64_t rows);
 int launch_gram_topk(const scedar_cells* c, int64_t row_begin, int64_t row_end,

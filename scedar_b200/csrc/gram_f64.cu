@@ -57,7 +57,7 @@ constexpr int GROUP_ROWS = 16;  // row tiles per L2 swizzle group (32 MB of row 
                                 // 32 tiles thrash L2: 160 GB of DRAM reads instead of 65 at n = 100k)
 constexpr int kMaxPeers = 16;
 
-enum Mode { MODE_STORE = 0, MODE_DIAG = 2, MODE_TOPK = 3 };
+enum Mode { MODE_STORE = 0, MODE_DIAG = 2, MODE_TOPK = 3, MODE_RAW = 4 };  // RAW: STORE of the bare dot products
 
 struct GramArgs {
   const double* xw;
@@ -355,7 +355,7 @@ gram_f64_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant_
           a.out[i0 + tid] = sv;
         }
       } else {
-        tile_to_smem<false>(acc, smem, a.stat, i0, j0, a.euclid, a.row_ids);
+        tile_to_smem<MODE == MODE_RAW>(acc, smem, a.stat, i0, j0, a.euclid, a.row_ids);
         consumer_sync();
         if (MODE == MODE_TOPK) {
           // warp w scans rows w, w+8, ...; lane l holds entry l of the row's list
@@ -565,6 +565,41 @@ int launch_gram_gathered(const scedar_cells* c, const double* g, const int64_t* 
   const int64_t tiles = RT * (c->n_pad / BN);
   if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "too many rows for one launch");
   return launch<MODE_STORE>(c, a, dim3((unsigned)tiles), s, &gmap);
+}
+
+// Bare Gram matrix X.Xt of the prepared rows [n, n] (no metric epilogue): lower
+// tiles contracted once and mirrored.  The PCA producer calls it on the
+// transposed cells (features x samples), where it is the scatter matrix XtX.
+int launch_gram_raw_symmetric(const scedar_cells* c, double* out, int64_t ldd, cudaStream_t s) {
+  if (c->n <= 0) return SCEDAR_OK;
+  GramArgs a = base_args(c);
+  a.row_begin = 0;
+  a.row_end = c->n;
+  a.out = out;
+  a.ldd = ldd;
+  a.mirror = 1;
+  const int64_t RT = (c->n + BM - 1) / BM;
+  const int64_t tiles = RT * (c->n_pad / BN);
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "matrix too large for one launch");
+  return launch<MODE_RAW>(c, a, dim3((unsigned)tiles), s);
+}
+
+// Bare cross products A.Bt: the rows of `ca` (its working copy, all n_a of them)
+// against the rows of `cb`; out [n_a, n_b].  Both must have the same number of
+// columns.  Tall-skinny use: n_b <= a few hundred (the projection on principal axes).
+int launch_gram_raw_cross(const scedar_cells* ca, const scedar_cells* cb, double* out,
+                          int64_t ldd, cudaStream_t s) {
+  if (ca->n <= 0 || cb->n <= 0) return SCEDAR_OK;
+  if (ca->p_pad != cb->p_pad) return fail(SCEDAR_ERR_ARG, "operands differ in their column count");
+  GramArgs a = base_args(cb);
+  a.row_begin = 0;
+  a.row_end = ca->n;
+  a.out = out;
+  a.ldd = ldd;
+  const int64_t RT = (ca->n + BM - 1) / BM;
+  const int64_t tiles = RT * (cb->n_pad / BN);
+  if (tiles > 0x7fffffffLL) return fail(SCEDAR_ERR_UNSUPPORTED, "too many rows for one launch");
+  return launch<MODE_RAW>(cb, a, dim3((unsigned)tiles), s, &ca->xmap);
 }
 
 int launch_gram_symmetric(const scedar_cells* c, double* d_out, int64_t ldd,

@@ -171,6 +171,53 @@ class Cells(object):
             out.stride(0) if self.n > 1 else self.n, _stream()))
         return out
 
+    # -- PCA producer pieces --------------------------
+    def col_means(self):
+        """Mean of every column of the working copy over the real rows."""
+        out = torch.empty(self.p, dtype=torch.float64, device="cuda")
+        _capi.check(_capi.load().scedar_cells_col_means(
+            self._h, _ptr(out), _stream()))
+        return out
+
+    def shift_cols(self, shift):
+        """working copy -= shift[column], in place (column centring)."""
+        shift = _f64(shift).contiguous()
+        assert shift.numel() == self.p
+        _capi.check(_capi.load().scedar_cells_shift_cols(
+            self._h, _ptr(shift), _stream()))
+
+    def transposed(self, shift=None):
+        """New handle over the transposed working copy (rows = features),
+        optionally minus ``shift[feature]``."""
+        if shift is not None:
+            shift = _f64(shift).contiguous()
+            assert shift.numel() == self.p
+        h = ctypes.c_void_p()
+        _capi.check(_capi.load().scedar_cells_transposed(
+            self._h, _ptr(shift), _stream(), ctypes.byref(h)))
+        torch.cuda.current_stream().synchronize()   # shift may now be freed
+        return Cells(h, self.p, self.n, self.metric)
+
+    def gram_raw(self, out=None):
+        """Bare Gram matrix of the prepared rows [n, n] (FP64 tensor cores)."""
+        if out is None:
+            out = torch.empty((self.n, self.n), dtype=torch.float64,
+                              device="cuda")
+        _capi.check(_capi.load().scedar_gram_raw(
+            self._h, _ptr(out), out.stride(0) if self.n > 1 else self.n,
+            _stream()))
+        return out
+
+    def gram_raw_cross(self, other, out=None):
+        """self.rows . other.rows^T -> [self.n, other.n]."""
+        if out is None:
+            out = torch.empty((self.n, other.n), dtype=torch.float64,
+                              device="cuda")
+        _capi.check(_capi.load().scedar_gram_raw_cross(
+            self._h, other._h, _ptr(out),
+            out.stride(0) if self.n > 1 else other.n, _stream()))
+        return out
+
     # -- kNN without D ------------------------------------------------------
     def knn_stripe(self, k, exclude=EXCLUDE_SELF, row_begin=0, row_end=None,
                    precision="fp64"):

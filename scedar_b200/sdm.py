@@ -184,6 +184,13 @@ class SampleDistanceMatrix(object):
             selected_s_inds = slice(None, None)
         if selected_f_inds is None:
             selected_f_inds = slice(None, None)
+        for sel in (selected_s_inds, selected_f_inds):
+            # NumPy's rule for a dense x (IndexError); scipy.sparse answers a
+            # non-integer index with whatever its version happens to raise
+            if not isinstance(sel, slice) and \
+                    np.asarray(sel).dtype.kind not in "iub":
+                raise IndexError("only integers, slices and integer or "
+                                 "boolean arrays are valid indices")
         sub_d = None
         if self._use_pdist:
             sub_d = self.d_block(selected_s_inds, selected_s_inds)
