@@ -132,6 +132,30 @@ def main():
     dist.barrier()
     del gx, gidc
     sdm.close()
+    # ---- the same D with the INT8 split kernel: every tile pair computed by one
+    # rank and stored into both owners' stripes (own HBM or the peer's over
+    # NVLink), against the single-GPU matrix of the same kernel, bit for bit
+    xb = torch.empty((n, p), dtype=torch.float64, device=device)
+    if rank == 0:
+        xb.copy_(x)
+    dist.broadcast(xb, src=0)
+    for prec in ("fp64_i8", "fp64_i8s6"):
+        s8 = StripedDistanceMatrix(xb, "euclidean", shape=(n, p), device=device,
+                                   broadcast=False, precision=prec)
+        peers.tensor(rank).fill_(-3.0)
+        for _ in range(2):
+            _, t_d = timed(lambda: s8.compute_d(peers=peers))
+        out["d_p2p_{}_ms".format(prec)] = round(t_d, 2)
+        cells = dev.Cells.from_dense(xb, "euclidean")
+        d1 = cells.pdist_symmetric(precision=prec)
+        mine = peers.tensor(rank)
+        same = bool(torch.equal(d1[s8.row_begin:s8.row_end], mine))
+        cells.close()
+        flag = torch.tensor([1.0 if same else 0.0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert float(flag.item()) == 1.0, "peer-store D ({}) differs".format(prec)
+        del d1
+        s8.close()
     peers.close()
     if rank == 0:
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
