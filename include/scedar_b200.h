@@ -58,8 +58,8 @@ enum {
                                 on the INT8 tensor pipe (tcgen05 kind::i8, 7
                                 byte slices, exact INT32 accumulation, float64
                                 epilogue): <=1e-10 rel like FP64, dot products
-                                of integer data exact.  n_features <= 4096,
-                                otherwise the DMMA path runs                  */
+                                of integer data exact; rows longer than 4096
+                                features are contracted in K chunks           */
   SCEDAR_PRECISION_FP64_I8S6 = 3  /* the same with 6 slices (21 instead of 28
                                 products): |dD| <= 1e-11 of max|x|^2-scaled
                                 products, see gram_oz.cu                      */

@@ -91,7 +91,10 @@ static_assert(oz_smem(6) <= 227 * 1024 && oz_smem(7) <= 227 * 1024, "shared memo
 constexpr int OZ_EPI_WARPS = 8;
 constexpr int OZ_EPI_THREADS = 32 * OZ_EPI_WARPS;
 constexpr int OZ_THREADS = 64 + OZ_EPI_THREADS;
-constexpr int OZ_KMAX = 4096;      // K columns: 7 * 255^2 * 4096 < 2^31
+constexpr int OZ_KCHUNK = 4096;    // K columns accumulated in INT32 at a time: 7 * 255^2 * 4096
+                                   // < 2^31; longer rows are contracted chunk by chunk, the
+                                   // float64 chunk values summed in the epilogue's registers
+constexpr int OZ_CHUNK_SLABS = OZ_KCHUNK / OKB;
 constexpr int kOzPeers = 16;
 constexpr int TILE_DIRECT = 1, TILE_MIRROR = 2;
 
@@ -103,10 +106,12 @@ struct OzTile {
 
 struct OzArgs {
   const double* sc;        // 2^(e_i - 15)
-  const long long* hi;     // offset corrections of the two halves of the weighted sum
-  const long long* lo;
+  const long long* hi;     // offset corrections of the two halves of the weighted sum,
+  const long long* lo;     // [row][chunk]
+  int n_chunks;            // K chunks of <= 4096 columns
+  long long c0_last;       // c0 of the last (possibly shorter) chunk
   const double* stat;      // sqrt(1/P_ii) (0 for zero rows) or P_ii, from the same integers
-  long long c0;            // 2^14 K << 16: the offset x offset term of diagonal 0
+  long long c0;            // 2^14 K_chunk << 16: the offset x offset term of diagonal 0
   int64_t n, n_pl;         // cells; rows per slice plane
   int64_t row_lo, row_hi;  // rows of D this launch may store
   int kslabs;
@@ -160,74 +165,85 @@ oz_slice_kernel(const double* __restrict__ xw, int64_t n, int64_t p, int64_t p_p
   for (int w = 1; w < 8; ++w) m = fmax(m, smax[w]);
   int e = 0;
   if (m > 0.0) frexp(m, &e);   // m = f 2^e, f in [0.5, 1): |x| < 2^e
-  long long R[S], dg[S];
+  const int n_chunks = (int)((p_oz + OZ_KCHUNK - 1) / OZ_KCHUNK);
+  const double sci = scalbn(1.0, e - 15);
+  double p_ii = 0.0;   // thread 0: sum of the chunk values (same order as the tile epilogue)
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int64_t k_begin = (int64_t)ch * OZ_KCHUNK;
+    const int64_t k_end = k_begin + OZ_KCHUNK < p_oz ? k_begin + OZ_KCHUNK : p_oz;
+    long long R[S], dg[S];
 #pragma unroll
-  for (int s = 0; s < S; ++s) R[s] = dg[s] = 0;
-  for (int64_t k4 = (int64_t)tid * 4; k4 < p_oz; k4 += 1024) {
-    uint32_t pack[S];
+    for (int s = 0; s < S; ++s) R[s] = dg[s] = 0;
+    for (int64_t k4 = k_begin + (int64_t)tid * 4; k4 < k_end; k4 += 1024) {
+      uint32_t pack[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) pack[s] = 0;
+      for (int s = 0; s < S; ++s) pack[s] = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t k = k4 + u;
-      const double x = (real && k < p) ? xr[k] : 0.0;
-      const long long q = __double2ll_rd(scalbn(x, F - e));
-      int dgt[S];
-      const int top = (int)(q >> (8 * (S - 1)));   // [-128, 127]
-      dgt[0] = top + 128;
-      R[0] += top;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t k = k4 + u;
+        const double x = (real && k < p) ? xr[k] : 0.0;
+        const long long q = __double2ll_rd(scalbn(x, F - e));
+        int dgt[S];
+        const int top = (int)(q >> (8 * (S - 1)));   // [-128, 127]
+        dgt[0] = top + 128;
+        R[0] += top;
 #pragma unroll
-      for (int s = 1; s < S; ++s) {
-        dgt[s] = (int)((q >> (8 * (S - 1 - s))) & 255);
-        R[s] += dgt[s];
+        for (int s = 1; s < S; ++s) {
+          dgt[s] = (int)((q >> (8 * (S - 1 - s))) & 255);
+          R[s] += dgt[s];
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) pack[s] |= (uint32_t)dgt[s] << (8 * u);
+        // what the tensor core accumulates for the pair (row, row)
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int t = 0; s + t < S; ++t) dg[s + t] += (long long)(dgt[s] * dgt[t]);
       }
-#pragma unroll
-      for (int s = 0; s < S; ++s) pack[s] |= (uint32_t)dgt[s] << (8 * u);
-      // what the tensor core accumulates for the pair (row, row)
 #pragma unroll
       for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int t = 0; s + t < S; ++t) dg[s + t] += (long long)(dgt[s] * dgt[t]);
+        *reinterpret_cast<uint32_t*>(planes + ((int64_t)s * n_pl + row) * p_oz + k4) = pack[s];
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-      *reinterpret_cast<uint32_t*>(planes + ((int64_t)s * n_pl + row) * p_oz + k4) = pack[s];
-  }
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    for (int o = 16; o > 0; o >>= 1) {
-      R[s] += __shfl_xor_sync(0xffffffffu, R[s], o);
-      dg[s] += __shfl_xor_sync(0xffffffffu, dg[s], o);
-    }
-    if (lane == 0) {
-      sred[warp][s] = R[s];
-      sred[warp][S + s] = dg[s];
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t acc[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      long long r = 0, g = 0;
-      for (int w = 0; w < 8; ++w) {
-        r += sred[w][s];
-        g += sred[w][S + s];
+      for (int o = 16; o > 0; o >>= 1) {
+        R[s] += __shfl_xor_sync(0xffffffffu, R[s], o);
+        dg[s] += __shfl_xor_sync(0xffffffffu, dg[s], o);
       }
-      R[s] = r;
-      acc[s] = (uint32_t)g;
+      if (lane == 0) {
+        sred[warp][s] = R[s];
+        sred[warp][S + s] = dg[s];
+      }
     }
-    const long long hi_i = 128 * ((R[0] << 16) + (R[1] << 8) + R[2]);
-    long long lo_i = 0;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t acc[S];
 #pragma unroll
-    for (int d = 3; d < S; ++d) lo_i = (lo_i << 8) + R[d];
-    lo_i *= 128;
-    const double sci = scalbn(1.0, e - 15);
+      for (int s = 0; s < S; ++s) {
+        long long r = 0, g = 0;
+        for (int w = 0; w < 8; ++w) {
+          r += sred[w][s];
+          g += sred[w][S + s];
+        }
+        R[s] = r;
+        acc[s] = (uint32_t)g;
+      }
+      const long long hi_i = 128 * ((R[0] << 16) + (R[1] << 8) + R[2]);
+      long long lo_i = 0;
+#pragma unroll
+      for (int d = 3; d < S; ++d) lo_i = (lo_i << 8) + R[d];
+      lo_i *= 128;
+      hi[row * n_chunks + ch] = hi_i;
+      lo[row * n_chunks + ch] = lo_i;
+      const long long c0c = ((long long)16384 * (k_end - k_begin)) << 16;
+      const double v = oz_value<S>(acc, 2 * hi_i + c0c, 2 * lo_i);
+      p_ii = ch == 0 ? v : __dadd_rn(p_ii, v);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
     sc[row] = sci;
-    hi[row] = hi_i;
-    lo[row] = lo_i;
-    const double v = oz_value<S>(acc, 2 * hi_i + c0, 2 * lo_i);
-    const double P = __dmul_rn(v, __dmul_rn(sci, sci));
+    const double P = __dmul_rn(p_ii, __dmul_rn(sci, sci));
     double sv = 0.0;
     if (real) sv = euclid ? P : __dsqrt_rn(P != 0.0 ? __ddiv_rn(1.0, P) : 0.0);
     stat[row] = sv;
@@ -341,12 +357,17 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t it = 0, tcount = 0;
     long long w_tempty = 0, w_full = 0;
     const long long t_begin = clock64();
-    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tcount) {
-      long long c0 = a.dbg ? clock64() : 0;
-      mbar_wait(tempty, (tcount & 1) ^ 1);   // the epilogue has drained the accumulators
-      if (a.dbg) w_tempty += clock64() - c0;
-      tc::fence_after();
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
       for (int ks = 0; ks < KS; ++ks, ++it) {
+        const int kc = ks % OZ_CHUNK_SLABS;    // slab inside its K chunk
+        long long c0 = 0;
+        if (kc == 0) {
+          // a new chunk (or tile): the epilogue has drained the accumulators
+          c0 = a.dbg ? clock64() : 0;
+          mbar_wait(tempty, (tcount & 1) ^ 1);
+          if (a.dbg) w_tempty += clock64() - c0;
+          tc::fence_after();
+        }
         const uint32_t buf = it & 1;
         c0 = a.dbg ? clock64() : 0;
         mbar_wait(full_b + 8 * buf, (it >> 1) & 1);
@@ -363,16 +384,15 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int kk = 0; kk < OKB / 32; ++kk) {
             // slice sl of the row tile x slices [0, S - sl) of the column tile in one
             // instruction (N = 64 m <= 256) or two.  An instruction costs
-            // max(N / 2, ~100) cycles -- the 4 KB row operand is read from shared
-            // memory at ~41 B/cycle whatever N is (measured: the S = 6 and S = 7
-            // tile times fit this model to 2 %) -- so a run of 5 or 6 slices is cut
-            // into two instructions of <= 192 columns (100 + 100 cycles), not 256 +
-            // a short one (128 + 100).  Slice 0 goes first in a tile: it covers
-            // every diagonal, so its first K step zero-initialises them.
+            // ~128 cycles for m = 3, 4 and ~96 for m = 1, 2 (ideal 32 m): the
+            // 128 x 32-byte row operand is re-read from shared memory by every
+            // instruction (measured: the S = 6 and S = 7 tile times fit this
+            // model to 2 %).  Slice 0 goes first in a chunk: it covers every
+            // diagonal, so its first K step zero-initialises them.
             constexpr int kFullRun = 4;
             const int run = S - sl;
             const int first = run <= kFullRun ? run : (run + 1) / 2;
-            const uint32_t acc = (ks | kk | sl) != 0;
+            const uint32_t acc = (kc | kk | sl) != 0;
             if (el) {
               tc::mma_i8(tmem_base + (uint32_t)(sl * ON), da + (uint64_t)((kk * 32) >> 4),
                          db + (uint64_t)((kk * 32) >> 4), tc::idesc_u8(ON * first), acc);
@@ -388,9 +408,12 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (el) tc::commit(empty_b + 8 * buf);
         __syncwarp();
+        if (kc == OZ_CHUNK_SLABS - 1 || ks == KS - 1) {
+          if (el) tc::commit(tfull);            // this chunk's accumulators are complete
+          __syncwarp();
+          ++tcount;
+        }
       }
-      if (el) tc::commit(tfull);              // accumulators complete
-      __syncwarp();
     }
     if (a.dbg && lane == 0) {
       a.dbg[8 * blockIdx.x + 0] = (unsigned long long)w_tempty;
@@ -406,18 +429,15 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tcount = 0;
     long long e_wait = 0, e_p1 = 0, e_p2 = 0;
-    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tcount) {
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
       const OzTile tl = a.tiles[t];
       const int64_t i0 = (int64_t)tl.I * OM, j0 = (int64_t)tl.J * ON;
       const int64_t gi = i0 + r;
       const bool row_ok = gi < a.n;
       double sci = 0.0, sti = 0.0;
-      long long hii = 0, loi = 0;
       if (row_ok) {
         sci = __ldg(a.sc + gi);
         sti = __ldg(a.stat + gi);
-        hii = __ldg(a.hi + gi);
-        loi = __ldg(a.lo + gi);
       }
       // output stripes of the tile's rows and of its (mirrored) columns
       int od = 0, om = 0;
@@ -431,55 +451,62 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool direct = (tl.flags & TILE_DIRECT) && gi >= a.row_lo && gi < a.row_hi;
       const bool mirror = (tl.flags & TILE_MIRROR) && row_ok;
 
-      long long ec0 = a.dbg ? clock64() : 0;
-      mbar_wait(tfull, tcount & 1);
-      long long ec1 = a.dbg ? clock64() : 0;
-      tc::fence_after();
-      // phase 1: drain the accumulators into raw dot products held in registers
-      // (32 per thread), four columns at a time, the next four in flight while
-      // these are combined; then hand TMEM back so the next tile's MMAs run
-      // under phase 2
+      // phase 1, once per K chunk: drain the accumulators into raw dot products
+      // held in registers (32 per thread), four columns at a time, the next four
+      // in flight while these are combined; then hand TMEM back so the next
+      // chunk's / tile's MMAs run under the rest
       double pv[32];
-      uint32_t va[S][4], vb[S][4];
-      auto drain = [&](uint32_t (&v)[S][4], int c0) {
+      long long ec0 = 0, ec1 = 0;
+      for (int ch = 0; ch < a.n_chunks; ++ch, ++tcount) {
+        ec0 = a.dbg ? clock64() : 0;
+        mbar_wait(tfull, tcount & 1);
+        ec1 = a.dbg ? clock64() : 0;
+        if (a.dbg) e_wait += ec1 - ec0;
+        tc::fence_after();
+        const long long c0c = ch == a.n_chunks - 1 ? a.c0_last : a.c0;
+        const long long hic = row_ok ? __ldg(a.hi + gi * a.n_chunks + ch) : 0;
+        const long long loc = row_ok ? __ldg(a.lo + gi * a.n_chunks + ch) : 0;
+        uint32_t va[S][4], vb[S][4];
+        auto drain = [&](uint32_t (&v)[S][4], int c0) {
 #pragma unroll
-        for (int d = 0; d < S; ++d)
-          tc::tmem_ld4_async(lane_base + (uint32_t)(d * ON + h * 32 + c0), v[d]);
-      };
-      auto settle = [&](uint32_t (&v)[S][4]) {
+          for (int d = 0; d < S; ++d)
+            tc::tmem_ld4_async(lane_base + (uint32_t)(d * ON + h * 32 + c0), v[d]);
+        };
+        auto settle = [&](uint32_t (&v)[S][4]) {
 #pragma unroll
-        for (int d = 0; d < S; ++d) tc::tmem_wait4(v[d]);
-      };
-      auto combine = [&](const uint32_t (&v)[S][4], int c0) {
+          for (int d = 0; d < S; ++d) tc::tmem_wait4(v[d]);
+        };
+        auto combine = [&](const uint32_t (&v)[S][4], int c0) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int64_t gj = j0 + h * 32 + c0 + cc;
-          double P = 0.0;
-          if (gj < a.n) {
-            uint32_t acc[S];
+          for (int cc = 0; cc < 4; ++cc) {
+            const int64_t gj = j0 + h * 32 + c0 + cc;
+            double val = 0.0;
+            if (gj < a.n) {
+              uint32_t acc[S];
 #pragma unroll
-            for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
-            const double val = oz_value<S>(acc, hii + __ldg(a.hi + gj) + a.c0,
-                                           loi + __ldg(a.lo + gj));
-            P = __dmul_rn(val, __dmul_rn(sci, __ldg(a.sc + gj)));
+              for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
+              val = oz_value<S>(acc, hic + __ldg(a.hi + gj * a.n_chunks + ch) + c0c,
+                                loc + __ldg(a.lo + gj * a.n_chunks + ch));
+            }
+            pv[c0 + cc] = ch == 0 ? val : __dadd_rn(pv[c0 + cc], val);
           }
-          pv[c0 + cc] = P;
-        }
-      };
-      drain(va, 0);
-      settle(va);
+        };
+        drain(va, 0);
+        settle(va);
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 8) {
-        drain(vb, c0 + 4);
-        combine(va, c0);
-        settle(vb);
-        if (c0 + 8 < 32) drain(va, c0 + 8);
-        combine(vb, c0 + 4);
-        if (c0 + 8 < 32) settle(va);
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+          drain(vb, c0 + 4);
+          combine(va, c0);
+          settle(vb);
+          if (c0 + 8 < 32) drain(va, c0 + 8);
+          combine(vb, c0 + 4);
+          if (c0 + 8 < 32) settle(va);
+        }
+        tc::fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);   // the accumulators may be overwritten
+        if (a.dbg) e_p1 += clock64() - ec1;
       }
-      tc::fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);   // the accumulators may be overwritten
       long long ec2 = a.dbg ? clock64() : 0;
       // phase 2 (under the next tile's MMAs): metric epilogue and the two stores.
       // The mirrored tile is written straight from the registers -- lanes are
@@ -495,8 +522,8 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (gj < a.n) {
             const double stj = __ldg(a.stat + gj);
             const bool lower = gi >= gj;
-            dv[cc] = finish_entry(pv[c], lower ? sti : stj, lower ? stj : sti, gi == gj,
-                                  a.euclid);
+            const double P = __dmul_rn(pv[c], __dmul_rn(sci, __ldg(a.sc + gj)));
+            dv[cc] = finish_entry(P, lower ? sti : stj, lower ? stj : sti, gi == gj, a.euclid);
             if (mirror && gj >= a.row_lo && gj < a.row_hi) __stcs(mcol + (int64_t)c * a.ldd, dv[cc]);
           }
         }
@@ -511,11 +538,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      if (a.dbg) {
-        e_wait += ec1 - ec0;
-        e_p1 += ec2 - ec1;
-        e_p2 += clock64() - ec2;
-      }
+      if (a.dbg) e_p2 += clock64() - ec2;
     }
     if (a.dbg && threadIdx.x == 64) {
       a.dbg[8 * blockIdx.x + 3] = (unsigned long long)e_p1;
@@ -547,6 +570,7 @@ struct OzState {
   long long* lo = nullptr;
   double* stat = nullptr;
   int64_t n_pl = 0, p_oz = 0;
+  int n_chunks = 1;
   bool sliced_all = false;
   OzTile* tiles = nullptr;      // device tile list (grown on demand)
   size_t tiles_cap = 0;
@@ -569,9 +593,7 @@ void oz_state_free(void* p, cudaStream_t s) {
   delete o;
 }
 
-bool oz_supported(const scedar_cells* c) {
-  return c->p > 0 && round_up(c->p, OKB) <= OZ_KMAX;
-}
+bool oz_supported(const scedar_cells* c) { return c->p > 0; }
 
 namespace {
 
@@ -592,15 +614,18 @@ int oz_alloc(const scedar_cells* c, int S, cudaStream_t s, OzState** out) {
     mc->oz = nullptr;
   }
   if (!oz_supported(c))
-    return fail(SCEDAR_ERR_UNSUPPORTED, "the INT8 split path takes 1 <= n_features <= 4096");
+    return fail(SCEDAR_ERR_UNSUPPORTED, "the INT8 split path needs at least one feature");
   o = new OzState();
   o->S = S;
   o->n_pl = c->n_pad;
   o->p_oz = round_up(c->p, OKB);
   cudaError_t e = cudaMallocAsync(&o->planes, (size_t)S * o->n_pl * o->p_oz, s);
   if (e == cudaSuccess) e = cudaMallocAsync(&o->sc, sizeof(double) * o->n_pl, s);
-  if (e == cudaSuccess) e = cudaMallocAsync(&o->hi, sizeof(long long) * o->n_pl, s);
-  if (e == cudaSuccess) e = cudaMallocAsync(&o->lo, sizeof(long long) * o->n_pl, s);
+  o->n_chunks = (int)((o->p_oz + OZ_KCHUNK - 1) / OZ_KCHUNK);
+  if (e == cudaSuccess)
+    e = cudaMallocAsync(&o->hi, sizeof(long long) * o->n_pl * o->n_chunks, s);
+  if (e == cudaSuccess)
+    e = cudaMallocAsync(&o->lo, sizeof(long long) * o->n_pl * o->n_chunks, s);
   if (e == cudaSuccess) e = cudaMallocAsync(&o->stat, sizeof(double) * o->n_pl, s);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -618,7 +643,8 @@ int oz_alloc(const scedar_cells* c, int S, cudaStream_t s, OzState** out) {
   return SCEDAR_OK;
 }
 
-long long oz_c0(const OzState* o) { return ((long long)16384 * o->p_oz) << 16; }
+// offset x offset term of diagonal 0 for a chunk of `cols` K columns
+long long oz_c0(int64_t cols) { return ((long long)16384 * cols) << 16; }
 
 // slices / scales / statistic of the cells [row_begin, row_end) (padding rows allowed)
 int oz_slice_rows(const scedar_cells* c, OzState* o, int64_t row_begin, int64_t row_end,
@@ -628,11 +654,11 @@ int oz_slice_rows(const scedar_cells* c, OzState* o, int64_t row_begin, int64_t 
   const unsigned grid = (unsigned)(row_end - row_begin);
   if (o->S == 6)
     oz_slice_kernel<6><<<grid, 256, 0, s>>>(c->xw, c->n, c->p, c->p_pad, o->p_oz, o->n_pl,
-                                            row_begin, euclid, oz_c0(o), o->planes, o->sc, o->hi,
+                                            row_begin, euclid, 0, o->planes, o->sc, o->hi,
                                             o->lo, o->stat);
   else
     oz_slice_kernel<7><<<grid, 256, 0, s>>>(c->xw, c->n, c->p, c->p_pad, o->p_oz, o->n_pl,
-                                            row_begin, euclid, oz_c0(o), o->planes, o->sc, o->hi,
+                                            row_begin, euclid, 0, o->planes, o->sc, o->hi,
                                             o->lo, o->stat);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch();
@@ -682,7 +708,9 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
   a.hi = o->hi;
   a.lo = o->lo;
   a.stat = o->stat;
-  a.c0 = oz_c0(o);
+  a.n_chunks = o->n_chunks;
+  a.c0 = oz_c0(std::min<int64_t>(o->p_oz, OZ_KCHUNK));
+  a.c0_last = oz_c0(o->p_oz - (int64_t)(o->n_chunks - 1) * OZ_KCHUNK);
   a.n = c->n;
   a.n_pl = o->n_pl;
   a.kslabs = (int)(o->p_oz / OKB);

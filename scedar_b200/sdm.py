@@ -57,7 +57,7 @@ class SampleDistanceMatrix(object):
     ``precision`` (class or instance attribute, default from the environment
     variable ``SCEDAR_B200_PRECISION``, else ``"fp64"``) selects the Gram
     kernel: ``"fp64"`` matches the reference's float64 to 1e-10 -- with the
-    DMMA kernel, or, from 4,096 cells up and at most 4,096 features, with the
+    DMMA kernel, or, from 4,096 cells up, with the
     INT8 split on the tcgen05 tensor cores (``"fp64_i8"``, 2.7 x faster, same
     bar; ``SCEDAR_B200_FP64_KERNEL=dmma|i8`` forces one; both can also be
     named directly as ``"fp64_dmma"`` / ``"fp64_i8"`` / ``"fp64_i8s6"``);
@@ -70,7 +70,7 @@ class SampleDistanceMatrix(object):
     precision = os.environ.get("SCEDAR_B200_PRECISION", "fp64")
     # "fp64" picks the INT8 split kernel from this many cells up
     I8_MIN_CELLS = 4096
-    I8_MAX_FEATURES = 4096
+    I8_MAX_FEATURES = 1 << 16
 
     def _gram_precision(self, n=None, p=None):
         """The kernel name handed to the device layer for ``self.precision``."""

@@ -119,7 +119,12 @@ if __name__ == "__main__":
     check(3000, 2000, "correlation", "log")
     check(3000, 2000, "cosine", "counts")
     check(2500, 4000, "euclidean", "log")
+    check(600, 4200, "cosine", "counts")        # two K chunks
+    check(1500, 9000, "correlation", "log")     # three K chunks
+    check(3005, 19972, "correlation", "log")    # BASELINE config 1
+    check(900, 19972, "euclidean", "counts")
     timing(20000, 2000)
+    timing(3005, 19972)
     if mode == "full":
         timing(60000, 2000)
         timing(100000, 2000)
