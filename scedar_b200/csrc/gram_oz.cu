@@ -64,6 +64,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -457,14 +458,18 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // chunk's / tile's MMAs run under the rest
       double pv[32];
       long long ec0 = 0, ec1 = 0;
-      for (int ch = 0; ch < a.n_chunks; ++ch, ++tcount) {
+      // column constants of chunk `ch`: stride n_chunks from (gj, ch)
+      const long long* __restrict__ hi_col = a.hi + (j0 + h * 32) * a.n_chunks;
+      const long long* __restrict__ lo_col = a.lo + (j0 + h * 32) * a.n_chunks;
+      auto phase1 = [&](int ch, auto first_chunk) {
+        constexpr bool kFirst = decltype(first_chunk)::value;
         ec0 = a.dbg ? clock64() : 0;
         mbar_wait(tfull, tcount & 1);
         ec1 = a.dbg ? clock64() : 0;
         if (a.dbg) e_wait += ec1 - ec0;
         tc::fence_after();
         const long long c0c = ch == a.n_chunks - 1 ? a.c0_last : a.c0;
-        const long long hic = row_ok ? __ldg(a.hi + gi * a.n_chunks + ch) : 0;
+        const long long hic = (row_ok ? __ldg(a.hi + gi * a.n_chunks + ch) : 0) + c0c;
         const long long loc = row_ok ? __ldg(a.lo + gi * a.n_chunks + ch) : 0;
         uint32_t va[S][4], vb[S][4];
         auto drain = [&](uint32_t (&v)[S][4], int c0) {
@@ -479,16 +484,16 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         auto combine = [&](const uint32_t (&v)[S][4], int c0) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            const int64_t gj = j0 + h * 32 + c0 + cc;
+            const int c = c0 + cc;
             double val = 0.0;
-            if (gj < a.n) {
+            if (j0 + h * 32 + c < a.n) {
               uint32_t acc[S];
 #pragma unroll
               for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
-              val = oz_value<S>(acc, hic + __ldg(a.hi + gj * a.n_chunks + ch) + c0c,
-                                loc + __ldg(a.lo + gj * a.n_chunks + ch));
+              val = oz_value<S>(acc, hic + __ldg(hi_col + c * a.n_chunks + ch),
+                                loc + __ldg(lo_col + c * a.n_chunks + ch));
             }
-            pv[c0 + cc] = ch == 0 ? val : __dadd_rn(pv[c0 + cc], val);
+            pv[c] = kFirst ? val : __dadd_rn(pv[c], val);
           }
         };
         drain(va, 0);
@@ -506,7 +511,10 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty);   // the accumulators may be overwritten
         if (a.dbg) e_p1 += clock64() - ec1;
-      }
+        ++tcount;
+      };
+      phase1(0, std::true_type{});
+      for (int ch = 1; ch < a.n_chunks; ++ch) phase1(ch, std::false_type{});
       long long ec2 = a.dbg ? clock64() : 0;
       // phase 2 (under the next tile's MMAs): metric epilogue and the two stores.
       // The mirrored tile is written straight from the registers -- lanes are
