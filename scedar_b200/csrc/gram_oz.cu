@@ -50,11 +50,17 @@
 //              itself in 32-byte runs (st.global.v4.f64)
 // TMEM holds S x 64 columns (448 of 512 for S = 7): no second accumulator set,
 // so phase 1 (~8 k cycles of an ~80 k cycle tile at p = 2000) is not overlapped.
-// Measured cost model of the MMA stream (SCEDAR_B200_OZ_DEBUG=1 prints per-tile
-// cycle counters): an instruction of N = 64 m columns takes ~128 cycles for
-// m = 3, 4 and ~96 for m = 1, 2 (ideal 32 m): the 128 x 32-byte row operand is
-// re-read from shared memory by every instruction, so the triangular product
-// set (runs of 7, 6, ... 1 slices) runs at ~0.79 of the pipe's rate.
+// What bounds it (SCEDAR_B200_OZ_DEBUG=1 prints per-tile cycle counters;
+// tools/umma_probe.cu, profiles/r02_umma_probe.log): issued alone, from operands
+// resident in shared memory, the 10-instruction K step runs at 909 cycles (ideal
+// 896).  In the kernel it takes ~1,130: per K step the tensor core READS 96 KB of
+// operands from shared memory (10 x 4 KB row operand + 28 x 2 KB column slices,
+// 107 B/cycle) while TMA WRITES the next 42 KB (47 B/cycle) -- 154 B/cycle against
+// the 128 B/cycle of an SM's shared memory.  cta_group::2 would halve the column
+// operand's share, but splits the N columns of an instruction between the two
+// CTAs' shared memories, which breaks the stacking of slices along N (the second
+// half of every instruction would land on a diagonal that depends on the run
+// length).  So: ~0.79 of the pipe's rate, shared-memory bound.
 // Tiles (128 rows x 64 columns) come from a host-built list in L2-friendly
 // order, dealt round-robin to the CTAs; the list also carries what to store
 // (tile / mirrored tile), so the whole-matrix, row-stripe, peer-store and
@@ -359,61 +365,55 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     long long w_tempty = 0, w_full = 0;
     const long long t_begin = clock64();
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-      for (int ks = 0; ks < KS; ++ks, ++it) {
-        const int kc = ks % OZ_CHUNK_SLABS;    // slab inside its K chunk
-        long long c0 = 0;
-        if (kc == 0) {
-          // a new chunk (or tile): the epilogue has drained the accumulators
+      for (int ks0 = 0; ks0 < KS; ks0 += OZ_CHUNK_SLABS, ++tcount) {
+        // a new K chunk (or tile): the epilogue has drained the accumulators
+        long long c0 = a.dbg ? clock64() : 0;
+        mbar_wait(tempty, (tcount & 1) ^ 1);
+        if (a.dbg) w_tempty += clock64() - c0;
+        tc::fence_after();
+        const int kc_end = KS - ks0 < OZ_CHUNK_SLABS ? KS - ks0 : OZ_CHUNK_SLABS;
+        for (int kc = 0; kc < kc_end; ++kc, ++it) {
+          const uint32_t buf = it & 1;
           c0 = a.dbg ? clock64() : 0;
-          mbar_wait(tempty, (tcount & 1) ^ 1);
-          if (a.dbg) w_tempty += clock64() - c0;
-          tc::fence_after();
-        }
-        const uint32_t buf = it & 1;
-        c0 = a.dbg ? clock64() : 0;
-        mbar_wait(full_b + 8 * buf, (it >> 1) & 1);
-        if (a.dbg) w_full += clock64() - c0;
-        const uint64_t db = tc::desc_sw128(ring_b + buf * B_STAGE);
-#pragma unroll
-        for (int sl = 0; sl < S; ++sl) {
-          c0 = a.dbg ? clock64() : 0;
-          mbar_wait(full_a + 8 * sl, it & 1);
+          mbar_wait(full_b + 8 * buf, (it >> 1) & 1);
           if (a.dbg) w_full += clock64() - c0;
-          tc::fence_after();
-          const uint64_t da = tc::desc_sw128(ring_a + sl * A_SLAB);
+          const uint64_t db = tc::desc_sw128(ring_b + buf * B_STAGE);
 #pragma unroll
-          for (int kk = 0; kk < OKB / 32; ++kk) {
-            // slice sl of the row tile x slices [0, S - sl) of the column tile in one
-            // instruction (N = 64 m <= 256) or two.  An instruction costs
-            // ~128 cycles for m = 3, 4 and ~96 for m = 1, 2 (ideal 32 m): the
-            // 128 x 32-byte row operand is re-read from shared memory by every
-            // instruction (measured: the S = 6 and S = 7 tile times fit this
-            // model to 2 %).  Slice 0 goes first in a chunk: it covers every
-            // diagonal, so its first K step zero-initialises them.
-            constexpr int kFullRun = 4;
-            const int run = S - sl;
-            const int first = run <= kFullRun ? run : (run + 1) / 2;
-            const uint32_t acc = (kc | kk | sl) != 0;
-            if (el) {
-              tc::mma_i8(tmem_base + (uint32_t)(sl * ON), da + (uint64_t)((kk * 32) >> 4),
-                         db + (uint64_t)((kk * 32) >> 4), tc::idesc_u8(ON * first), acc);
-              if (run > first)
-                tc::mma_i8(tmem_base + (uint32_t)((sl + first) * ON),
-                           da + (uint64_t)((kk * 32) >> 4),
-                           db + (uint64_t)((first * B_SLAB + kk * 32) >> 4),
-                           tc::idesc_u8(ON * (run - first)), acc);
+          for (int sl = 0; sl < S; ++sl) {
+            c0 = a.dbg ? clock64() : 0;
+            mbar_wait(full_a + 8 * sl, it & 1);
+            if (a.dbg) w_full += clock64() - c0;
+            tc::fence_after();
+            const uint64_t da = tc::desc_sw128(ring_a + sl * A_SLAB);
+#pragma unroll
+            for (int kk = 0; kk < OKB / 32; ++kk) {
+              // slice sl of the row tile x slices [0, S - sl) of the column tile in
+              // one instruction (N = 64 m <= 256) or two of about equal length
+              // (N = 64 alone would take 54 cycles instead of 32, N >= 128 runs at
+              // N / 2: tools/umma_probe.cu).  Slice 0 goes first in a chunk: it
+              // covers every diagonal, so its first K step zero-initialises them.
+              constexpr int kFullRun = 4;
+              const int run = S - sl;
+              const int first = run <= kFullRun ? run : (run + 1) / 2;
+              const uint32_t acc = (kc | kk | sl) != 0;
+              if (el) {
+                tc::mma_i8(tmem_base + (uint32_t)(sl * ON), da + (uint64_t)((kk * 32) >> 4),
+                           db + (uint64_t)((kk * 32) >> 4), tc::idesc_u8(ON * first), acc);
+                if (run > first)
+                  tc::mma_i8(tmem_base + (uint32_t)((sl + first) * ON),
+                             da + (uint64_t)((kk * 32) >> 4),
+                             db + (uint64_t)((first * B_SLAB + kk * 32) >> 4),
+                             tc::idesc_u8(ON * (run - first)), acc);
+              }
             }
+            if (el) tc::commit(empty_a + 8 * sl);   // slot reusable once these MMAs retire
+            __syncwarp();
           }
-          if (el) tc::commit(empty_a + 8 * sl);   // slot reusable once these MMAs retire
+          if (el) tc::commit(empty_b + 8 * buf);
           __syncwarp();
         }
-        if (el) tc::commit(empty_b + 8 * buf);
+        if (el) tc::commit(tfull);              // this chunk's accumulators are complete
         __syncwarp();
-        if (kc == OZ_CHUNK_SLABS - 1 || ks == KS - 1) {
-          if (el) tc::commit(tfull);            // this chunk's accumulators are complete
-          __syncwarp();
-          ++tcount;
-        }
       }
     }
     if (a.dbg && lane == 0) {

@@ -296,6 +296,137 @@ rate_kernel(int N, int S, int iters, int mode, uint32_t idesc, unsigned long lon
   tmem_teardown<CG>(tmem_base, warp);
 }
 
+// ---- rate2: a tight, warp-uniform issue loop (elected lane, descriptors =
+// base + constant, fully unrolled) -- what gram_oz.cu really issues.  cta_group 1.
+//   mode 0  SS: A and B from shared memory, one N
+//   mode 1  TS: A from TMEM (8 columns at 480), B from shared memory, one N
+//   mode 2  SS, the S = 7 stacked schedule of gram_oz.cu (10 instructions / K step)
+//   mode 3  TS + one tcgen05.cp 128x256b per 4 MMAs (re-staging A in TMEM)
+//   mode 4  SS, every instruction N = 256 (7 per K step: the ideal packing)
+__device__ __forceinline__ bool elect1() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b,
+                                        uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+               "r"(a_tmem), "l"(b), "r"(idesc)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_cp(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__global__ void __launch_bounds__(128, 1)
+rate2_kernel(int N, int mode, int iters, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  // A: 7 slices x 8 KB (128 rows x 64 B); B: 7 slices x 4 KB stacked (64 rows x 64 B)
+  const uint32_t sa = base, sb = base + 7 * 8192;
+  const uint32_t bars = sb + 16 * 4096;
+  const uint32_t done = bars;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(g + (bars - base) + 64);
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < (bars - base) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(g)[i] = 0x01020301u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  const uint32_t tmem_base = tmem_setup<1>(bars + 64, slot, warp);
+  if (warp == 0) {
+    const bool el = elect1();
+    const uint64_t da = umma_desc64(sa), db = umma_desc64(sb);
+    const uint32_t idN = (2u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+    const uint32_t id64 = (2u << 4) | (8u << 17) | (8u << 24), id128 = (2u << 4) | (16u << 17) | (8u << 24),
+                   id192 = (2u << 4) | (24u << 17) | (8u << 24), id256 = (2u << 4) | (32u << 17) | (8u << 24);
+    const uint32_t a_t = tmem_base + 480;
+    __syncwarp();
+    const long long t0 = clock64();
+    long long n_mma = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        if (mode == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (el) umma<1, 0>(tmem_base + (q & 1) * 224, da + (uint64_t)(((q % 7) * 8192 + kk * 32) >> 4),
+                               db + (uint64_t)((kk * 32) >> 4), idN, 1);
+          n_mma += 8;
+        } else if (mode == 1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (el) umma_ts(tmem_base + (q & 1) * 224, a_t, db + (uint64_t)((kk * 32) >> 4), idN);
+          n_mma += 8;
+        } else if (mode == 2) {
+          // slice s x slices [0, 7 - s): 4+3, 3+3, 3+2, 4, 3, 2, 1
+          if (el) {
+            umma<1, 0>(tmem_base + 0, da + (uint64_t)((0 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id256, 1);
+            umma<1, 0>(tmem_base + 256, da + (uint64_t)((0 * 8192 + kk * 32) >> 4), db + (uint64_t)((4 * 4096 + kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 64, da + (uint64_t)((1 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 256, da + (uint64_t)((1 * 8192 + kk * 32) >> 4), db + (uint64_t)((3 * 4096 + kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 128, da + (uint64_t)((2 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 320, da + (uint64_t)((2 * 8192 + kk * 32) >> 4), db + (uint64_t)((3 * 4096 + kk * 32) >> 4), id128, 1);
+            umma<1, 0>(tmem_base + 192, da + (uint64_t)((3 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id256, 1);
+            umma<1, 0>(tmem_base + 256, da + (uint64_t)((4 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 320, da + (uint64_t)((5 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id128, 1);
+            umma<1, 0>(tmem_base + 384, da + (uint64_t)((6 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id64, 1);
+          }
+          n_mma += 10;
+        } else if (mode == 3) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if ((q & 3) == 0 && el) tmem_cp(a_t, da + (uint64_t)(((q % 7) * 8192 + kk * 32) >> 4));
+            if (el) umma_ts(tmem_base + (q & 1) * 224, a_t, db + (uint64_t)((kk * 32) >> 4), idN);
+          }
+          n_mma += 8;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 7; ++q)
+            if (el) umma<1, 0>(tmem_base + (q & 1) * 256, da + (uint64_t)((q * 8192 + kk * 32) >> 4),
+                               db + (uint64_t)(((q % 4) * 4096 + kk * 32) >> 4), id256, 1);
+          n_mma += 7;
+        }
+      }
+      __syncwarp();
+    }
+    if (el) commit<1>(done);
+    __syncwarp();
+    mbar_wait(done, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) {
+      out[2 * blockIdx.x] = (unsigned long long)(t1 - t0);
+      out[2 * blockIdx.x + 1] = (unsigned long long)n_mma;
+    }
+  }
+  tmem_teardown<1>(tmem_base, warp);
+}
+
+static void run_rate2(int N, int mode, const char* what) {
+  const int units = 148;
+  const int smem = 1024 + 7 * 8192 + 16 * 4096 + 256;
+  unsigned long long* out;
+  CK(cudaMalloc(&out, sizeof(unsigned long long) * 2 * units));
+  CK(cudaFuncSetAttribute(rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int rep = 0; rep < 2; ++rep) {
+    rate2_kernel<<<units, 128, smem>>>(N, mode, 300, out);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<unsigned long long> h(2 * units);
+  CK(cudaMemcpy(h.data(), out, sizeof(unsigned long long) * 2 * units, cudaMemcpyDeviceToHost));
+  std::vector<double> per;
+  for (int u = 0; u < units; ++u) per.push_back((double)h[2 * u] / (double)h[2 * u + 1]);
+  std::sort(per.begin(), per.end());
+  printf("rate2 %-44s N=%3d: %.1f cycles per MMA (ideal N/2 = %d)\n", what, N,
+         per[per.size() / 2], N / 2);
+  cudaFree(out);
+}
+
 template <int CG>
 static int run_check(int N, int a_signed, int b_signed) {
   const int rows = 256 + 256, cols = 64;
@@ -426,6 +557,11 @@ int main() {
     run_rate<1, 1>(N, 4, 1);
     run_rate<2, 1>(N, 4, 1);
   }
+  for (int N : {64, 128, 192, 256}) run_rate2(N, 0, "SS (A, B from shared memory)");
+  for (int N : {64, 128, 192, 256}) run_rate2(N, 1, "TS (A from TMEM)");
+  for (int N : {64, 128, 192, 256}) run_rate2(N, 3, "TS + tcgen05.cp 128x256b per 4 MMAs");
+  run_rate2(0, 2, "SS, stacked S = 7 schedule (10 per K step)");
+  run_rate2(256, 4, "SS, all N = 256 (7 per K step)");
   // three accumulators (two-pass split): S = 3 pattern at N = 128 / 160
   run_rate<1, 0>(128, 3, 0);
   run_rate<2, 0>(128, 3, 0);
