@@ -444,9 +444,20 @@ def run_b200(a):
     # uploads its shard over its own PCIe link and the shards are all-gathered
     # over NVLink (stripes.gather_x) -- 1.6 GB cross the host links once in
     # total, in parallel, instead of through rank 0's link alone.
-    from scedar_b200.stripes import gather_x, shard_rows
+    from scedar_b200.stripes import (gather_x, piece_layout, shard_rows,
+                                     take_shard)
     sb, se = shard_rows(n, world)[rank]
-    if world > 1:
+    pipelined = world > 1 and prec != "fp64"
+    if world > 1 and pipelined:
+        # piece-interleaved row shards: rank r holds its 1/N of every row piece
+        layout = piece_layout(n, world, 8)
+        shard_host = take_shard(x_dev[:n], layout, rank, world).cpu() \
+            .pin_memory()                                  # set-up, not timed
+        shard_dev = torch.empty(tuple(shard_host.shape), dtype=torch.float64,
+                                device=dev)
+        cap = max(b + world * m for b, _, m in layout)
+        x_e2e = torch.empty((cap, p), dtype=torch.float64, device=dev)
+    elif world > 1:
         shard_host = x_dev[sb:se].cpu().pin_memory()      # set-up, not timed
         shard_dev = torch.empty((se - sb, p), dtype=torch.float64, device=dev)
 
@@ -457,6 +468,13 @@ def run_b200(a):
             # lower triangle it completes are contracted at once
             sdm = StripedDistanceMatrix.from_host(x_host, a.metric, out=d_buf,
                                                   x_dev=x_dev, precision=prec)
+            idx, dd = sdm.knn(k, EXCLUDE_FIRST)
+            sdm.close()
+        elif pipelined:
+            # upload, all-gather and contraction pipelined over 8 row pieces
+            sdm = StripedDistanceMatrix.from_host_shards(
+                shard_host, layout, (n, p), peers, metric=a.metric,
+                precision=prec, x_dev=x_e2e, shard_dev=shard_dev)
             idx, dd = sdm.knn(k, EXCLUDE_FIRST)
             sdm.close()
         else:
@@ -708,7 +726,11 @@ def run_b200(a):
                           if world == 1 else
                           "x row-sharded over the {} ranks' pinned host "
                           "buffers, uploaded in parallel, all-gathered over "
-                          "NVLink".format(world))},
+                          "NVLink{}".format(
+                              world, " -- piece by piece (8 row pieces), the "
+                              "contraction of a piece's rows running while "
+                              "the next piece is uploaded and gathered"
+                              if pipelined else ""))},
         "e2e_api": api,
         "gpu_launches": int(launches),
         "roofline": roof,

@@ -171,6 +171,21 @@ int scedar_pdist_stripe_p2p(const scedar_cells_t* cells, int precision, int rank
                             double* const* stripe_ptr, int64_t ldd,
                             void* stream);
 
+/* Row-range form of scedar_pdist_stripe_p2p for cells that arrive piece by piece
+ * (scedar_cells_alloc + scedar_cells_fill_rows on every rank as the pieces of x
+ * are uploaded and gathered): the lower-triangle tiles of the rows [row_begin,
+ * row_end) -- which need the cells [0, row_end) only -- dealt column block by
+ * column block over the ranks, each stored with its transpose into the owners'
+ * stripes.  Called for consecutive ranges in ascending order on every rank it
+ * yields the matrix of scedar_pdist_stripe_p2p bit for bit.  reserve_sms SMs
+ * are left idle for the collective that gathers the next piece.  INT8 split
+ * kernels only (SCEDAR_PRECISION_FP64_I8 / _FP64_I8S6). */
+int scedar_pdist_p2p_rows(const scedar_cells_t* cells, int precision, int rank,
+                          int world, const int64_t* stripe_begin,
+                          double* const* stripe_ptr, int64_t ldd,
+                          int64_t row_begin, int64_t row_end, int reserve_sms,
+                          void* stream);
+
 /* Stripe buffers that can be mapped by the peer processes of one node
  * (cudaMalloc + CUDA IPC).  handle64 is a 64-byte opaque blob to ship to the
  * peers (e.g. torch.distributed.all_gather_object). */

@@ -55,6 +55,10 @@ SIGNATURES = {
     "scedar_pdist_stripe_p2p": (c_int, [c_void_p, c_int, c_int, c_int,
                                         POINTER(c_int64), POINTER(c_void_p),
                                         c_int64, c_void_p]),
+    "scedar_pdist_p2p_rows": (c_int, [c_void_p, c_int, c_int, c_int,
+                                      POINTER(c_int64), POINTER(c_void_p),
+                                      c_int64, c_int64, c_int64, c_int,
+                                      c_void_p]),
     "scedar_stripe_alloc": (c_int, [ctypes.c_size_t, POINTER(c_void_p)]),
     "scedar_stripe_free": (c_int, [c_void_p]),
     "scedar_stripe_export": (c_int, [c_void_p, c_void_p]),

@@ -377,6 +377,23 @@ int scedar_pdist_stripe_p2p(const scedar_cells_t* c, int precision, int rank, in
                                 static_cast<cudaStream_t>(stream));
 }
 
+int scedar_pdist_p2p_rows(const scedar_cells_t* c, int precision, int rank, int world,
+                          const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
+                          int64_t row_begin, int64_t row_end, int reserve_sms, void* stream) {
+  SCEDAR_CHECK(check_rows(c, row_begin, row_end));
+  SCEDAR_CHECK(check_precision(precision));
+  if (!stripe_begin || !stripe_ptr) return fail(SCEDAR_ERR_ARG, "NULL stripe table");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (reserve_sms < 0) return fail(SCEDAR_ERR_ARG, "reserve_sms must be >= 0");
+  const int S = oz_slices(c, precision);
+  if (!S)
+    return fail(SCEDAR_ERR_UNSUPPORTED,
+                "row ranges of the peer-store contraction run on the INT8 split kernel "
+                "(precision fp64_i8 / fp64_i8s6)");
+  return launch_oz_p2p_rows(c, S, rank, world, stripe_begin, stripe_ptr, ldd, row_begin, row_end,
+                            reserve_sms, static_cast<cudaStream_t>(stream));
+}
+
 // ---- PCA producer pieces ------------------------------------------------------
 int scedar_cells_col_means(const scedar_cells_t* c, double* mean_out, void* stream) {
   if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");

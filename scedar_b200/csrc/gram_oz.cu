@@ -569,6 +569,18 @@ int oz_group_rows() {
 
 }  // namespace
 
+// Tile lists live on the device, keyed by matrix size, launch form and range:
+// they depend on nothing else, so the handles of successive steps (and the row
+// pieces of a pipelined upload, every step) share them.
+struct OzTileList {
+  int device;
+  int64_t n;
+  int mode;
+  int64_t ka, kb, kc, kd;
+  OzTile* dev;
+  int count;
+};
+
 // working set of the INT8 split of a cells handle (created on first use)
 struct OzState {
   int S = 0;
@@ -580,12 +592,8 @@ struct OzState {
   int64_t n_pl = 0, p_oz = 0;
   int n_chunks = 1;
   bool sliced_all = false;
-  OzTile* tiles = nullptr;      // device tile list (grown on demand)
-  size_t tiles_cap = 0;
-  std::vector<OzTile> host_tiles;
-  // key of the list currently on the device
-  int key_mode = -1;
-  int64_t key_a = -1, key_b = -1, key_c = -1, key_d = -1;
+  const struct OzTileList* current = nullptr;   // list of the launch being prepared
+  std::vector<OzTile> host_tiles;               // scratch of the list builders
   CUtensorMap map_a, map_b;
 };
 
@@ -597,7 +605,6 @@ void oz_state_free(void* p, cudaStream_t s) {
   if (o->hi) cudaFreeAsync(o->hi, s);
   if (o->lo) cudaFreeAsync(o->lo, s);
   if (o->stat) cudaFreeAsync(o->stat, s);
-  if (o->tiles) cudaFreeAsync(o->tiles, s);
   delete o;
 }
 
@@ -682,36 +689,46 @@ int ensure_oz(const scedar_cells* c, int S, cudaStream_t s, OzState** out) {
   return SCEDAR_OK;
 }
 
-bool oz_have_tiles(const OzState* o, int mode, int64_t ka, int64_t kb, int64_t kc, int64_t kd) {
-  return o->key_mode == mode && o->key_a == ka && o->key_b == kb && o->key_c == kc &&
-         o->key_d == kd;
+std::vector<OzTileList>& oz_lists() {
+  static std::vector<OzTileList> lists;
+  if (lists.capacity() < 256) lists.reserve(256);   // `current` points into the vector
+  return lists;
 }
 
-// upload the host tile list unless the same list is already on the device
-int oz_put_tiles(OzState* o, int mode, int64_t ka, int64_t kb, int64_t kc, int64_t kd,
-                 cudaStream_t s) {
-  if (oz_have_tiles(o, mode, ka, kb, kc, kd)) return SCEDAR_OK;
-  const size_t need = o->host_tiles.size();
-  if (need > o->tiles_cap) {
-    if (o->tiles) cudaFreeAsync(o->tiles, s);
-    o->tiles = nullptr;
-    o->tiles_cap = 0;
-    SCEDAR_CUDA(cudaMallocAsync(&o->tiles, sizeof(OzTile) * need, s));
-    o->tiles_cap = need;
+bool oz_have_tiles(const scedar_cells* c, OzState* o, int mode, int64_t ka, int64_t kb,
+                   int64_t kc, int64_t kd) {
+  for (const auto& l : oz_lists())
+    if (l.device == c->device && l.n == c->n && l.mode == mode && l.ka == ka && l.kb == kb &&
+        l.kc == kc && l.kd == kd) {
+      o->current = &l;
+      return true;
+    }
+  return false;
+}
+
+// keep the freshly built host list on the device under its key (unless it is there)
+int oz_put_tiles(const scedar_cells* c, OzState* o, int mode, int64_t ka, int64_t kb, int64_t kc,
+                 int64_t kd, cudaStream_t s) {
+  if (oz_have_tiles(c, o, mode, ka, kb, kc, kd)) return SCEDAR_OK;
+  auto& lists = oz_lists();
+  if (lists.size() >= 256) {          // many different shapes: start over
+    for (auto& l : lists)
+      if (l.dev) cudaFreeAsync(l.dev, s);
+    lists.clear();
   }
-  if (need)
-    SCEDAR_CUDA(cudaMemcpyAsync(o->tiles, o->host_tiles.data(), sizeof(OzTile) * need,
+  OzTileList l{c->device, c->n, mode, ka, kb, kc, kd, nullptr, (int)o->host_tiles.size()};
+  if (l.count) {
+    SCEDAR_CUDA(cudaMallocAsync(&l.dev, sizeof(OzTile) * l.count, s));
+    // the copy from pageable memory is staged before the call returns
+    SCEDAR_CUDA(cudaMemcpyAsync(l.dev, o->host_tiles.data(), sizeof(OzTile) * l.count,
                                 cudaMemcpyHostToDevice, s));
-  // the copy from pageable memory is staged before the call returns
-  o->key_mode = mode;
-  o->key_a = ka;
-  o->key_b = kb;
-  o->key_c = kc;
-  o->key_d = kd;
+  }
+  lists.push_back(l);
+  o->current = &lists.back();
   return SCEDAR_OK;
 }
 
-int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
+int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s, int reserve_sms = 0) {
   a.sc = o->sc;
   a.hi = o->hi;
   a.lo = o->lo;
@@ -723,8 +740,9 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
   a.n_pl = o->n_pl;
   a.kslabs = (int)(o->p_oz / OKB);
   a.euclid = c->metric == SCEDAR_METRIC_EUCLIDEAN;
-  a.tiles = o->tiles;
-  a.n_tiles = (int)o->host_tiles.size();
+  if (!o->current) return fail(SCEDAR_ERR_CUDA, "no tile list");
+  a.tiles = o->current->dev;
+  a.n_tiles = o->current->count;
   if (a.n_tiles == 0) return SCEDAR_OK;
   Scratch dbg;
   const bool debug = getenv("SCEDAR_B200_OZ_DEBUG") != nullptr;
@@ -737,7 +755,7 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
   a.vec_ok = a.ldd % 4 == 0;
   for (int r = 0; r < a.world; ++r)
     if (reinterpret_cast<uintptr_t>(a.stripe_ptr[r]) % 32 != 0) a.vec_ok = 0;
-  int grid = std::min(a.n_tiles, num_sms());
+  int grid = std::min(a.n_tiles, std::max(1, num_sms() - reserve_sms));
   if (const char* e = getenv("SCEDAR_B200_OZ_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
   if (o->S == 6) {
     SCEDAR_CUDA(cudaFuncSetAttribute(gram_oz_kernel<6>,
@@ -770,21 +788,26 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s) {
   return SCEDAR_OK;
 }
 
-// Tiles of the row tiles [rt0, rt1) in L2-friendly order.  `want(I, Jr)` decides
-// for the pair (row tile I, row tile Jr = J / 2 holding the 64 columns) whether
-// this launch computes it and what it stores.
+// Tiles of the row tiles [rt0, rt1) in L2-friendly order: groups of G row tiles,
+// inside a group column block after column block.  `want(I, J)` says whether this
+// launch computes the tile and what it stores; with `lower` only the blocks at
+// or left of the diagonal (J / 2 <= I) are visited, every `j_step`-th starting
+// at `j_first` (in units of 128-column block pairs).
 template <typename Want>
-void oz_list(std::vector<OzTile>& out, int64_t rt0, int64_t rt1, int64_t n, Want want) {
+void oz_list(std::vector<OzTile>& out, int64_t rt0, int64_t rt1, int64_t n, bool lower,
+             int64_t jr_first, int64_t jr_step, Want want) {
   out.clear();
   const int64_t CT = (n + ON - 1) / ON;
   const int G = oz_group_rows();
   for (int64_t g0 = rt0; g0 < rt1; g0 += G) {
     const int64_t g1 = std::min<int64_t>(rt1, g0 + G);
-    for (int64_t J = 0; J < CT; ++J)
-      for (int64_t I = g0; I < g1; ++I) {
-        const int f = want(I, J);
-        if (f) out.push_back(OzTile{(int32_t)I, (int32_t)J, f, 0});
-      }
+    const int64_t jr_end = lower ? std::min<int64_t>(g1, (CT + 1) / 2) : (CT + 1) / 2;
+    for (int64_t Jr = jr_first; Jr < jr_end; Jr += jr_step)
+      for (int64_t J = 2 * Jr; J < std::min<int64_t>(2 * Jr + 2, CT); ++J)
+        for (int64_t I = lower ? std::max<int64_t>(g0, Jr) : g0; I < g1; ++I) {
+          const int f = want(I, J);
+          if (f) out.push_back(OzTile{(int32_t)I, (int32_t)J, f, 0});
+        }
   }
 }
 
@@ -812,8 +835,8 @@ int launch_oz_stripe(const scedar_cells* c, int S, int64_t row_begin, int64_t ro
   auto inside = [&](int64_t T) {
     return T * OM >= row_begin && std::min<int64_t>((T + 1) * OM, n) <= row_end;
   };
-  if (!oz_have_tiles(o, 0, row_begin, row_end, oz_group_rows(), 0))
-  oz_list(o->host_tiles, rt0, rt1, n, [&](int64_t I, int64_t J) -> int {
+  if (!oz_have_tiles(c, o, 0, row_begin, row_end, oz_group_rows(), 0))
+  oz_list(o->host_tiles, rt0, rt1, n, false, 0, 1, [&](int64_t I, int64_t J) -> int {
     const int64_t Jr = J / 2;
     if (inside(I) && inside(Jr)) {
       if (Jr > I) return 0;                     // produced as a mirror
@@ -821,7 +844,7 @@ int launch_oz_stripe(const scedar_cells* c, int S, int64_t row_begin, int64_t ro
     }
     return TILE_DIRECT;
   });
-  SCEDAR_CHECK(oz_put_tiles(o, 0, row_begin, row_end, oz_group_rows(), 0, s));
+  SCEDAR_CHECK(oz_put_tiles(c, o, 0, row_begin, row_end, oz_group_rows(), 0, s));
   OzArgs a{};
   a.ldd = ldd;
   a.world = 1;
@@ -866,15 +889,15 @@ int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
     while (r + 1 < world && T * OM >= stripe_begin[r + 1]) ++r;
     return r;
   };
-  if (!oz_have_tiles(o, 1, rank, world, stripe_begin[rank], oz_group_rows()))
-  oz_list(o->host_tiles, 0, RT, n, [&](int64_t I, int64_t J) -> int {
+  if (!oz_have_tiles(c, o, 1, rank, world, stripe_begin[rank], oz_group_rows()))
+  oz_list(o->host_tiles, 0, RT, n, true, 0, 1, [&](int64_t I, int64_t J) -> int {
     const int64_t Jr = J / 2;
     if (Jr > I) return 0;
     if (Jr == I) return owner(I) == rank ? TILE_DIRECT : 0;
     const int64_t by = ((I + Jr) & 1) == 0 ? I : Jr;
     return owner(by) == rank ? TILE_DIRECT | TILE_MIRROR : 0;
   });
-  SCEDAR_CHECK(oz_put_tiles(o, 1, rank, world, stripe_begin[rank], oz_group_rows(), s));
+  SCEDAR_CHECK(oz_put_tiles(c, o, 1, rank, world, stripe_begin[rank], oz_group_rows(), s));
   OzArgs a{};
   a.ldd = ldd;
   a.world = world;
@@ -903,12 +926,13 @@ int launch_oz_lower_rows(const scedar_cells* c, int S, int64_t row_begin, int64_
   SCEDAR_CHECK(oz_slice_rows(c, o, row_begin, std::min<int64_t>(pad_end, c->n_pad), s));
   if (row_begin == 0 && row_end == n) o->sliced_all = true;
   const int64_t rt0 = row_begin / OM, rt1 = (row_end + OM - 1) / OM;
-  oz_list(o->host_tiles, rt0, rt1, std::min<int64_t>(n, rt1 * OM), [&](int64_t I, int64_t J) -> int {
+  if (!oz_have_tiles(c, o, 2, row_begin, row_end, oz_group_rows(), 0))
+  oz_list(o->host_tiles, rt0, rt1, std::min<int64_t>(n, rt1 * OM), true, 0, 1, [&](int64_t I, int64_t J) -> int {
     const int64_t Jr = J / 2;
     if (Jr > I) return 0;
     return Jr == I ? TILE_DIRECT : TILE_DIRECT | TILE_MIRROR;
   });
-  SCEDAR_CHECK(oz_put_tiles(o, 2, row_begin, row_end, oz_group_rows(), 0, s));
+  SCEDAR_CHECK(oz_put_tiles(c, o, 2, row_begin, row_end, oz_group_rows(), 0, s));
   OzArgs a{};
   a.ldd = ldd;
   a.world = 1;
@@ -918,6 +942,54 @@ int launch_oz_lower_rows(const scedar_cells* c, int S, int64_t row_begin, int64_
   a.row_lo = 0;
   a.row_hi = n;
   return oz_launch(c, o, a, s);
+}
+
+// Row-range form of the peer-store contraction, for cells that arrive piece by
+// piece (the upload of x and its all-gather run behind it): the tiles (I, J) with
+// I in the range and J at or left of the diagonal, every `world`-th column block
+// taken by this rank (balanced inside every row tile, whatever part of the
+// matrix has arrived so far); tile and mirrored tile go to their owners' stripes,
+// local or over NVLink.  `reserve_sms` SMs are left to the collective that
+// gathers the next piece.
+int launch_oz_p2p_rows(const scedar_cells* c, int S, int rank, int world,
+                       const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
+                       int64_t row_begin, int64_t row_end, int reserve_sms, cudaStream_t s) {
+  if (world < 1 || world > kOzPeers) return fail(SCEDAR_ERR_ARG, "world must be in 1..16");
+  if (rank < 0 || rank >= world) return fail(SCEDAR_ERR_ARG, "rank out of range");
+  if (row_end <= row_begin) return SCEDAR_OK;
+  if (row_begin % OM != 0) return fail(SCEDAR_ERR_ARG, "row_begin must be 128-aligned");
+  const int64_t n = c->n;
+  for (int r = 0; r <= world; ++r) {
+    const int64_t b = stripe_begin[r];
+    if (!(b % OM == 0 || b == n) || (r > 0 && b < stripe_begin[r - 1]))
+      return fail(SCEDAR_ERR_ARG, "stripes must be ascending and 128-row aligned");
+  }
+  if (stripe_begin[0] != 0 || stripe_begin[world] != n)
+    return fail(SCEDAR_ERR_ARG, "stripes must cover [0, n)");
+  OzState* o = nullptr;
+  SCEDAR_CHECK(oz_alloc(c, S, s, &o));
+  const int64_t pad_end = row_end == n ? c->n_pad : round_up(row_end, OM);
+  SCEDAR_CHECK(oz_slice_rows(c, o, row_begin, std::min<int64_t>(pad_end, c->n_pad), s));
+  if (row_begin == 0 && row_end == n) o->sliced_all = true;
+  const int64_t rt0 = row_begin / OM, rt1 = (row_end + OM - 1) / OM;
+  if (!oz_have_tiles(c, o, 3, row_begin, row_end, rank * 64 + world, oz_group_rows()))
+    oz_list(o->host_tiles, rt0, rt1, std::min<int64_t>(n, rt1 * OM), true, rank, world,
+            [&](int64_t I, int64_t J) -> int {
+              return J / 2 == I ? TILE_DIRECT : TILE_DIRECT | TILE_MIRROR;
+            });
+  SCEDAR_CHECK(
+      oz_put_tiles(c, o, 3, row_begin, row_end, rank * 64 + world, oz_group_rows(), s));
+  OzArgs a{};
+  a.ldd = ldd;
+  a.world = world;
+  for (int r = 0; r < world; ++r) {
+    a.stripe_begin[r] = stripe_begin[r];
+    a.stripe_ptr[r] = stripe_ptr[r];
+  }
+  a.stripe_begin[world] = stripe_begin[world];
+  a.row_lo = 0;
+  a.row_hi = n;
+  return oz_launch(c, o, a, s, reserve_sms);
 }
 
 }  // namespace scedar

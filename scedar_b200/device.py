@@ -384,6 +384,18 @@ def pdist_stripe_p2p(cells, peers, rank, precision="fp64"):
         peers.n, _stream()))
 
 
+def pdist_p2p_rows(cells, peers, rank, row_begin, row_end, precision="fp64_i8",
+                   reserve_sms=0):
+    """Row-range form of ``pdist_stripe_p2p`` (INT8 split kernels): the
+    lower-triangle tiles of rows [row_begin, row_end) this rank takes, stored
+    with their transposes into the owners' stripes; needs the cells
+    [0, row_end) only."""
+    begins, ptrs = peers.tables()
+    _capi.check(_capi.load().scedar_pdist_p2p_rows(
+        cells._h, PRECISION_IDS[precision], rank, peers.world, begins, ptrs,
+        peers.n, int(row_begin), int(row_end), int(reserve_sms), _stream()))
+
+
 # ---------------------------------------------------------------------------
 # consumers behind the path (SURVEY.md 8f): kNN graph, rare samples, imputation
 # ---------------------------------------------------------------------------
@@ -602,3 +614,14 @@ def _copy_stream():
     if d not in _COPY_STREAMS:
         _COPY_STREAMS[d] = torch.cuda.Stream(device=d)
     return _COPY_STREAMS[d]
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream():
+    """Stream the collectives of a pipelined upload are issued on."""
+    d = torch.cuda.current_device()
+    if d not in _COMM_STREAMS:
+        _COMM_STREAMS[d] = torch.cuda.Stream(device=d)
+    return _COMM_STREAMS[d]

@@ -59,6 +59,42 @@ def gather_x(x_rows, n, group=None):
     return out[:n]
 
 
+def piece_layout(n, world, n_pieces=8):
+    """Row pieces for the pipelined multi-rank upload of x (``from_host_shards``):
+    a list of ``(row_begin, row_end, rows_per_rank)``.  Piece boundaries are
+    multiples of 128 * world (the last piece ends at n), so a piece is a whole
+    number of row tiles and splits evenly over the ranks; inside piece q rank r
+    holds the rows ``[b + r m, min(b + (r + 1) m, e))``, m = ceil((e - b) /
+    world) -- the last piece may leave some ranks short (padding rows)."""
+    unit = TILE * world
+    units = (n + unit - 1) // unit
+    n_pieces = max(1, min(n_pieces, units))
+    out, u0 = [], 0
+    for q in range(n_pieces):
+        u1 = units * (q + 1) // n_pieces
+        b, e = min(u0 * unit, n), min(u1 * unit, n)
+        if e > b:
+            out.append((b, e, (e - b + world - 1) // world))
+        u0 = u1
+    return out
+
+
+def take_shard(x, layout, rank, world):
+    """Rank ``rank``'s host shard of x for ``layout``: its sub-range of every
+    piece, one after the other, each padded with zero rows to the piece's
+    rows-per-rank (what a per-process loader would hold)."""
+    parts = []
+    for b, e, m in layout:
+        lo, hi = min(b + rank * m, e), min(b + (rank + 1) * m, e)
+        blk = x[lo:hi]
+        if hi - lo < m:
+            pad = torch.zeros((m - (hi - lo), x.shape[1]), dtype=x.dtype,
+                              device=blk.device)
+            blk = torch.cat([blk, pad], dim=0)
+        parts.append(blk)
+    return torch.cat(parts, dim=0).contiguous()
+
+
 class _DeviceOps(object):
     """The CUDA library (default operators)."""
 
@@ -151,6 +187,71 @@ class StripedDistanceMatrix(object):
         self.cells, self.d_stripe = device.pdist_symmetric_from_host(
             x_host, metric, out=out, x_dev=x_dev, precision=precision)
         self.d_device = self.d_stripe.device
+        return self
+
+    @classmethod
+    def from_host_shards(cls, shard_host, layout, shape, peers, metric="correlation",
+                         precision="fp64_i8", x_dev=None, shard_dev=None,
+                         group=None, reserve_sms=8):
+        """Several ranks, x row-sharded over the ranks' pinned HOST buffers
+        (``take_shard``): the upload, the all-gather and the contraction run as
+        a pipeline over the row pieces of ``layout``.  Every rank copies its
+        share of piece q over its own PCIe link on a copy stream, the shares
+        are all-gathered over NVLink on a communication stream, and as soon as
+        a piece has landed its cells are prepared and the lower-triangle tiles
+        of its rows -- which need nothing beyond this piece -- are contracted
+        and stored into the owners' stripes (``device.pdist_p2p_rows``, INT8
+        split kernels), while the next piece is on its way.  ``reserve_sms``
+        SMs are left to the all-gather kernels.  On return D (this rank's
+        stripe of ``peers``) is complete on every rank."""
+        from . import device
+        self = cls.__new__(cls)
+        self.ops = _DeviceOps()
+        self.group = group
+        self.distributed = True
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n, self.p = shape
+        n, p, world, rank = self.n, self.p, self.world, self.rank
+        self.metric, self.precision = metric, precision
+        self.stripes = partition(n, world)
+        self.row_begin, self.row_end = self.stripes[rank]
+        dev_ = peers.tensor(rank).device
+        self.d_device = dev_
+        cap = max(b + world * m for b, _, m in layout)
+        if x_dev is None:
+            x_dev = torch.empty((cap, p), dtype=torch.float64, device=dev_)
+        assert x_dev.shape[0] >= cap and x_dev.shape[1] == p
+        rows_total = sum(m for _, _, m in layout)
+        if shard_dev is None:
+            shard_dev = torch.empty((rows_total, p), dtype=torch.float64,
+                                    device=dev_)
+        main = torch.cuda.current_stream()
+        copy, comm = device._copy_stream(), device._comm_stream()
+        copy.wait_stream(main)
+        comm.wait_stream(main)
+        self._fence()              # nobody still reads a stripe of the last step
+        self.cells = device.Cells.alloc(n, p, metric)
+        off = 0
+        for b, e, m in layout:
+            with torch.cuda.stream(copy):
+                shard_dev[off:off + m].copy_(shard_host[off:off + m],
+                                             non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(copy)
+            with torch.cuda.stream(comm):
+                comm.wait_event(up)
+                dist.all_gather_into_tensor(x_dev[b:b + world * m],
+                                            shard_dev[off:off + m], group=group)
+                landed = torch.cuda.Event()
+                landed.record(comm)
+            main.wait_event(landed)
+            self.cells.fill_rows(x_dev[b:e], b)
+            device.pdist_p2p_rows(self.cells, peers, rank, b, e,
+                                  precision=precision, reserve_sms=reserve_sms)
+            off += m
+        self._fence()              # every peer store has landed
+        self.d_stripe = peers.tensor(rank)
         return self
 
     @classmethod

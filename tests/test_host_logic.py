@@ -111,3 +111,29 @@ def test_partition_is_tile_aligned_and_covers():
             assert all(b % 128 == 0 or b == n for b, _ in parts)
     sizes = [e - b for b, e in partition(100000, 8)]
     assert max(sizes) - min(sizes) <= 128 + 96
+
+
+def test_piece_layout_and_shards():
+    """Row pieces of the pipelined multi-rank upload (stripes.piece_layout /
+    take_shard): pieces tile [0, n) on 128 * world boundaries, and gathering
+    the ranks' shares piece by piece rebuilds x."""
+    import torch
+    from scedar_b200.stripes import piece_layout, take_shard
+    for n, w, q in ((100000, 8, 8), (100000, 2, 8), (3005, 4, 8), (700, 3, 8),
+                    (128, 8, 8), (1000, 1, 4), (5, 2, 3)):
+        lay = piece_layout(n, w, q)
+        assert lay[0][0] == 0 and lay[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(lay, lay[1:]))
+        assert all(b % (128 * w) == 0 for b, _, _ in lay)
+        assert all(m * w >= e - b for b, e, m in lay)
+        x = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3)
+        shards = [take_shard(x, lay, r, w) for r in range(w)]
+        assert all(s.shape[0] == sum(m for _, _, m in lay) for s in shards)
+        cap = max(b + w * m for b, _, m in lay)
+        xd = torch.full((cap, 3), -1.0, dtype=torch.float64)
+        off = 0
+        for b, e, m in lay:
+            for r in range(w):               # what all_gather_into_tensor does
+                xd[b + r * m:b + (r + 1) * m] = shards[r][off:off + m]
+            off += m
+        assert torch.equal(xd[:n], x)

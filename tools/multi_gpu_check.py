@@ -154,6 +154,21 @@ def main():
         flag = torch.tensor([1.0 if same else 0.0], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         assert float(flag.item()) == 1.0, "peer-store D ({}) differs".format(prec)
+        # the pipelined form: x sharded over the ranks' host buffers, uploaded,
+        # gathered and contracted piece by piece -- the same matrix again
+        from scedar_b200.stripes import piece_layout, take_shard
+        lay = piece_layout(n, world, 4)
+        shard = take_shard(xb, lay, rank, world).cpu().pin_memory()
+        peers.tensor(rank).fill_(-5.0)
+        for _ in range(2):
+            s9, t_pipe = timed(lambda: StripedDistanceMatrix.from_host_shards(
+                shard, lay, (n, p), peers, metric="euclidean", precision=prec))
+            s9.close()
+        out["d_pipelined_{}_ms".format(prec)] = round(t_pipe, 2)
+        same = bool(torch.equal(d1[s8.row_begin:s8.row_end], peers.tensor(rank)))
+        flag = torch.tensor([1.0 if same else 0.0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert float(flag.item()) == 1.0, "pipelined D ({}) differs".format(prec)
         del d1
         s8.close()
     peers.close()

@@ -316,6 +316,13 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
                "r"(a_tmem), "l"(b), "r"(idesc)
                : "memory");
 }
+__device__ __forceinline__ void umma_ts_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t b,
+                                            uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+               "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_cp(uint32_t taddr, uint64_t sdesc) {
   asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
@@ -385,6 +392,24 @@ rate2_kernel(int N, int mode, int iters, unsigned long long* out) {
             if (el) umma_ts(tmem_base + (q & 1) * 224, a_t, db + (uint64_t)((kk * 32) >> 4), idN);
           }
           n_mma += 8;
+        } else if (mode == 5) {
+          // the stacked S = 7 schedule with the row operand staged in TMEM: one
+          // tcgen05.cp per slice and K step (slot 448 + 8 s), MMAs read it there
+          if (el) {
+#pragma unroll
+            for (int sl = 0; sl < 7; ++sl) {
+              const uint32_t at = tmem_base + 448 + 8 * sl;
+              tmem_cp(at, da + (uint64_t)((sl * 8192 + kk * 32) >> 4));
+              const int run = 7 - sl, first = run <= 4 ? run : (run + 1) / 2;
+              const uint32_t id1 = (2u << 4) | ((uint32_t)(first * 8) << 17) | (8u << 24);
+              umma_ts(tmem_base + sl * 64, at, db + (uint64_t)((kk * 32) >> 4), id1);
+              if (run > first) {
+                const uint32_t id2 = (2u << 4) | ((uint32_t)((run - first) * 8) << 17) | (8u << 24);
+                umma_ts(tmem_base + (sl + first) * 64, at, db + (uint64_t)((first * 4096 + kk * 32) >> 4), id2);
+              }
+            }
+          }
+          n_mma += 10;
         } else {
 #pragma unroll
           for (int q = 0; q < 7; ++q)
@@ -425,6 +450,51 @@ static void run_rate2(int N, int mode, const char* what) {
   printf("rate2 %-44s N=%3d: %.1f cycles per MMA (ideal N/2 = %d)\n", what, N,
          per[per.size() / 2], N / 2);
   cudaFree(out);
+}
+
+// ---- check (TS): the row operand is copied shared memory -> TMEM with
+// tcgen05.cp.128x256b (one 32-byte K step of the 64B-swizzled tile) and the MMA
+// reads it from there; must give the same products as the SS form
+__global__ void __launch_bounds__(128, 1)
+check_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                int N, uint32_t idesc, int32_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  const uint32_t sa = base, sb = base + 8192;
+  const uint32_t bars = base + 8192 + 16384;
+  const uint32_t full = bars, done = bars + 8;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(g + 8192 + 16384 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  const uint32_t tmem_base = tmem_setup<1>(bars + 64, slot, warp);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(full, 8192 + N * 64);
+    tma_load_2d(sa, &map_a, 0, 0, full);
+    tma_load_2d(sb, &map_b, 0, 256, full);
+    mbar_wait(full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int kk = 0; kk < 2; ++kk) {
+      tmem_cp(tmem_base + 480, umma_desc64(sa + kk * 32));
+      umma_ts_acc(tmem_base, tmem_base + 480, umma_desc64(sb + kk * 32), idesc, kk != 0);
+    }
+    commit<1>(done);
+  }
+  __syncthreads();
+  mbar_wait(done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    for (int c = 0; c < 32; ++c) out[row * N + c0 + c] = (int32_t)v[c];
+  }
+  tmem_teardown<1>(tmem_base, warp);
 }
 
 template <int CG>
@@ -479,6 +549,44 @@ static int run_check(int N, int a_signed, int b_signed) {
     }
   printf("check cg=%d N=%d A=%s B=%s: %s (%ld of %d wrong)\n", CG, N, a_signed ? "s8" : "u8",
          b_signed ? "s8" : "u8", bad ? "FAIL" : "ok", bad, M * N);
+  cudaFree(d);
+  cudaFree(out);
+  return bad != 0;
+}
+
+static int run_check_ts(int N) {
+  const int rows = 256 + 256, cols = 64;
+  std::vector<uint8_t> h((size_t)rows * cols);
+  srand(99 + N);
+  for (auto& v : h) v = (uint8_t)(rand() & 0xff);
+  uint8_t* d;
+  int32_t* out;
+  CK(cudaMalloc(&d, h.size()));
+  CK(cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&out, sizeof(int32_t) * 128 * N));
+  CK(cudaMemset(out, 0xff, sizeof(int32_t) * 128 * N));
+  CUtensorMap ma, mb;
+  if (encode_u8_map(&ma, d, rows, cols, 128, 64)) return 1;
+  if (encode_u8_map(&mb, d, rows, cols, N, 64)) return 1;
+  const int smem = 1024 + 8192 + 16384 + 256;
+  CK(cudaFuncSetAttribute(check_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  check_ts_kernel<<<1, 128, smem>>>(ma, mb, N, idesc_i8(128, N, 0, 0), out);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> got((size_t)128 * N);
+  CK(cudaMemcpy(got.data(), out, got.size() * 4, cudaMemcpyDeviceToHost));
+  long bad = 0;
+  for (int i = 0; i < 128; ++i)
+    for (int j = 0; j < N; ++j) {
+      long long acc = 0;
+      for (int k = 0; k < cols; ++k)
+        acc += (long long)h[(size_t)i * cols + k] * (long long)h[(size_t)(256 + j) * cols + k];
+      if ((long long)got[(size_t)i * N + j] != acc) {
+        if (bad < 5) printf("  TS mismatch (%d,%d): got %d want %lld\n", i, j, got[(size_t)i * N + j], acc);
+        ++bad;
+      }
+    }
+  printf("check TS (A via tcgen05.cp -> TMEM) N=%d u8 x u8: %s (%ld of %d wrong)\n", N,
+         bad ? "FAIL" : "ok", bad, 128 * N);
   cudaFree(d);
   cudaFree(out);
   return bad != 0;
@@ -544,6 +652,8 @@ int main() {
   fails += run_check<2>(128, 1, 0);
   fails += run_check<1>(256, 1, 0);
   fails += run_check<2>(256, 1, 0);
+  fails += run_check_ts(64);
+  fails += run_check_ts(256);
   fails += run_check<1>(32, 1, 0);
   fails += run_check<2>(32, 1, 0);
   const int Ns[] = {32, 64, 96, 128, 160, 256};
@@ -562,6 +672,7 @@ int main() {
   for (int N : {64, 128, 192, 256}) run_rate2(N, 3, "TS + tcgen05.cp 128x256b per 4 MMAs");
   run_rate2(0, 2, "SS, stacked S = 7 schedule (10 per K step)");
   run_rate2(256, 4, "SS, all N = 256 (7 per K step)");
+  run_rate2(0, 5, "TS stacked S = 7 schedule + 7 tcgen05.cp / K step");
   // three accumulators (two-pass split): S = 3 pattern at N = 128 / 160
   run_rate<1, 0>(128, 3, 0);
   run_rate<2, 0>(128, 3, 0);
