@@ -76,6 +76,11 @@ def parse():
                     help="--impl reference: wall time the warm-up + timed "
                          "steps may take; the sample shrinks to fit")
     ap.add_argument("--check-rows", type=int, default=64)
+    ap.add_argument("--e2e-mode", default=os.environ.get(
+        "SCEDAR_BENCH_E2E_MODE", "simple"), choices=["simple", "pipelined"],
+        help="N > 1: 'simple' uploads the row shards, all-gathers x and runs "
+             "the step; 'pipelined' overlaps upload, all-gather and contraction "
+             "over 8 row pieces (StripedDistanceMatrix.from_host_shards)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the dmma_path / fast_path / e2e_api extras")
@@ -447,7 +452,7 @@ def run_b200(a):
     from scedar_b200.stripes import (gather_x, piece_layout, shard_rows,
                                      take_shard)
     sb, se = shard_rows(n, world)[rank]
-    pipelined = world > 1 and prec != "fp64"
+    pipelined = world > 1 and prec != "fp64" and a.e2e_mode == "pipelined"
     if world > 1 and pipelined:
         # piece-interleaved row shards: rank r holds its 1/N of every row piece
         layout = piece_layout(n, world, 8)

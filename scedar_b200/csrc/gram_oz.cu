@@ -889,14 +889,36 @@ int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
     while (r + 1 < world && T * OM >= stripe_begin[r + 1]) ++r;
     return r;
   };
-  if (!oz_have_tiles(c, o, 1, rank, world, stripe_begin[rank], oz_group_rows()))
-  oz_list(o->host_tiles, 0, RT, n, true, 0, 1, [&](int64_t I, int64_t J) -> int {
-    const int64_t Jr = J / 2;
-    if (Jr > I) return 0;
-    if (Jr == I) return owner(I) == rank ? TILE_DIRECT : 0;
-    const int64_t by = ((I + Jr) & 1) == 0 ? I : Jr;
-    return owner(by) == rank ? TILE_DIRECT | TILE_MIRROR : 0;
-  });
+  if (!oz_have_tiles(c, o, 1, rank, world, stripe_begin[rank], oz_group_rows())) {
+    // The pair of row tiles {u, v} is computed by the owner of the higher one
+    // when u + v is even, of the lower one when odd (balanced: every rank gets
+    // the same number of pairs), and it is ORIENTED so that the computing
+    // rank's own tile supplies the 128 rows: the tile itself (32-byte runs per
+    // row) then lands in the rank's own HBM and only the mirrored tile (1 KB
+    // contiguous per row of D) crosses NVLink.  The rank's row operands are
+    // thus always its own stripe -- groups of G of its row tiles stay in L2
+    // while the partners' column blocks stream once per group.
+    o->host_tiles.clear();
+    const int64_t CT = (n + ON - 1) / ON;
+    const int64_t u0 = stripe_begin[rank] / OM, u1 = (stripe_begin[rank + 1] + OM - 1) / OM;
+    const int G = oz_group_rows();
+    for (int64_t g0 = u0; g0 < u1; g0 += G) {
+      const int64_t g1 = std::min<int64_t>(u1, g0 + G);
+      for (int64_t v = 0; v < RT; ++v)
+        for (int64_t J = 2 * v; J < std::min<int64_t>(2 * v + 2, CT); ++J)
+          for (int64_t u = g0; u < g1; ++u) {
+            if (u == v) {
+              o->host_tiles.push_back(OzTile{(int32_t)u, (int32_t)J, TILE_DIRECT, 0});
+              continue;
+            }
+            const int64_t hi = std::max(u, v), lo = std::min(u, v);
+            const int by = owner(((hi + lo) & 1) == 0 ? hi : lo);
+            // both tiles in this rank's stripe: the lower-triangle orientation
+            if (by != rank || (owner(v) == rank && v > u)) continue;
+            o->host_tiles.push_back(OzTile{(int32_t)u, (int32_t)J, TILE_DIRECT | TILE_MIRROR, 0});
+          }
+    }
+  }
   SCEDAR_CHECK(oz_put_tiles(c, o, 1, rank, world, stripe_begin[rank], oz_group_rows(), s));
   OzArgs a{};
   a.ldd = ldd;
