@@ -32,8 +32,10 @@
 // up to 1.5e-3 * max |x| of d.  The fast kNN is EXACT: the
 // tensor-core pass only proposes candidates (32 per cell and column split),
 // which are re-ranked with float64 distances computed like the FP64 path and
-// verified against the candidate threshold; cells whose margin is too small
-// are recomputed by the FP64 kernel.
+// verified against the candidate threshold with a margin that is the larger of
+// 8 x the error observed on the re-ranked candidates and an a-priori bound of
+// the FP32 accumulation (margin_kernel); cells whose margin is too small are
+// recomputed by the FP64 kernel.
 //
 // Structure (one CTA per SM, 192 threads):
 //   warp 0   TMA producer: per 32-wide K slab 4 boxes (A_hi, A_lo: 128 rows;
@@ -905,16 +907,28 @@ rerank_kernel(const double* __restrict__ xw, const double* __restrict__ stat,
 
 __global__ void __launch_bounds__(256)
 margin_kernel(const double* __restrict__ tau, const double* __restrict__ dk,
-              const unsigned int* __restrict__ err_bits, int64_t rows, int64_t row_begin,
+              const unsigned int* __restrict__ err_bits, const double* __restrict__ scale,
+              int euclid, int kblocks, int64_t rows, int64_t row_begin,
               unsigned char* __restrict__ tile_flag, unsigned char* __restrict__ row_flag,
               int* __restrict__ n_flagged) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  // a cell that was not re-ranked has approximate metric >= tau, hence exact
-  // metric >= tau - eps; it cannot enter the top k+1 if dk < tau - eps (the
-  // relative term keeps two squared distances that pass apart after sqrt)
+  // A cell that was not re-ranked has approximate metric >= tau, hence exact
+  // metric >= tau - eps; it cannot enter the top k+1 if dk < tau - eps.  eps is
+  // the larger of (a) 8 x the largest error OBSERVED on the re-ranked candidates
+  // of this launch and (b) an a-priori bound that does not depend on what was
+  // re-ranked: every K slab of 32 adds 6 tensor-core products (K = 16 each) to
+  // the FP32 accumulator, each addition rounding at 2^-24 of a partial sum that
+  // is bounded by B in margin space, plus the dropped lo.lo term and the FP16
+  // split of the operands (2^-21 B).  B: |cos| <= 1 for unit vectors (cosine,
+  // correlation); for euclidean the key is s^2 (|y_c|^2 - 2 y_r.y_c) with
+  // s^2 |y|^2 < 2^15, i.e. |partial| <= 3 * 2^15 / s^2 in squared-distance units.
   const double d = dk[row];
-  const double eps = 8.0 * (double)__uint_as_float(*err_bits) + 1e-12 * (d > 1.0 ? d : 1.0);
+  const double B = euclid ? 3.0 * 32768.0 * scale[1] : 1.0;
+  const double eps_prior = ((6.0 * (double)kblocks + 2.0) * 5.9604644775390625e-8 +
+                            4.76837158203125e-7) * B;
+  const double eps_seen = 8.0 * (double)__uint_as_float(*err_bits);
+  const double eps = (eps_seen > eps_prior ? eps_seen : eps_prior) + 1e-12 * (d > 1.0 ? d : 1.0);
   const bool bad = !(d + eps < tau[row]);
   row_flag[row] = bad;
   if (bad) {
@@ -1211,8 +1225,8 @@ int launch_fast_knn(const scedar_cells* c, int k, int exclude, int64_t row_begin
         dk.as<double>());
   }
   margin_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
-      tau.as<double>(), dk.as<double>(), err_bits, rows, row_begin, flags.as<unsigned char>(),
-      rflags.as<unsigned char>(), n_flagged);
+      tau.as<double>(), dk.as<double>(), err_bits, f->scale, a.euclid, a.kblocks, rows, row_begin,
+      flags.as<unsigned char>(), rflags.as<unsigned char>(), n_flagged);
   SCEDAR_CUDA(cudaGetLastError());
   count_launch(2);
   // rows whose candidate margin is too thin are recomputed by the FP64 kernel

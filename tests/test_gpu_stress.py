@@ -123,3 +123,34 @@ def test_random_stripes_and_csr(seed):
     want, idc, _ = korc.impute(x, arr, kk, n_do, 0.5, 2)
     np.testing.assert_array_equal(got[0], want)
     np.testing.assert_array_equal(got[1].toarray(), idc)
+
+
+def test_fast_knn_adversarial_margin():
+    """The exactness of the fast kNN must not rest on the errors that happen to
+    be observed among the re-ranked candidates: a wide dynamic range (a tight
+    cluster far from the centroid, where the FP32 accumulation of the
+    tensor-core pass cancels catastrophically, next to ordinary cells) with
+    near-ties at the candidate threshold.  The a-priori bound of margin_kernel
+    must send the affected cells to the FP64 kernel: identical lists."""
+    import torch
+    from scedar_b200 import device as dev
+    from scedar_b200._capi import EXCLUDE_SELF
+    rng = np.random.default_rng(77)
+    p = 96
+    base = rng.standard_normal((3000, p))
+    far = 4.0e3 + 1e-2 * rng.standard_normal((400, p))      # tight, far away
+    # near-ties: groups of cells on a sphere shell around shared centres
+    centres = rng.standard_normal((50, p)) * 3
+    shell = rng.standard_normal((50 * 40, p))
+    shell /= np.linalg.norm(shell, axis=1, keepdims=True)
+    ties = np.repeat(centres, 40, axis=0) + shell * (1.0 + 1e-7 * rng.standard_normal((2000, 1)))
+    x = np.vstack([base, far, ties])
+    rng.shuffle(x)
+    for metric in ("euclidean", "cosine", "correlation"):
+        cells = dev.Cells.from_dense(dev.to_device(x), metric)
+        for k in (5, 15, 40):
+            fi, fd = cells.knn_stripe(k, EXCLUDE_SELF, precision="fast")
+            ei, ed = cells.knn_stripe(k, EXCLUDE_SELF, precision="fp64")
+            assert torch.equal(fi, ei), (metric, k)
+            assert torch.equal(fd, ed), (metric, k)
+        cells.close()
