@@ -56,6 +56,7 @@ def install_sdm(cls):
     if not hasattr(cls, "precision"):
         cls.precision = fast.precision
     cls.I8_MIN_CELLS = fast.I8_MIN_CELLS
+    cls.I8_MIN_WORK = fast.I8_MIN_WORK
     cls.I8_MAX_FEATURES = fast.I8_MAX_FEATURES
     if not hasattr(cls, "_pca_x"):
         cls._pca_x = fast.__dict__["_pca_x"]

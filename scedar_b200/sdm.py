@@ -57,7 +57,7 @@ class SampleDistanceMatrix(object):
     ``precision`` (class or instance attribute, default from the environment
     variable ``SCEDAR_B200_PRECISION``, else ``"fp64"``) selects the Gram
     kernel: ``"fp64"`` matches the reference's float64 to 1e-10 -- with the
-    DMMA kernel, or, from 4,096 cells up, with the
+    DMMA kernel, or, from 1,024 cells and n^2 p = 2e10 up, with the
     INT8 split on the tcgen05 tensor cores (``"fp64_i8"``, 2.7 x faster, same
     bar; ``SCEDAR_B200_FP64_KERNEL=dmma|i8`` forces one; both can also be
     named directly as ``"fp64_dmma"`` / ``"fp64_i8"`` / ``"fp64_i8s6"``);
@@ -68,8 +68,10 @@ class SampleDistanceMatrix(object):
     re-rank of the tensor-core candidates).
     """
     precision = os.environ.get("SCEDAR_B200_PRECISION", "fp64")
-    # "fp64" picks the INT8 split kernel from this many cells up
-    I8_MIN_CELLS = 4096
+    # "fp64" picks the INT8 split kernel where it pays: enough cells to fill the
+    # SMs with 128 x 64 tiles and enough work (n^2 p) to amortise the slicing
+    I8_MIN_CELLS = 1024
+    I8_MIN_WORK = 2e10
     I8_MAX_FEATURES = 1 << 16
 
     def _gram_precision(self, n=None, p=None):
@@ -87,7 +89,8 @@ class SampleDistanceMatrix(object):
         fits = 0 < p <= self.I8_MAX_FEATURES
         if forced == "i8":
             return "fp64_i8" if fits else "fp64"
-        return "fp64_i8" if (fits and n >= self.I8_MIN_CELLS) else "fp64"
+        big = n >= self.I8_MIN_CELLS and float(n) * n * p >= self.I8_MIN_WORK
+        return "fp64_i8" if (fits and big) else "fp64"
 
     def __init__(self, x, d=None, metric="cosine", use_pdist=True,
                  sids=None, fids=None, nprocs=None):

@@ -50,8 +50,15 @@ def c1():
     sdm = SampleDistanceMatrix(x, metric="correlation")
     _, t_d = wall(lambda: sdm._d)
     _, t_lut = wall(lambda: sdm.s_knn_ind_lut(k))
+    cells = dev.Cells.from_dense(dev.to_device(x), "correlation")
+    d = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    k_dmma = ev(lambda: cells.pdist_symmetric(out=d, precision="fp64"))
+    k_i8 = ev(lambda: cells.pdist_symmetric(out=d, precision="fp64_i8"))
+    cells.close()
     return {"config": "C1 3005x19972 correlation + s_knn_ind_lut(15)",
-            "d_ms_incl_h2d_d2h": round(t_d, 2), "lut_ms": round(t_lut, 2)}
+            "d_ms_incl_h2d_d2h": round(t_d, 2), "lut_ms": round(t_lut, 2),
+            "d_kernel_ms_dmma": round(k_dmma, 3), "d_kernel_ms_int8_split": round(k_i8, 3),
+            "gram_kernel_of_the_api_call": sdm._gram_precision()}
 
 
 def c2():
@@ -61,9 +68,15 @@ def c2():
     _, t_knn = wall(lambda: sdm.s_knns(k))
     conn, t_conn = wall(lambda: sdm.s_knn_connectivity_matrix(k))
     _, t_aff = wall(lambda: SampleDistanceMatrix.knn_conn_mat_to_aff_edges(conn))
+    cells = sdm._cells("cosine")
+    d = sdm._d_dev
+    k_dmma = ev(lambda: cells.pdist_symmetric(out=d, precision="fp64"), 2)
+    k_i8 = ev(lambda: cells.pdist_symmetric(out=d, precision="fp64_i8"), 2)
     return {"config": "C2 CSR 20000x20000 (10% nnz) cosine + kNN graph k=15",
             "nnz": int(xs.nnz), "first_s_knns_ms_incl_prep_and_D": round(t_knn, 2),
-            "connectivity_ms": round(t_conn, 2), "affinity_edges_ms": round(t_aff, 2)}
+            "connectivity_ms": round(t_conn, 2), "affinity_edges_ms": round(t_aff, 2),
+            "d_kernel_ms_dmma": round(k_dmma, 2), "d_kernel_ms_int8_split": round(k_i8, 2),
+            "gram_kernel_of_the_api_call": sdm._gram_precision()}
 
 
 def c3():
@@ -75,6 +88,9 @@ def c3():
     cells = dev.Cells.from_dense(xt, "euclidean")
     d = cells.pdist_symmetric()
     out["d_symmetric_ms"] = round(ev(lambda: cells.pdist_symmetric(out=d), 1), 2)
+    out["d_symmetric_int8_split_ms"] = round(
+        ev(lambda: cells.pdist_symmetric(out=d, precision="fp64_i8"), 1), 2)
+    cells.pdist_symmetric(out=d)
     idx, dist = dev.knn_from_d(d, k, EXCLUDE_FIRST)
     alive = torch.ones(n, dtype=torch.uint8, device="cuda")
     alive[::7] = 0
