@@ -336,7 +336,8 @@ def run_b200(a):
     import torch.distributed as dist
     from scedar_b200 import _capi, synth
     from scedar_b200._capi import EXCLUDE_FIRST
-    from scedar_b200.stripes import StripedDistanceMatrix, partition
+    from scedar_b200.stripes import (I8_PRECISIONS, StripedDistanceMatrix,
+                                     partition)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -368,10 +369,17 @@ def run_b200(a):
     peers = None
     if world > 1:
         from scedar_b200.device import PeerStripes
-        peers = PeerStripes(partition(n, world), n, rank=rank)
+        peers = PeerStripes(partition(n, world), n, rank=rank,
+                            blockmin=a.precision in I8_PRECISIONS)
         d_buf = peers.tensor(rank)
     else:
         d_buf = torch.empty((r1 - r0, n), dtype=torch.float64, device=dev)
+    # block minima of D (a by-product of the INT8 split kernel; the selection
+    # reads them instead of the whole matrix)
+    bmin_buf = None
+    if world == 1 and a.precision in I8_PRECISIONS:
+        from scedar_b200.device import new_blockmin
+        bmin_buf = new_blockmin(r1 - r0, n)
     idx_host = torch.empty((n, k), dtype=torch.int64).pin_memory()
     dist_host = torch.empty((n, k), dtype=torch.float64).pin_memory()
     phase_events = []
@@ -393,7 +401,7 @@ def run_b200(a):
             ev[1].record()
         if trace:
             trace.append(time.perf_counter())
-        sdm.compute_d(out=d_buf, peers=peers)              # K2
+        sdm.compute_d(out=d_buf, peers=peers, bmin=bmin_buf)   # K2
         if ev:
             ev[2].record()
         if trace:
@@ -479,7 +487,8 @@ def run_b200(a):
             # on a copy stream, each range is prepared and the rows of the
             # lower triangle it completes are contracted at once
             sdm = StripedDistanceMatrix.from_host(x_host, a.metric, out=d_buf,
-                                                  x_dev=x_dev, precision=prec)
+                                                  x_dev=x_dev, precision=prec,
+                                                  bmin=bmin_buf)
             idx, dd = sdm.knn(k, EXCLUDE_FIRST)
             sdm.close()
         elif pipelined:

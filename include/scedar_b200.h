@@ -258,6 +258,26 @@ int scedar_knn_from_d(const double* d, int64_t ldd, int64_t n_cols,
                       int64_t row_begin, int64_t row_end, int k, int exclude,
                       int64_t* idx_out, double* dist_out, void* stream);
 
+/* Block minima, an optional by-product of the INT8 split launches
+ * (SCEDAR_PRECISION_FP64_I8 / _I8S6): while a tile of D is in registers the
+ * kernel also stores the minimum of every aligned run of 32 entries of each
+ * row, and the selection below then reads n/32 minima plus the ~k+1 runs that
+ * can hold a neighbour instead of the whole row (same lists, bit for bit).
+ * stripe_bmin[r] is the buffer of output stripe r -- the stripes of the launch
+ * that follows: one for the single-device forms, `world` for the peer-store
+ * forms -- laid out [rows of the stripe][ldb], ldb >= ceil(n / 32), row 0 =
+ * first row of the stripe.  world = 0 detaches the buffers. */
+int scedar_cells_set_blockmin(scedar_cells_t* cells, double* const* stripe_bmin,
+                              int world, int64_t ldb);
+/* scedar_knn_from_d over rows that an INT8 split launch on `cells` has written
+ * together with their block minima (an error if none has since
+ * scedar_cells_set_blockmin).  bmin: [(row_end-row_begin), ldb]. */
+int scedar_knn_from_d_blockmin(const scedar_cells_t* cells, const double* d,
+                               int64_t ldd, const double* bmin, int64_t ldb,
+                               int64_t row_begin, int64_t row_end, int k,
+                               int exclude, int64_t* idx_out, double* dist_out,
+                               void* stream);
+
 /* ------------------------------------------------------------------------
  * Full stable sort of every column of a symmetric D (sdm.py:1289-1305,
  * np.sort / np.argsort(kind="mergesort", axis=0)).  Column j of a symmetric D

@@ -70,6 +70,10 @@ SIGNATURES = {
                                   c_int64, c_void_p, c_void_p, c_void_p]),
     "scedar_knn_from_d": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64,
                                   c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "scedar_cells_set_blockmin": (c_int, [c_void_p, c_void_p, c_int, c_int64]),
+    "scedar_knn_from_d_blockmin": (c_int, [c_void_p, c_void_p, c_int64, c_void_p,
+                                           c_int64, c_int64, c_int64, c_int, c_int,
+                                           c_void_p, c_void_p, c_void_p]),
     "scedar_col_sort": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                 c_void_p, c_void_p]),
     "scedar_num_correct_dist_mat": (c_int, [c_void_p, c_int64, c_int64, c_int,

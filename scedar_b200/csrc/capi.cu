@@ -483,6 +483,43 @@ int scedar_knn_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row_
                             static_cast<cudaStream_t>(stream));
 }
 
+int scedar_cells_set_blockmin(scedar_cells_t* c, double* const* stripe_bmin, int world,
+                              int64_t ldb) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells is NULL");
+  if (world < 0 || world > 16) return fail(SCEDAR_ERR_ARG, "world must be in 0..16");
+  if (world > 0) {
+    if (!stripe_bmin) return fail(SCEDAR_ERR_ARG, "NULL buffer table");
+    if (ldb < (c->n + 31) / 32) return fail(SCEDAR_ERR_ARG, "ldb must be >= ceil(n / 32)");
+    for (int r = 0; r < world; ++r)
+      if (!stripe_bmin[r]) return fail(SCEDAR_ERR_ARG, "NULL block-minima buffer");
+  }
+  for (int r = 0; r < 16; ++r) c->bmin[r] = r < world ? stripe_bmin[r] : nullptr;
+  c->bmin_count = world;
+  c->bmin_ld = world > 0 ? ldb : 0;
+  c->bmin_filled = false;
+  return SCEDAR_OK;
+}
+
+int scedar_knn_from_d_blockmin(const scedar_cells_t* c, const double* d, int64_t ldd,
+                               const double* bmin, int64_t ldb, int64_t row_begin,
+                               int64_t row_end, int k, int exclude, int64_t* idx_out,
+                               double* dist_out, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells is NULL");
+  SCEDAR_CHECK(check_rows(c, row_begin, row_end));
+  if (k < 0 || k > c->n - 1) return fail(SCEDAR_ERR_ARG, "k should >= 0 and <= n_samples-1");
+  if (exclude != SCEDAR_EXCLUDE_FIRST && exclude != SCEDAR_EXCLUDE_SELF)
+    return fail(SCEDAR_ERR_ARG, "exclude must be 0 (first) or 1 (self)");
+  if (k == 0 || row_end == row_begin) return SCEDAR_OK;
+  if (!d || !bmin || !idx_out || !dist_out) return fail(SCEDAR_ERR_ARG, "NULL buffer");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (ldb < (c->n + 31) / 32) return fail(SCEDAR_ERR_ARG, "ldb must be >= ceil(n / 32)");
+  if (!c->bmin_filled)
+    return fail(SCEDAR_ERR_ARG,
+                "no INT8 split launch has written block minima for this handle");
+  return launch_topk_blockmin(d, ldd, c->n, bmin, ldb, row_begin, row_end, k, exclude, idx_out,
+                              dist_out, static_cast<cudaStream_t>(stream));
+}
+
 int scedar_knn_stripe(const scedar_cells_t* c, int precision, int k, int exclude,
                       int64_t row_begin, int64_t row_end, int64_t* idx_out, double* dist_out,
                       void* stream) {

@@ -67,6 +67,13 @@ struct scedar_cells {
   cudaStream_t stream = nullptr;  // creation stream: the frees are ordered on it
   void* fast = nullptr;  // FastState of the tensor-core path (gram_tc.cu), lazy
   void* oz = nullptr;    // OzState of the INT8 split path (gram_oz.cu), lazy
+  // optional by-product of the INT8 split launches: per output stripe, the
+  // minimum of every aligned run of 32 entries of each row of D
+  // ([rows of the stripe][bmin_ld]); consumed by launch_topk_blockmin
+  double* bmin[16] = {nullptr};
+  int bmin_count = 0;
+  int64_t bmin_ld = 0;
+  bool bmin_filled = false;
   CUtensorMap xmap;      // TMA view of xw: boxes of 128 rows x 16 doubles, 128B swizzle
 };
 
@@ -149,6 +156,9 @@ int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols,
                        int64_t row_begin, int64_t row_end, int k, int exclude,
                        int64_t* idx_out, double* dist_out, cudaStream_t s,
                        const int64_t* row_ids = nullptr, int64_t out_base = 0);
+int launch_topk_blockmin(const double* d, int64_t ldd, int64_t n_cols, const double* bmin,
+                         int64_t ldb, int64_t row_begin, int64_t row_end, int k, int exclude,
+                         int64_t* idx_out, double* dist_out, cudaStream_t s);
 int launch_topk_merge(const double* part_d, const int32_t* part_i, int splits,
                       int64_t rows, int K, int64_t row_begin, int k,
                       int exclude, int64_t* idx_out, double* dist_out,

@@ -93,7 +93,12 @@ constexpr int B_SLAB = ON * OKB;   // 8 KB
 // as the MMAs of its slice have retired (the MMA loop runs slice-major), and
 // TWO slabs of column-tile slices (all S are needed from the first slice on)
 constexpr int OZ_BAR_BYTES = 256;
-constexpr int oz_smem(int S) { return 1024 + S * A_SLAB + 2 * S * B_SLAB + OZ_BAR_BYTES; }
+// per-tile column constants staged for the epilogue: {hi, lo} and {sc, stat} of
+// the tile's 64 columns (16 bytes per column each)
+constexpr int OZ_CST_BYTES = 2 * ON * 16;
+constexpr int oz_smem(int S) {
+  return S * A_SLAB + 2 * S * B_SLAB + OZ_BAR_BYTES + OZ_CST_BYTES;
+}
 static_assert(oz_smem(6) <= 227 * 1024 && oz_smem(7) <= 227 * 1024, "shared memory budget");
 constexpr int OZ_EPI_WARPS = 8;
 constexpr int OZ_EPI_THREADS = 32 * OZ_EPI_WARPS;
@@ -131,6 +136,11 @@ struct OzArgs {
   int world;                              // output stripes (1 for a single buffer)
   int64_t stripe_begin[kOzPeers + 1];     // row ranges of the stripes
   double* stripe_ptr[kOzPeers];
+  // block minima for the top-k that follows (optional): bmin[r][row - begin_r][b]
+  // = min of D[row][32 b .. 32 b + 31]; same stripe table as D
+  double* bmin_ptr[kOzPeers];
+  int64_t ldb;
+  int skip;     // EXPERIMENT
 };
 
 // weighted sum of the diagonal accumulators minus the offset terms -> float64
@@ -270,10 +280,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const OzArgs a) {
   constexpr int A_STAGE = S * A_SLAB, B_STAGE = S * B_SLAB;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - raw);
+  if (raw & 1023u) __trap();        // the 128B-swizzled slabs need 1024-byte alignment
+  const uint32_t base = raw;
+  uint8_t* gbase = smem_raw;
   const uint32_t ring_a = base, ring_b = base + A_STAGE;
   const uint32_t bars = ring_b + 2 * B_STAGE;
   // barrier slots (8 bytes each): fullA[S], emptyA[S], fullB[2], emptyB[2], tfull, tempty
@@ -281,6 +292,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                  tfull = bars + 160, tempty = bars + 168;
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(gbase + (bars - base) + 192);
+  const uint32_t cst = bars + OZ_BAR_BYTES;     // column constants (epilogue warps)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = a.kslabs;
 
@@ -332,6 +344,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int sl = 0; sl < S; ++sl) {
           mbar_wait(empty_a + 8 * sl, (uint32_t)((it & 1) ^ 1));
+          if (a.skip & 32) { mbar_arrive(full_a + 8 * sl); continue; }
           mbar_expect_tx(full_a + 8 * sl, A_SLAB);
           tma_load_2d(ring_a + sl * A_SLAB, &map_a, ks * OKB, (int)(sl * a.n_pl) + i0,
                       full_a + 8 * sl);
@@ -342,6 +355,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         coords(it, i0, j0, ks);
         const uint32_t buf = (uint32_t)(it & 1), ph = (uint32_t)((it >> 1) & 1);
         mbar_wait(empty_b + 8 * buf, ph ^ 1);
+        if (a.skip & 32) { mbar_arrive(full_b + 8 * buf); return; }
         mbar_expect_tx(full_b + 8 * buf, B_STAGE);
         const uint32_t st = ring_b + buf * B_STAGE;
 #pragma unroll
@@ -396,7 +410,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int run = S - sl;
               const int first = run <= kFullRun ? run : (run + 1) / 2;
               const uint32_t acc = (kc | kk | sl) != 0;
-              if (el) {
+              if (el && !(a.skip & 16)) {
                 tc::mma_i8(tmem_base + (uint32_t)(sl * ON), da + (uint64_t)((kk * 32) >> 4),
                            db + (uint64_t)((kk * 32) >> 4), tc::idesc_u8(ON * first), acc);
                 if (run > first)
@@ -430,8 +444,44 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t tcount = 0;
     long long e_wait = 0, e_p1 = 0, e_p2 = 0;
+    // The constants of the tile's 64 columns -- {hi, lo} of the current K chunk and
+    // {sc, stat} -- are staged in shared memory once per tile by the 256 epilogue
+    // threads (one value each) and read back as 16-byte broadcasts: fetched per
+    // entry from global memory they were the epilogue's main stall.  The next
+    // tile's descriptor and constant are fetched a tile ahead.
+    const int e_tid = threadIdx.x - 64;       // 0..255
+    const int st_col = e_tid & 63, st_kind = e_tid >> 6;   // 0 hi, 1 lo, 2 sc, 3 stat
+    const uint32_t st_addr = cst + (uint32_t)((st_kind >> 1) * (ON * 16) + st_col * 16 +
+                                              (st_kind & 1) * 8);
+    auto fetch_const = [&](int64_t j0, int ch) -> unsigned long long {
+      const int64_t gj = j0 + st_col;         // < n_pl: the arrays cover the padding
+      if (st_kind == 0) return (unsigned long long)__ldg(a.hi + gj * a.n_chunks + ch);
+      if (st_kind == 1) return (unsigned long long)__ldg(a.lo + gj * a.n_chunks + ch);
+      return (unsigned long long)__double_as_longlong(
+          __ldg((st_kind == 2 ? a.sc : a.stat) + gj));
+    };
+    auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto put_const = [&](unsigned long long v) {
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(st_addr), "l"(v) : "memory");
+    };
+    auto col_pair = [&](uint32_t table, int col, unsigned long long& x, unsigned long long& y) {
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];"
+                   : "=l"(x), "=l"(y)
+                   : "r"(cst + table * (ON * 16) + (uint32_t)col * 16));
+    };
+    OzTile tl_next{0, 0, 0, 0};
+    unsigned long long pre = 0;
+    if ((int)blockIdx.x < a.n_tiles) {
+      tl_next = a.tiles[blockIdx.x];
+      pre = fetch_const((int64_t)tl_next.J * ON, 0);
+    }
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-      const OzTile tl = a.tiles[t];
+      const OzTile tl = tl_next;
+      epi_sync();                             // the last tile's constants are done with
+      put_const(pre);
+      epi_sync();
+      const bool more = t + (int)gridDim.x < a.n_tiles;
+      if (more) tl_next = a.tiles[t + gridDim.x];
       const int64_t i0 = (int64_t)tl.I * OM, j0 = (int64_t)tl.J * ON;
       const int64_t gi = i0 + r;
       const bool row_ok = gi < a.n;
@@ -451,6 +501,16 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           a.stripe_ptr[om] + (j0 + h * 32 - a.stripe_begin[om]) * a.ldd + gi;
       const bool direct = (tl.flags & TILE_DIRECT) && gi >= a.row_lo && gi < a.row_hi;
       const bool mirror = (tl.flags & TILE_MIRROR) && row_ok;
+      // block minima: this thread's 32 entries are block (j0 + 32 h) / 32 of row gi;
+      // column c of the mirrored tile is row j0 + c, whose block (i0 + 32 q) / 32
+      // is the minimum over this warp's 32 rows
+      double* __restrict__ bm_row = nullptr;
+      double* __restrict__ bm_col = nullptr;
+      if (a.bmin_ptr[0]) {
+        bm_row = a.bmin_ptr[od] + (gi - a.stripe_begin[od]) * a.ldb + (j0 >> 5) + h;
+        bm_col = a.bmin_ptr[om] + (j0 + h * 32 - a.stripe_begin[om]) * a.ldb + (i0 >> 5) + q;
+      }
+      double rmin = pos_inf();
 
       // phase 1, once per K chunk: drain the accumulators into raw dot products
       // held in registers (32 per thread), four columns at a time, the next four
@@ -458,9 +518,6 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // chunk's / tile's MMAs run under the rest
       double pv[32];
       long long ec0 = 0, ec1 = 0;
-      // column constants of chunk `ch`: stride n_chunks from (gj, ch)
-      const long long* __restrict__ hi_col = a.hi + (j0 + h * 32) * a.n_chunks;
-      const long long* __restrict__ lo_col = a.lo + (j0 + h * 32) * a.n_chunks;
       auto phase1 = [&](int ch, auto first_chunk) {
         constexpr bool kFirst = decltype(first_chunk)::value;
         ec0 = a.dbg ? clock64() : 0;
@@ -490,8 +547,9 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               uint32_t acc[S];
 #pragma unroll
               for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
-              val = oz_value<S>(acc, hic + __ldg(hi_col + c * a.n_chunks + ch),
-                                loc + __ldg(lo_col + c * a.n_chunks + ch));
+              unsigned long long chi, clo;
+              col_pair(0, h * 32 + c, chi, clo);
+              val = oz_value<S>(acc, hic + (long long)chi, loc + (long long)clo);
             }
             pv[c] = kFirst ? val : __dadd_rn(pv[c], val);
           }
@@ -514,7 +572,16 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ++tcount;
       };
       phase1(0, std::true_type{});
-      for (int ch = 1; ch < a.n_chunks; ++ch) phase1(ch, std::false_type{});
+      for (int ch = 1; ch < a.n_chunks; ++ch) {
+        // the next chunk's {hi, lo} replace the current ones
+        const unsigned long long v = st_kind < 2 ? fetch_const(j0, ch) : 0ull;
+        epi_sync();
+        if (st_kind < 2) put_const(v);
+        epi_sync();
+        phase1(ch, std::false_type{});
+      }
+      // next tile's constant: in flight under phase 2
+      if (more) pre = fetch_const((int64_t)tl_next.J * ON, 0);
       long long ec2 = a.dbg ? clock64() : 0;
       // phase 2 (under the next tile's MMAs): metric epilogue and the two stores.
       // The mirrored tile is written straight from the registers -- lanes are
@@ -528,14 +595,38 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int64_t gj = j0 + h * 32 + c;
           dv[cc] = 0.0;
           if (gj < a.n) {
-            const double stj = __ldg(a.stat + gj);
+            unsigned long long csc = 0x3ff0000000000000ull, cst_j = 0x3ff0000000000000ull;
+            if (!(a.skip & 4)) col_pair(1, h * 32 + c, csc, cst_j);
+            const double stj = __longlong_as_double((long long)cst_j);
             const bool lower = gi >= gj;
-            const double P = __dmul_rn(pv[c], __dmul_rn(sci, __ldg(a.sc + gj)));
-            dv[cc] = finish_entry(P, lower ? sti : stj, lower ? stj : sti, gi == gj, a.euclid);
-            if (mirror && gj >= a.row_lo && gj < a.row_hi) __stcs(mcol + (int64_t)c * a.ldd, dv[cc]);
+            const double P = __dmul_rn(
+                pv[c], __dmul_rn(sci, __longlong_as_double((long long)csc)));
+            dv[cc] = (a.skip & 8) ? P : finish_entry(P, lower ? sti : stj, lower ? stj : sti, gi == gj, a.euclid);
+            if (mirror && !(a.skip & 2) && gj >= a.row_lo && gj < a.row_hi) __stcs(mcol + (int64_t)c * a.ldd, dv[cc]);
+            rmin = fmin(rmin, dv[cc]);
           }
         }
-        if (direct) {
+        if (bm_col && (tl.flags & TILE_MIRROR)) {
+          // minima of these four columns over the warp's 32 rows (= one block of
+          // four rows of D each): a halving exchange -- after two steps every
+          // lane holds one column's partial minimum, three more finish it
+          double w[4];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            w[cc] = (row_ok && j0 + h * 32 + c0 + cc < a.n) ? dv[cc] : pos_inf();
+          const bool b4 = lane & 16, b3 = lane & 8;
+          double k0 = b4 ? w[2] : w[0], k1 = b4 ? w[3] : w[1];
+          k0 = fmin(k0, __shfl_xor_sync(0xffffffffu, b4 ? w[0] : w[2], 16));
+          k1 = fmin(k1, __shfl_xor_sync(0xffffffffu, b4 ? w[1] : w[3], 16));
+          double m = fmin(b3 ? k1 : k0, __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8));
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+          const int c = c0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);
+          const int64_t gj = j0 + h * 32 + c;
+          if ((lane & 7) == 0 && gj < a.n && gj >= a.row_lo && gj < a.row_hi && i0 + q * 32 < a.n)
+            bm_col[(int64_t)c * a.ldb] = m;
+        }
+        if (direct && !(a.skip & 1)) {
           const int64_t gj0 = j0 + h * 32 + c0;
           if (a.vec_ok && gj0 + 3 < a.n) {
             st_cs_v4(drow + c0, dv[0], dv[1], dv[2], dv[3]);
@@ -546,6 +637,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      if (bm_row && direct && j0 + h * 32 < a.n) *bm_row = rmin;
       if (a.dbg) e_p2 += clock64() - ec2;
     }
     if (a.dbg && threadIdx.x == 64) {
@@ -752,6 +844,15 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s, int 
     SCEDAR_CUDA(cudaMemsetAsync(dbg.ptr, 0, sizeof(unsigned long long) * 8 * num_sms(), s));
     a.dbg = dbg.as<unsigned long long>();
   }
+  // block minima ride along when the handle holds one buffer per output stripe
+  for (int r = 0; r < kOzPeers; ++r) a.bmin_ptr[r] = nullptr;
+  a.ldb = 0;
+  if (c->bmin_count == a.world && c->bmin_count > 0) {
+    for (int r = 0; r < a.world; ++r) a.bmin_ptr[r] = c->bmin[r];
+    a.ldb = c->bmin_ld;
+    const_cast<scedar_cells*>(c)->bmin_filled = true;
+  }
+  a.skip = getenv("SCEDAR_B200_OZ_SKIP") ? atoi(getenv("SCEDAR_B200_OZ_SKIP")) : 0;
   a.vec_ok = a.ldd % 4 == 0;
   for (int r = 0; r < a.world; ++r)
     if (reinterpret_cast<uintptr_t>(a.stripe_ptr[r]) % 32 != 0) a.vec_ok = 0;

@@ -56,6 +56,72 @@ topk_from_d_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols,
   L.emit(K, exclude, (int)self, idx_out + orow * k, dist_out + orow * k, lane);
 }
 
+// Selection from D with the block minima the INT8 split Gram kernel leaves
+// behind (min of every aligned run of 32 entries of a row): the k+1 smallest
+// entries of a row lie in runs whose minimum is <= the (k+1)-th smallest run
+// minimum t (k+1 different entries are <= t, so the (k+1)-th smallest entry is
+// too, and every entry that small sits in a run with minimum <= t -- ties
+// included).  Pass 1 finds t from the n/32 minima, pass 2 reads only those
+// runs of D: 8*n/32 + ~(k+1)*256 bytes per row instead of 8*n.
+template <int R>
+__global__ void __launch_bounds__(256)
+topk_blockmin_kernel(const double* __restrict__ d, int64_t ldd, int64_t n_cols,
+                     const double* __restrict__ bmin, int64_t ldb, int64_t row_begin,
+                     int64_t rows, int k, int exclude, int64_t* __restrict__ idx_out,
+                     double* __restrict__ dist_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int K = k + 1;
+  const int64_t nb = (n_cols + 31) / 32;
+  const double* __restrict__ mrow = bmin + row * ldb;
+  double t;
+  {
+    WarpList<R> M;
+    M.init();
+    constexpr int U = 4;
+    for (int64_t base = 0; base < nb; base += 32 * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = base + u * 32 + lane;
+        v[u] = b < nb ? __ldg(mrow + b) : pos_inf();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = base + u * 32 + lane;
+        M.offer(v[u], (int)b, b < nb, K, lane);
+      }
+    }
+    t = M.td;      // +inf while fewer than k+1 runs: everything is read
+  }
+  const double* __restrict__ src = d + row * ldd;
+  WarpList<R> L;
+  L.init();
+  for (int64_t base = 0; base < nb; base += 32) {
+    const int64_t b = base + lane;
+    const double m = b < nb ? __ldg(mrow + b) : pos_inf();
+    unsigned take = __ballot_sync(0xffffffffu, b < nb && m <= t);
+    while (take) {
+      // up to four runs in flight
+      int64_t c[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        c[u] = -1;
+        if (take) {
+          c[u] = (base + __ffs(take) - 1) * 32 + lane;
+          take &= take - 1;
+        }
+        v[u] = (c[u] >= 0 && c[u] < n_cols) ? __ldcs(src + c[u]) : pos_inf();
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) L.offer(v[u], (int)c[u], c[u] >= 0 && c[u] < n_cols, K, lane);
+    }
+  }
+  L.emit(K, exclude, (int)(row_begin + row), idx_out + row * k, dist_out + row * k, lane);
+}
+
 template <int R>
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const double* __restrict__ part_d, const int32_t* __restrict__ part_i,
@@ -194,6 +260,26 @@ int launch_topk_from_d(const double* d, int64_t ldd, int64_t n_cols, int64_t row
     topk_from_d_kernel<2><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out, row_ids, out_base);
   else if (K <= 32 * kMaxR)
     topk_from_d_kernel<4><<<grid, 256, 0, s>>>(d, ldd, n_cols, row_begin, rows, k, exclude, idx_out, dist_out, row_ids, out_base);
+  else
+    return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
+  SCEDAR_CUDA(cudaGetLastError());
+  count_launch();
+  return SCEDAR_OK;
+}
+
+int launch_topk_blockmin(const double* d, int64_t ldd, int64_t n_cols, const double* bmin,
+                         int64_t ldb, int64_t row_begin, int64_t row_end, int k, int exclude,
+                         int64_t* idx_out, double* dist_out, cudaStream_t s) {
+  const int64_t rows = row_end - row_begin;
+  if (rows <= 0 || k == 0) return SCEDAR_OK;
+  const int K = k + 1;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (K <= 32)
+    topk_blockmin_kernel<1><<<grid, 256, 0, s>>>(d, ldd, n_cols, bmin, ldb, row_begin, rows, k, exclude, idx_out, dist_out);
+  else if (K <= 64)
+    topk_blockmin_kernel<2><<<grid, 256, 0, s>>>(d, ldd, n_cols, bmin, ldb, row_begin, rows, k, exclude, idx_out, dist_out);
+  else if (K <= 32 * kMaxR)
+    topk_blockmin_kernel<4><<<grid, 256, 0, s>>>(d, ldd, n_cols, bmin, ldb, row_begin, rows, k, exclude, idx_out, dist_out);
   else
     return fail(SCEDAR_ERR_UNSUPPORTED, "k+1 > 128: use scedar_col_sort");
   SCEDAR_CUDA(cudaGetLastError());

@@ -146,6 +146,34 @@ class Cells(object):
         except Exception:
             pass
 
+    # -- block minima (by-product of the INT8 split launches) ----------------
+    def set_blockmin(self, bufs, ldb=None):
+        """Attach one block-minima buffer per output stripe of the launches
+        that follow (tensors [rows, ldb] or raw device pointers); ``None`` /
+        empty detaches.  Only the INT8 split kernels fill them."""
+        bufs = list(bufs or [])
+        ptrs = [b.data_ptr() if torch.is_tensor(b) else int(b) for b in bufs]
+        if bufs and ldb is None:
+            ldb = bufs[0].stride(0)
+        table = (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs)
+        _capi.check(_capi.load().scedar_cells_set_blockmin(
+            self._h, table, len(ptrs), int(ldb or 0)))
+        self._bmin_keep = bufs          # the handle holds raw pointers
+
+    def knn_from_d_blockmin(self, d, bmin, k, exclude=EXCLUDE_SELF, row_begin=0):
+        """``knn_from_d`` of rows that an INT8 split launch of this handle wrote
+        together with their block minima ``bmin`` [rows, ldb]: reads n / 32
+        minima and the few runs of 32 entries that can hold a neighbour."""
+        rows, n = d.shape
+        assert n == self.n and bmin.shape[0] == rows
+        idx = torch.empty((rows, k), dtype=torch.int64, device="cuda")
+        dist = torch.empty((rows, k), dtype=torch.float64, device="cuda")
+        _capi.check(_capi.load().scedar_knn_from_d_blockmin(
+            self._h, _ptr(d), d.stride(0) if rows > 1 else n, _ptr(bmin),
+            bmin.stride(0) if rows > 1 else bmin.shape[1], row_begin,
+            row_begin + rows, k, exclude, _ptr(idx), _ptr(dist), _stream()))
+        return idx, dist
+
     # -- distance matrix ----------------------------------------------------
     def pdist_stripe(self, row_begin=0, row_end=None, out=None,
                      precision="fp64"):
@@ -231,6 +259,16 @@ class Cells(object):
         return idx, dist
 
 
+def blockmin_ld(n):
+    """Row stride of a block-minima buffer: ceil(n / 32) rounded up to 4."""
+    return ((n + 31) // 32 + 3) // 4 * 4
+
+
+def new_blockmin(rows, n):
+    return torch.empty((max(rows, 0), blockmin_ld(n)), dtype=torch.float64,
+                       device="cuda")
+
+
 def knn_from_d(d, k, exclude=EXCLUDE_SELF, row_begin=0):
     """Top-k of every row of a materialised stripe ``d`` [rows, n]; row r is
     cell ``row_begin + r``."""
@@ -313,20 +351,25 @@ class PeerStripes(object):
     (single-process emulation of the N ranks on one GPU, used by the tests).
     """
 
-    def __init__(self, stripes, n, rank=None, group=None):
+    def __init__(self, stripes, n, rank=None, group=None, blockmin=False):
+        """``blockmin``: every stripe is followed, in the same allocation, by its
+        block-minima buffer [rows, ldb] (``Cells.set_blockmin``)."""
         _guard()
         import torch.distributed as dist
         self.lib = _capi.load()
         self.stripes, self.n, self.rank = list(stripes), int(n), rank
         self.world = len(self.stripes)
+        self.blockmin = bool(blockmin)
+        self.ldb = blockmin_ld(self.n)
         self.ptrs = [None] * self.world
         self._own, self._opened = [], []
         mine = range(self.world) if rank is None else [rank]
         for r in mine:
             b, e = self.stripes[r]
             p = ctypes.c_void_p()
+            extra = max(e - b, 0) * self.ldb * 8 if self.blockmin else 0
             _capi.check(self.lib.scedar_stripe_alloc(
-                max(e - b, 0) * self.n * 8, ctypes.byref(p)))
+                max(e - b, 0) * self.n * 8 + extra, ctypes.byref(p)))
             self.ptrs[r] = p.value
             self._own.append(p.value)
         if rank is not None and self.world > 1:
@@ -352,6 +395,20 @@ class PeerStripes(object):
             return torch.empty((0, self.n), dtype=torch.float64, device="cuda")
         return torch.as_tensor(_RawCuda(self.ptrs[r], (e - b, self.n), self),
                                device="cuda")
+
+    def bmin_ptrs(self):
+        """Device pointers of the stripes' block-minima buffers."""
+        assert self.blockmin
+        return [p + max(e - b, 0) * self.n * 8
+                for p, (b, e) in zip(self.ptrs, self.stripes)]
+
+    def bmin_tensor(self, r=None):
+        r = self.rank if r is None else r
+        b, e = self.stripes[r]
+        if e - b == 0:
+            return torch.empty((0, self.ldb), dtype=torch.float64, device="cuda")
+        return torch.as_tensor(
+            _RawCuda(self.bmin_ptrs()[r], (e - b, self.ldb), self), device="cuda")
 
     def tables(self):
         begins = [b for b, _ in self.stripes] + [self.stripes[-1][1]]
@@ -577,7 +634,7 @@ def upload_ranges(n, first=2048):
 
 
 def pdist_symmetric_from_host(x_host, metric, out=None, x_dev=None,
-                              precision="fp64"):
+                              precision="fp64", bmin=None):
     """FP64 distance matrix of a pinned HOST matrix with the upload hidden
     behind the contraction: x is copied range by range on a second stream,
     each range is prepared (K1 + diagonal) as it lands and the rows of the
@@ -595,6 +652,8 @@ def pdist_symmetric_from_host(x_host, metric, out=None, x_dev=None,
     copy = _copy_stream()
     copy.wait_stream(main)          # x_dev may still be read by earlier work
     cells = Cells.alloc(n, p, metric)
+    if bmin is not None:            # block minima ride along (INT8 split only)
+        cells.set_blockmin([bmin])
     for b, e in upload_ranges(n):
         with torch.cuda.stream(copy):
             x_dev[b:e].copy_(x_host[b:e], non_blocking=True)

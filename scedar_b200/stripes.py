@@ -17,10 +17,15 @@ path shards by contiguous, tile-aligned row stripes:
 The compute operators are injected (``ops``) so the sharding logic can be
 tested on CPU with the ``gloo`` backend; the default is the CUDA library.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 TILE = 128
+
+
+I8_PRECISIONS = ("fp64_i8", "fp64_i8s6")
 
 
 def partition(n, world):
@@ -113,9 +118,22 @@ class _DeviceOps(object):
         from . import device
         return device.knn_from_d(d, k, exclude, row_begin=row_begin)
 
-    def peer_stripes(self, stripes, n, rank, group):
+    # block minima of the INT8 split launches (device.Cells.set_blockmin);
+    # SCEDAR_B200_BLOCKMIN=0 selects from the whole of D instead (A/B timing)
+    blockmin = os.environ.get("SCEDAR_B200_BLOCKMIN", "1") != "0"
+
+    def new_blockmin(self, rows, n):
         from . import device
-        return device.PeerStripes(stripes, n, rank=rank, group=group)
+        return device.new_blockmin(rows, n)
+
+    def knn_from_d_blockmin(self, cells, d, bmin, k, exclude, row_begin):
+        return cells.knn_from_d_blockmin(d, bmin, k, exclude,
+                                         row_begin=row_begin)
+
+    def peer_stripes(self, stripes, n, rank, group, blockmin=False):
+        from . import device
+        return device.PeerStripes(stripes, n, rank=rank, group=group,
+                                  blockmin=blockmin)
 
     def pdist_stripe_p2p(self, cells, peers, rank, precision="fp64"):
         from . import device
@@ -166,7 +184,7 @@ class StripedDistanceMatrix(object):
 
     @classmethod
     def from_host(cls, x_host, metric="correlation", out=None, x_dev=None,
-                  ops=None, precision="fp64"):
+                  ops=None, precision="fp64", bmin=None):
         """Single-GPU form for a pinned HOST matrix: the upload of x is hidden
         behind the contraction (``device.pdist_symmetric_from_host``); on
         return the cells are prepared and D (float64, symmetric) is already
@@ -184,8 +202,13 @@ class StripedDistanceMatrix(object):
         self.precision = precision
         self.stripes = partition(self.n, 1)
         self.row_begin, self.row_end = self.stripes[0]
+        self.bmin = None
+        if precision in I8_PRECISIONS and getattr(self.ops, "blockmin", False):
+            self.bmin = (bmin if bmin is not None
+                         else self.ops.new_blockmin(self.n, self.n))
         self.cells, self.d_stripe = device.pdist_symmetric_from_host(
-            x_host, metric, out=out, x_dev=x_dev, precision=precision)
+            x_host, metric, out=out, x_dev=x_dev, precision=precision,
+            bmin=self.bmin)
         self.d_device = self.d_stripe.device
         return self
 
@@ -232,6 +255,10 @@ class StripedDistanceMatrix(object):
         comm.wait_stream(main)
         self._fence()              # nobody still reads a stripe of the last step
         self.cells = device.Cells.alloc(n, p, metric)
+        self.bmin = None
+        if peers.blockmin and precision in I8_PRECISIONS:
+            self.cells.set_blockmin(peers.bmin_ptrs(), peers.ldb)
+            self.bmin = peers.bmin_tensor(rank)
         off = 0
         for b, e, m in layout:
             with torch.cuda.stream(copy):
@@ -284,6 +311,7 @@ class StripedDistanceMatrix(object):
         self.row_begin, self.row_end = self.stripes[self.rank]
         self.cells = self.ops.prepare_csr(csr[0], csr[1], csr[2], (n, p), metric)
         self.d_stripe = None
+        self.bmin = None
         return self
 
     def __init__(self, x, metric="correlation", shape=None, group=None,
@@ -312,12 +340,13 @@ class StripedDistanceMatrix(object):
         self.row_begin, self.row_end = self.stripes[self.rank]
         self.cells = self.ops.prepare(x, metric)
         self.d_stripe = None
+        self.bmin = None
 
     @property
     def rows(self):
         return self.row_end - self.row_begin
 
-    def compute_d(self, out=None, peers=None):
+    def compute_d(self, out=None, peers=None, bmin=None):
         """This rank's rows of D, kept in HBM: tensor [rows, n].
 
         With ``peers`` (a ``device.PeerStripes`` shared by all ranks) the
@@ -328,12 +357,25 @@ class StripedDistanceMatrix(object):
         store must have landed before anyone reads."""
         extra = {} if self.precision == "fp64" else {
             "precision": self.precision}
+        # the INT8 split kernels leave the minimum of every run of 32 entries
+        # behind; the selection that follows then skips almost all of D
+        use_bmin = (self.precision in I8_PRECISIONS
+                    and getattr(self.ops, "blockmin", False))
+        self.bmin = None
         if peers is not None and self.world > 1:
+            if use_bmin and getattr(peers, "blockmin", False):
+                self.cells.set_blockmin(peers.bmin_ptrs(), peers.ldb)
+                self.bmin = peers.bmin_tensor(self.rank)
             self._fence()
             self.ops.pdist_stripe_p2p(self.cells, peers, self.rank, **extra)
             self._fence()
             self.d_stripe = peers.tensor(self.rank)
             return self.d_stripe
+        if use_bmin:
+            if bmin is None:
+                bmin = self.ops.new_blockmin(self.rows, self.n)
+            self.cells.set_blockmin([bmin])
+            self.bmin = bmin
         self.d_stripe = self.ops.pdist_stripe(self.cells, self.row_begin,
                                               self.row_end, out=out, **extra)
         return self.d_stripe
@@ -347,7 +389,11 @@ class StripedDistanceMatrix(object):
         dist.all_reduce(self._flag, group=self.group)
 
     def make_peer_stripes(self):
-        """Allocate this rank's peer-mappable D stripe and map the others."""
+        """Allocate this rank's peer-mappable D stripe (followed by its block
+        minima when the INT8 split kernels run) and map the others."""
+        if self.precision in I8_PRECISIONS and getattr(self.ops, "blockmin", False):
+            return self.ops.peer_stripes(self.stripes, self.n, self.rank,
+                                         self.group, blockmin=True)
         return self.ops.peer_stripes(self.stripes, self.n, self.rank,
                                      self.group)
 
@@ -358,6 +404,10 @@ class StripedDistanceMatrix(object):
         if from_d:
             if self.d_stripe is None:
                 self.compute_d()
+            if self.bmin is not None:
+                return self.ops.knn_from_d_blockmin(
+                    self.cells, self.d_stripe, self.bmin, k, exclude,
+                    self.row_begin)
             return self.ops.knn_from_d(self.d_stripe, k, exclude,
                                        self.row_begin)
         if precision == "fp64":

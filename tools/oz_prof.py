@@ -16,6 +16,9 @@ torch.cuda.set_device(0)
 x = torch.from_numpy(synth.log_counts(n, p, seed=n)).cuda()
 cells = dev.Cells.from_dense(x, "correlation")
 d = torch.empty((n, n), dtype=torch.float64, device="cuda")
+if os.environ.get("OZ_PROF_BLOCKMIN"):          # block minima ride along
+    bmin = dev.new_blockmin(n, n)
+    cells.set_blockmin([bmin])
 ts = []
 for _ in range(reps):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../scedar_b200/csrc/ptx_sm100.cuh"
@@ -452,6 +453,151 @@ static void run_rate2(int N, int mode, const char* what) {
   cudaFree(out);
 }
 
+// ---- contend: what does a busy tensor pipe cost the other warps of the SM? ----
+// Warp 0 issues the stacked S = 7 schedule (mode 2 of rate2) back to back while 8
+// more warps -- the epilogue warps of gram_oz.cu -- run a loop of one kind of
+// instruction, 4 independent chains per thread, and time themselves.
+//   work 0 none  1 DFMA  2 FFMA  3 IMAD  4 LDS (broadcast)  5 SHFL  6 STG  7 DMUL+DSETP
+template <int work>
+__global__ void __launch_bounds__(288, 1)
+contend_kernel(int with_mma, int iters, int witers, double* sink,
+               unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  const uint32_t sa = base, sb = base + 7 * 8192;
+  const uint32_t bars = sb + 16 * 4096;
+  const uint32_t done = bars;
+  volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(g + (bars - base) + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < (bars - base) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(g)[i] = 0x01020301u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    mbar_init(done, 1);
+    mbar_fence_init();
+  }
+  const uint32_t tmem_base = tmem_setup<1>(bars + 64, slot, warp);
+  if (warp == 0) {
+    const bool el = elect1();
+    const uint64_t da = umma_desc64(sa), db = umma_desc64(sb);
+    const uint32_t id64 = (2u << 4) | (8u << 17) | (8u << 24), id128 = (2u << 4) | (16u << 17) | (8u << 24),
+                   id192 = (2u << 4) | (24u << 17) | (8u << 24), id256 = (2u << 4) | (32u << 17) | (8u << 24);
+    __syncwarp();
+    const long long t0 = clock64();
+    long long n_mma = 0;
+    if (with_mma) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (el) {
+            umma<1, 0>(tmem_base + 0, da + (uint64_t)((0 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id256, 1);
+            umma<1, 0>(tmem_base + 256, da + (uint64_t)((0 * 8192 + kk * 32) >> 4), db + (uint64_t)((4 * 4096 + kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 64, da + (uint64_t)((1 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 256, da + (uint64_t)((1 * 8192 + kk * 32) >> 4), db + (uint64_t)((3 * 4096 + kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 128, da + (uint64_t)((2 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 320, da + (uint64_t)((2 * 8192 + kk * 32) >> 4), db + (uint64_t)((3 * 4096 + kk * 32) >> 4), id128, 1);
+            umma<1, 0>(tmem_base + 192, da + (uint64_t)((3 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id256, 1);
+            umma<1, 0>(tmem_base + 256, da + (uint64_t)((4 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id192, 1);
+            umma<1, 0>(tmem_base + 320, da + (uint64_t)((5 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id128, 1);
+            umma<1, 0>(tmem_base + 384, da + (uint64_t)((6 * 8192 + kk * 32) >> 4), db + (uint64_t)((kk * 32) >> 4), id64, 1);
+          }
+          n_mma += 10;
+        }
+        __syncwarp();
+      }
+      if (el) commit<1>(done);
+      __syncwarp();
+      mbar_wait(done, 0);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) {
+      out[4 * blockIdx.x] = (unsigned long long)(t1 - t0);
+      out[4 * blockIdx.x + 1] = (unsigned long long)n_mma;
+    }
+  } else {
+    double d0 = 1.0 + lane, d1 = 2.0, d2 = 3.0, d3 = 4.0;
+    const double m = 1.0000001, c = 1e-9;
+    float f0 = 1.f + lane, f1 = 2.f, f2 = 3.f, f3 = 4.f;
+    int i0 = lane, i1 = 2, i2 = 3, i3 = 4;
+    double* my = sink + ((size_t)blockIdx.x * 288 + threadIdx.x) * 4;
+    const long long t0 = clock64();
+    for (int it = 0; it < witers; ++it) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (work == 1) {
+          d0 = fma(d0, m, c); d1 = fma(d1, m, c); d2 = fma(d2, m, c); d3 = fma(d3, m, c);
+        } else if (work == 2) {
+          f0 = fmaf(f0, 1.0001f, 1e-5f); f1 = fmaf(f1, 1.0001f, 1e-5f);
+          f2 = fmaf(f2, 1.0001f, 1e-5f); f3 = fmaf(f3, 1.0001f, 1e-5f);
+        } else if (work == 3) {
+          i0 = i0 * 3 + 1; i1 = i1 * 3 + 1; i2 = i2 * 3 + 1; i3 = i3 * 3 + 1;
+        } else if (work == 4) {
+          unsigned long long x, y;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(sa + (uint32_t)((u + i0) & 63) * 16));
+          i0 += (int)(x & 1);
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(sa + (uint32_t)((u + i1) & 63) * 16));
+          i1 += (int)(y & 1);
+        } else if (work == 5) {
+          i0 = __shfl_xor_sync(0xffffffffu, i0, 16); i1 = __shfl_xor_sync(0xffffffffu, i1, 8);
+          i2 = __shfl_xor_sync(0xffffffffu, i2, 4); i3 = __shfl_xor_sync(0xffffffffu, i3, 2);
+        } else if (work == 6) {
+          __stcs(my + (u & 3), d0);
+        } else if (work == 7) {
+          d0 = __dmul_rn(d0, m); d1 = fmin(d1, d0); d2 = __dmul_rn(d2, m); d3 = fmin(d3, d2);
+        } else if (work == 8) {
+          d0 += (double)(long long)i0; d1 += (double)(long long)(i0 + u);
+          d2 += (double)(((long long)i0 << 20) + u); d3 += (double)(((long long)i0 << 21) + u);
+        } else if (work == 9) {
+          d0 = __dadd_rn(d0, m); d1 = __dadd_rn(d1, c); d2 = __dadd_rn(d2, m); d3 = __dadd_rn(d3, c);
+        }
+      }
+    }
+    const long long t1 = clock64();
+    if (d0 + d1 + d2 + d3 + f0 + f1 + f2 + f3 + i0 + i1 + i2 + i3 == 12345.678) my[0] = 1.0;
+    if (threadIdx.x == 32) {
+      out[4 * blockIdx.x + 2] = (unsigned long long)(t1 - t0);
+      out[4 * blockIdx.x + 3] = (unsigned long long)witers * 8;
+    }
+  }
+  tmem_teardown<1>(tmem_base, warp);
+}
+
+template <int work>
+static void run_contend(const char* what, int per_round) {
+  const int units = 148;
+  const int smem = 1024 + 7 * 8192 + 16 * 4096 + 256;
+  unsigned long long* out;
+  double* sink;
+  CK(cudaMalloc(&out, sizeof(unsigned long long) * 4 * units));
+  CK(cudaMalloc(&sink, sizeof(double) * 4 * 288 * units));
+  CK(cudaFuncSetAttribute(contend_kernel<work>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  double res[2][2];
+  for (int with = 0; with < 2; ++with) {
+    for (int rep = 0; rep < 2; ++rep) {
+      contend_kernel<work><<<units, 288, smem>>>(with, 3000, 4000, sink, out);
+      CK(cudaDeviceSynchronize());
+    }
+    std::vector<unsigned long long> h(4 * units);
+    CK(cudaMemcpy(h.data(), out, sizeof(unsigned long long) * 4 * units, cudaMemcpyDeviceToHost));
+    std::vector<double> pm, pw;
+    for (int u = 0; u < units; ++u) {
+      pm.push_back(h[4 * u + 1] ? (double)h[4 * u] / (double)h[4 * u + 1] : 0.0);
+      pw.push_back((double)h[4 * u + 2] / (double)h[4 * u + 3]);
+    }
+    std::sort(pm.begin(), pm.end());
+    std::sort(pw.begin(), pw.end());
+    res[with][0] = pm[units / 2];
+    res[with][1] = pw[units / 2];
+  }
+  printf("contend %-26s: cycles per round of %d instr/thread (8 warps): alone %.1f, under MMA %.1f "
+         "(x%.2f) | cycles per MMA under this work %.1f (alone 90.9)\n",
+         what, per_round, res[0][1], res[1][1], res[1][1] / res[0][1], res[1][0]);
+  cudaFree(out);
+  cudaFree(sink);
+}
+
 // ---- check (TS): the row operand is copied shared memory -> TMEM with
 // tcgen05.cp.128x256b (one 32-byte K step of the 64B-swizzled tile) and the MMA
 // reads it from there; must give the same products as the SS form
@@ -636,9 +782,26 @@ static void run_rate(int N, int S, int mode) {
   cudaFree(out);
 }
 
-int main() {
+static void run_contend_all() {
+  run_contend<0>("no work", 0);
+  run_contend<1>("DFMA", 4);
+  run_contend<9>("DADD", 4);
+  run_contend<7>("2 DMUL + 2 fmin", 4);
+  run_contend<8>("4 x (I2F.F64.S64 + DADD)", 8);
+  run_contend<2>("FFMA", 4);
+  run_contend<3>("IMAD", 4);
+  run_contend<4>("LDS.128 broadcast", 2);
+  run_contend<5>("SHFL", 4);
+  run_contend<6>("STG.64 (.cs)", 1);
+}
+
+int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
+  if (argc > 1 && std::string(argv[1]) == "contend") {
+    run_contend_all();
+    return 0;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   printf("device: %s, %d SMs, clock %d kHz\n", prop.name, prop.multiProcessorCount, prop.clockRate);
@@ -673,6 +836,7 @@ int main() {
   run_rate2(0, 2, "SS, stacked S = 7 schedule (10 per K step)");
   run_rate2(256, 4, "SS, all N = 256 (7 per K step)");
   run_rate2(0, 5, "TS stacked S = 7 schedule + 7 tcgen05.cp / K step");
+  run_contend_all();
   // three accumulators (two-pass split): S = 3 pattern at N = 128 / 160
   run_rate<1, 0>(128, 3, 0);
   run_rate<2, 0>(128, 3, 0);
