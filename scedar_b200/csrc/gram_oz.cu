@@ -23,13 +23,16 @@
 // instructions per 32-byte K step); the dropped pairs are below 2^-(8S-2) of
 // the row scales.  The offset of the top bytes contributes 128 (R_d[i] +
 // R_d[j]) (+ 2^14 K on diagonal 0) with R_d the byte sums of a row; the
-// epilogue subtracts it exactly in 64-bit integers, converts the two halves of
-// the weighted sum to float64 (each conversion exact) and joins them with one
-// FMA: P = 2^(e_i + e_j - 30) (hi + lo 2^(-8(S-3))).  Integer input (counts)
-// therefore gives the exact dot product, identical rows give P_ij == P_ii ==
-// P_jj bit for bit (the statistic comes from the same integers), and for S = 7
-// the truncation (<= 6 p 2^-56 of the row scales, a few 1e-15 of |x_i||x_j| on
-// log counts) is of the size of DGEMM's own rounding.
+// epilogue subtracts it exactly in 64-bit integers and joins the two halves of
+// the weighted sum into ONE 64-bit integer W with 17 fraction bits below the
+// unit of the upper half (oz_weighted; the cut, 2^-48 of the row scales, is below
+// what the dropped diagonals are worth), converted to float64 once:
+// P = 2^(e_i + e_j - 30 - 17) W.  Integer input (counts) therefore gives the
+// exact dot product, identical rows give P_ij == P_ii == P_jj bit for bit (the
+// statistic comes from the same integers through the same function), and for
+// S = 7 the truncation (<= 6 p 2^-56 of the row scales, a few 1e-15 of
+// |x_i||x_j| on log counts) is of the size of DGEMM's own rounding.  K chunks
+// (4096 columns per INT32 accumulation) are summed as integers too.
 //
 // Kernel (persistent, one CTA per SM, 320 threads):
 //   warp 0     TMA producer, 128-byte K slabs (128B swizzle; with 64-byte box rows
@@ -43,24 +46,34 @@
 //              = slot base + constant
 //   warps 2-9  epilogue: TMEM lane quarter = warp % 4, column half = (warp-2)/4.
 //              Phase 1 drains the accumulators (S x tcgen05.ld.x4 per 4 columns,
-//              the next 4 in flight) into 32 float64 dot products per thread and
-//              hands TMEM back; phase 2 (under the next tile's MMAs) applies
-//              finish_entry and stores: the mirrored tile straight from the
-//              registers (lanes = consecutive entries of a row of D), the tile
-//              itself in 32-byte runs (st.global.v4.f64)
+//              the next 4 in flight) into 32 integer weighted sums per thread
+//              and hands TMEM back; phase 2 (under the next tile's MMAs) converts
+//              them (one I2F each), applies the metric and stores: the mirrored
+//              tile straight from the registers (lanes = consecutive entries of
+//              a row of D), the tile itself in 32-byte runs (st.global.v4.f64),
+//              and -- when the handle carries block-minima buffers -- the minimum
+//              of every run of 32 entries of both, for the selection that follows
 // TMEM holds S x 64 columns (448 of 512 for S = 7): no second accumulator set,
-// so phase 1 (~8 k cycles of an ~80 k cycle tile at p = 2000) is not overlapped.
+// so phase 1 (~3 k cycles of a ~75 k cycle tile at p = 2000) is not overlapped.
 // What bounds it (SCEDAR_B200_OZ_DEBUG=1 prints per-tile cycle counters;
-// tools/umma_probe.cu, profiles/r02_umma_probe.log): issued alone, from operands
-// resident in shared memory, the 10-instruction K step runs at 909 cycles (ideal
-// 896).  In the kernel it takes ~1,130: per K step the tensor core READS 96 KB of
-// operands from shared memory (10 x 4 KB row operand + 28 x 2 KB column slices,
-// 107 B/cycle) while TMA WRITES the next 42 KB (47 B/cycle) -- 154 B/cycle against
-// the 128 B/cycle of an SM's shared memory.  cta_group::2 would halve the column
-// operand's share, but splits the N columns of an instruction between the two
-// CTAs' shared memories, which breaks the stacking of slices along N (the second
-// half of every instruction would land on a diagonal that depends on the run
-// length).  So: ~0.79 of the pipe's rate, shared-memory bound.
+// tools/umma_probe.cu, profiles/r02_umma_probe.log, r02_umma_contend.log):
+// * issued alone, from operands resident in shared memory, the 10-instruction K
+//   step runs at 909 cycles (ideal 896); in the kernel it takes ~1,130.
+// * while the tensor pipe is busy the other warps of the SM pay ~12x for every
+//   FP64 instruction and ~4x for every shared-memory load (and the MMAs lose
+//   8 % to them); integer work, shuffles and global stores are unaffected.  The
+//   first round-2 epilogue (FP64 scaling, column constants from L1) took 53-69 k
+//   cycles per tile in phase 2 and 12.7 k in phase 1 and had become the critical
+//   path; the integer form above takes 37 k / 3.2 k and waits for the MMAs.
+// * the cycles saved do not show as time: the launch runs under the board's
+//   power cap, the SM clock settles where the executed INT8 MACs fit the power
+//   budget (~1.65 GHz before, ~1.45 GHz after, same 214-225 ms at 100k x 2000).
+//   Executed MACs are 0.93 of twice the sustained bf16 rate of
+//   MEASURED_PEAKS.json; what is left is S (6 slices: 0.79 of the time at
+//   2.7e-12 instead of 4e-14).
+// cta_group::2 would halve the column operand's shared-memory reads, but splits
+// the N columns of an instruction between the two CTAs' shared memories, which
+// breaks the stacking of slices along N.
 // Tiles (128 rows x 64 columns) come from a host-built list in L2-friendly
 // order, dealt round-robin to the CTAs; the list also carries what to store
 // (tile / mirrored tile), so the whole-matrix, row-stripe, peer-store and
@@ -93,19 +106,14 @@ constexpr int B_SLAB = ON * OKB;   // 8 KB
 // as the MMAs of its slice have retired (the MMA loop runs slice-major), and
 // TWO slabs of column-tile slices (all S are needed from the first slice on)
 constexpr int OZ_BAR_BYTES = 256;
-// per-tile column constants staged for the epilogue: {hi, lo} and {sc, stat} of
-// the tile's 64 columns (16 bytes per column each)
-constexpr int OZ_CST_BYTES = 2 * ON * 16;
-constexpr int oz_smem(int S) {
-  return S * A_SLAB + 2 * S * B_SLAB + OZ_BAR_BYTES + OZ_CST_BYTES;
-}
+constexpr int oz_smem(int S) { return S * A_SLAB + 2 * S * B_SLAB + OZ_BAR_BYTES; }
 static_assert(oz_smem(6) <= 227 * 1024 && oz_smem(7) <= 227 * 1024, "shared memory budget");
 constexpr int OZ_EPI_WARPS = 8;
 constexpr int OZ_EPI_THREADS = 32 * OZ_EPI_WARPS;
 constexpr int OZ_THREADS = 64 + OZ_EPI_THREADS;
 constexpr int OZ_KCHUNK = 4096;    // K columns accumulated in INT32 at a time: 7 * 255^2 * 4096
                                    // < 2^31; longer rows are contracted chunk by chunk, the
-                                   // float64 chunk values summed in the epilogue's registers
+                                   // integer chunk sums added in the epilogue's registers
 constexpr int OZ_CHUNK_SLABS = OZ_KCHUNK / OKB;
 constexpr int kOzPeers = 16;
 constexpr int TILE_DIRECT = 1, TILE_MIRROR = 2;
@@ -140,21 +148,36 @@ struct OzArgs {
   // = min of D[row][32 b .. 32 b + 31]; same stripe table as D
   double* bmin_ptr[kOzPeers];
   int64_t ldb;
-  int skip;     // EXPERIMENT
+  int wshift;   // fraction bits of the integer weighted sums (oz_wshift)
 };
 
-// weighted sum of the diagonal accumulators minus the offset terms -> float64
+// Weighted sum of the diagonal accumulators minus the offset terms, as ONE
+// 64-bit integer.  hi (unit 1) and lo (unit 2^-8(S-3)) are exact: diagonal d
+// holds d + 1 products of at most 255^2 * 4096 < 2^28 each, so |hi| < 2^45 and
+// |lo| < 2^56.  W = hi 2^ws + round(lo 2^(ws - 8(S-3))) keeps ws fraction bits
+// below the hi unit (ws = 17 for a single K chunk: |W| < 2^62).  The cut is
+// <= 2^-18 hi units = 2^-48 of the row scales, against up to 6 p 2^-56 from the
+// diagonals the contraction drops; integer input whose dot products are
+// integers of the hi unit's scale stays exact.  ls = 8 (S - 3) - ws >= 1.
 template <int S>
-__device__ __forceinline__ double oz_value(const uint32_t (&acc)[S], long long hi_corr,
-                                           long long lo_corr) {
+__device__ __forceinline__ long long oz_weighted(const uint32_t (&acc)[S], long long hi_corr,
+                                                 long long lo_corr, int ws, int ls) {
   long long hi = ((long long)acc[0] << 16) + ((long long)acc[1] << 8) + (long long)acc[2];
   long long lo = 0;
 #pragma unroll
   for (int d = 3; d < S; ++d) lo = (lo << 8) + (long long)acc[d];
   hi -= hi_corr;
   lo -= lo_corr;
-  constexpr double w = 1.0 / (double)(1ull << (8 * (S - 3)));
-  return fma((double)lo, w, (double)hi);
+  return (hi << ws) + ((lo + (1ll << (ls - 1))) >> ls);
+}
+// fraction bits for n_chunks K chunks summed as integers: |sum| < 2^63
+__host__ __device__ inline int oz_wshift(int n_chunks) {
+  int ws = 17;
+  while (n_chunks > 1) {
+    --ws;
+    n_chunks = (n_chunks + 1) >> 1;
+  }
+  return ws;
 }
 
 // ---- K1': slices, scales, offset corrections and the Gram diagonal -----------
@@ -184,7 +207,8 @@ oz_slice_kernel(const double* __restrict__ xw, int64_t n, int64_t p, int64_t p_p
   if (m > 0.0) frexp(m, &e);   // m = f 2^e, f in [0.5, 1): |x| < 2^e
   const int n_chunks = (int)((p_oz + OZ_KCHUNK - 1) / OZ_KCHUNK);
   const double sci = scalbn(1.0, e - 15);
-  double p_ii = 0.0;   // thread 0: sum of the chunk values (same order as the tile epilogue)
+  long long w_ii = 0;   // thread 0: the weighted sum of (row, row), as the tile epilogue forms it
+  const int ws = oz_wshift(n_chunks), ls = 8 * (S - 3) - ws;
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int64_t k_begin = (int64_t)ch * OZ_KCHUNK;
     const int64_t k_end = k_begin + OZ_KCHUNK < p_oz ? k_begin + OZ_KCHUNK : p_oz;
@@ -253,13 +277,13 @@ oz_slice_kernel(const double* __restrict__ xw, int64_t n, int64_t p, int64_t p_p
       hi[row * n_chunks + ch] = hi_i;
       lo[row * n_chunks + ch] = lo_i;
       const long long c0c = ((long long)16384 * (k_end - k_begin)) << 16;
-      const double v = oz_value<S>(acc, 2 * hi_i + c0c, 2 * lo_i);
-      p_ii = ch == 0 ? v : __dadd_rn(p_ii, v);
+      w_ii += oz_weighted<S>(acc, 2 * hi_i + c0c, 2 * lo_i, ws, ls);
     }
     __syncthreads();
   }
   if (tid == 0) {
     sc[row] = sci;
+    const double p_ii = __dmul_rn((double)w_ii, __longlong_as_double((long long)(1023 - ws) << 52));
     const double P = __dmul_rn(p_ii, __dmul_rn(sci, sci));
     double sv = 0.0;
     if (real) sv = euclid ? P : __dsqrt_rn(P != 0.0 ? __ddiv_rn(1.0, P) : 0.0);
@@ -292,7 +316,6 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                  tfull = bars + 160, tempty = bars + 168;
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(gbase + (bars - base) + 192);
-  const uint32_t cst = bars + OZ_BAR_BYTES;     // column constants (epilogue warps)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = a.kslabs;
 
@@ -344,7 +367,6 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int sl = 0; sl < S; ++sl) {
           mbar_wait(empty_a + 8 * sl, (uint32_t)((it & 1) ^ 1));
-          if (a.skip & 32) { mbar_arrive(full_a + 8 * sl); continue; }
           mbar_expect_tx(full_a + 8 * sl, A_SLAB);
           tma_load_2d(ring_a + sl * A_SLAB, &map_a, ks * OKB, (int)(sl * a.n_pl) + i0,
                       full_a + 8 * sl);
@@ -355,7 +377,6 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         coords(it, i0, j0, ks);
         const uint32_t buf = (uint32_t)(it & 1), ph = (uint32_t)((it >> 1) & 1);
         mbar_wait(empty_b + 8 * buf, ph ^ 1);
-        if (a.skip & 32) { mbar_arrive(full_b + 8 * buf); return; }
         mbar_expect_tx(full_b + 8 * buf, B_STAGE);
         const uint32_t st = ring_b + buf * B_STAGE;
 #pragma unroll
@@ -410,7 +431,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int run = S - sl;
               const int first = run <= kFullRun ? run : (run + 1) / 2;
               const uint32_t acc = (kc | kk | sl) != 0;
-              if (el && !(a.skip & 16)) {
+              if (el) {
                 tc::mma_i8(tmem_base + (uint32_t)(sl * ON), da + (uint64_t)((kk * 32) >> 4),
                            db + (uint64_t)((kk * 32) >> 4), tc::idesc_u8(ON * first), acc);
                 if (run > first)
@@ -438,58 +459,48 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ---- epilogue warps 2..9 -----------------------------------------------------
+    // While the tensor pipe is busy, FP64 instructions of the same SM issue ~12x
+    // slower and shared-memory loads ~4x slower; integer work, shuffles and
+    // global stores are unaffected (tools/umma_probe.cu `contend`,
+    // profiles/r02_umma_contend.log).  So the epilogue keeps everything it can
+    // in integers: the weighted sum stays a 64-bit integer until one conversion
+    // per entry, the power-of-two scales are folded into the per-row / per-column
+    // factors (exact), clamps and minima compare bit patterns (the distances are
+    // non-negative), and the constants of the tile's columns live in registers
+    // -- lane c holds column c's -- and travel by shuffle.
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int h = (warp - 2) >> 2;            // column half
     const int r = q * 32 + lane;              // tile row
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr unsigned kFull = 0xffffffffu;
+    const int ws = a.wshift;                  // fraction bits kept below the `hi` unit
+    const int ls = 8 * (S - 3) - ws;
     uint32_t tcount = 0;
     long long e_wait = 0, e_p1 = 0, e_p2 = 0;
-    // The constants of the tile's 64 columns -- {hi, lo} of the current K chunk and
-    // {sc, stat} -- are staged in shared memory once per tile by the 256 epilogue
-    // threads (one value each) and read back as 16-byte broadcasts: fetched per
-    // entry from global memory they were the epilogue's main stall.  The next
-    // tile's descriptor and constant are fetched a tile ahead.
-    const int e_tid = threadIdx.x - 64;       // 0..255
-    const int st_col = e_tid & 63, st_kind = e_tid >> 6;   // 0 hi, 1 lo, 2 sc, 3 stat
-    const uint32_t st_addr = cst + (uint32_t)((st_kind >> 1) * (ON * 16) + st_col * 16 +
-                                              (st_kind & 1) * 8);
-    auto fetch_const = [&](int64_t j0, int ch) -> unsigned long long {
-      const int64_t gj = j0 + st_col;         // < n_pl: the arrays cover the padding
-      if (st_kind == 0) return (unsigned long long)__ldg(a.hi + gj * a.n_chunks + ch);
-      if (st_kind == 1) return (unsigned long long)__ldg(a.lo + gj * a.n_chunks + ch);
-      return (unsigned long long)__double_as_longlong(
-          __ldg((st_kind == 2 ? a.sc : a.stat) + gj));
-    };
-    auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    auto put_const = [&](unsigned long long v) {
-      asm volatile("st.shared.b64 [%0], %1;" ::"r"(st_addr), "l"(v) : "memory");
-    };
-    auto col_pair = [&](uint32_t table, int col, unsigned long long& x, unsigned long long& y) {
-      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];"
-                   : "=l"(x), "=l"(y)
-                   : "r"(cst + table * (ON * 16) + (uint32_t)col * 16));
-    };
     OzTile tl_next{0, 0, 0, 0};
-    unsigned long long pre = 0;
-    if ((int)blockIdx.x < a.n_tiles) {
-      tl_next = a.tiles[blockIdx.x];
-      pre = fetch_const((int64_t)tl_next.J * ON, 0);
-    }
+    if ((int)blockIdx.x < a.n_tiles) tl_next = a.tiles[blockIdx.x];
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
       const OzTile tl = tl_next;
-      epi_sync();                             // the last tile's constants are done with
-      put_const(pre);
-      epi_sync();
-      const bool more = t + (int)gridDim.x < a.n_tiles;
-      if (more) tl_next = a.tiles[t + gridDim.x];
+      if (t + (int)gridDim.x < a.n_tiles) tl_next = a.tiles[t + gridDim.x];
       const int64_t i0 = (int64_t)tl.I * OM, j0 = (int64_t)tl.J * ON;
       const int64_t gi = i0 + r;
       const bool row_ok = gi < a.n;
+      // this thread's row: scale, statistic; this lane's column (j0 + 32 h + lane,
+      // inside the padded planes): the same plus the corrections of chunk 0
+      const int64_t gjl = j0 + h * 32 + lane;
       double sci = 0.0, sti = 0.0;
       if (row_ok) {
         sci = __ldg(a.sc + gi);
         sti = __ldg(a.stat + gi);
       }
+      const double scl = __ldg(a.sc + gjl), stl = __ldg(a.stat + gjl);
+      long long chi = __ldg(a.hi + gjl * a.n_chunks), clo = __ldg(a.lo + gjl * a.n_chunks);
+      // factors: cosine / correlation d = 1 - (W f_hi) f_lo with f = stat sc (and the
+      // 2^-ws of W on the row side); euclidean d^2 = (W (-2 sc_i 2^-ws)) sc_j + s_hi + s_lo
+      const double wsc = __longlong_as_double((long long)(1023 - ws) << 52);
+      const double rowf = a.euclid ? __dmul_rn(__dmul_rn(-2.0, sci), wsc)
+                                   : __dmul_rn(__dmul_rn(sti, sci), wsc);
+      const double colf = a.euclid ? scl : __dmul_rn(stl, scl);
       // output stripes of the tile's rows and of its (mirrored) columns
       int od = 0, om = 0;
       while (od + 1 < a.world && i0 >= a.stripe_begin[od + 1]) ++od;
@@ -502,32 +513,38 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool direct = (tl.flags & TILE_DIRECT) && gi >= a.row_lo && gi < a.row_hi;
       const bool mirror = (tl.flags & TILE_MIRROR) && row_ok;
       // block minima: this thread's 32 entries are block (j0 + 32 h) / 32 of row gi;
-      // column c of the mirrored tile is row j0 + c, whose block (i0 + 32 q) / 32
-      // is the minimum over this warp's 32 rows
+      // column c of the mirrored tile is row j0 + 32 h + c, whose block
+      // (i0 + 32 q) / 32 is the minimum over this warp's 32 rows
       double* __restrict__ bm_row = nullptr;
       double* __restrict__ bm_col = nullptr;
       if (a.bmin_ptr[0]) {
         bm_row = a.bmin_ptr[od] + (gi - a.stripe_begin[od]) * a.ldb + (j0 >> 5) + h;
         bm_col = a.bmin_ptr[om] + (j0 + h * 32 - a.stripe_begin[om]) * a.ldb + (i0 >> 5) + q;
       }
-      double rmin = pos_inf();
+      const bool want_cmin = bm_col != nullptr && (tl.flags & TILE_MIRROR);
+      constexpr long long kInfBits = 0x7ff0000000000000LL;
+      long long rmin = kInfBits;
 
-      // phase 1, once per K chunk: drain the accumulators into raw dot products
-      // held in registers (32 per thread), four columns at a time, the next four
-      // in flight while these are combined; then hand TMEM back so the next
-      // chunk's / tile's MMAs run under the rest
-      double pv[32];
+      // phase 1, once per K chunk: drain the accumulators into the weighted sums
+      // (64-bit integers, 32 per thread), four columns at a time, the next four in
+      // flight while these are combined; then hand TMEM back so the next chunk's /
+      // tile's MMAs run under the rest
+      long long pw[32];
       long long ec0 = 0, ec1 = 0;
       auto phase1 = [&](int ch, auto first_chunk) {
         constexpr bool kFirst = decltype(first_chunk)::value;
+        if (!kFirst) {
+          chi = __ldg(a.hi + gjl * a.n_chunks + ch);
+          clo = __ldg(a.lo + gjl * a.n_chunks + ch);
+        }
+        const long long c0c = ch == a.n_chunks - 1 ? a.c0_last : a.c0;
+        const long long hic = (row_ok ? __ldg(a.hi + gi * a.n_chunks + ch) : 0) + c0c;
+        const long long loc = row_ok ? __ldg(a.lo + gi * a.n_chunks + ch) : 0;
         ec0 = a.dbg ? clock64() : 0;
         mbar_wait(tfull, tcount & 1);
         ec1 = a.dbg ? clock64() : 0;
         if (a.dbg) e_wait += ec1 - ec0;
         tc::fence_after();
-        const long long c0c = ch == a.n_chunks - 1 ? a.c0_last : a.c0;
-        const long long hic = (row_ok ? __ldg(a.hi + gi * a.n_chunks + ch) : 0) + c0c;
-        const long long loc = row_ok ? __ldg(a.lo + gi * a.n_chunks + ch) : 0;
         uint32_t va[S][4], vb[S][4];
         auto drain = [&](uint32_t (&v)[S][4], int c0) {
 #pragma unroll
@@ -542,16 +559,13 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const int c = c0 + cc;
-            double val = 0.0;
-            if (j0 + h * 32 + c < a.n) {
-              uint32_t acc[S];
+            uint32_t acc[S];
 #pragma unroll
-              for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
-              unsigned long long chi, clo;
-              col_pair(0, h * 32 + c, chi, clo);
-              val = oz_value<S>(acc, hic + (long long)chi, loc + (long long)clo);
-            }
-            pv[c] = kFirst ? val : __dadd_rn(pv[c], val);
+            for (int d = 0; d < S; ++d) acc[d] = v[d][cc];
+            const long long w =
+                oz_weighted<S>(acc, hic + __shfl_sync(kFull, chi, c),
+                               loc + __shfl_sync(kFull, clo, c), ws, ls);
+            pw[c] = kFirst ? w : pw[c] + w;
           }
         };
         drain(va, 0);
@@ -572,72 +586,74 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ++tcount;
       };
       phase1(0, std::true_type{});
-      for (int ch = 1; ch < a.n_chunks; ++ch) {
-        // the next chunk's {hi, lo} replace the current ones
-        const unsigned long long v = st_kind < 2 ? fetch_const(j0, ch) : 0ull;
-        epi_sync();
-        if (st_kind < 2) put_const(v);
-        epi_sync();
-        phase1(ch, std::false_type{});
-      }
-      // next tile's constant: in flight under phase 2
-      if (more) pre = fetch_const((int64_t)tl_next.J * ON, 0);
+      for (int ch = 1; ch < a.n_chunks; ++ch) phase1(ch, std::false_type{});
       long long ec2 = a.dbg ? clock64() : 0;
       // phase 2 (under the next tile's MMAs): metric epilogue and the two stores.
       // The mirrored tile is written straight from the registers -- lanes are
       // consecutive entries of a row of D; the tile itself in 32-byte runs
+      const int cols_ok = (int)(a.n - (j0 + h * 32) < 32 ? a.n - (j0 + h * 32) : 32);  // may be <= 0
 #pragma unroll
       for (int c0 = 0; c0 < 32; c0 += 4) {
         double dv[4];
+        long long db[4];       // bit patterns: non-negative doubles order like integers
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c = c0 + cc;
           const int64_t gj = j0 + h * 32 + c;
-          dv[cc] = 0.0;
-          if (gj < a.n) {
-            unsigned long long csc = 0x3ff0000000000000ull, cst_j = 0x3ff0000000000000ull;
-            if (!(a.skip & 4)) col_pair(1, h * 32 + c, csc, cst_j);
-            const double stj = __longlong_as_double((long long)cst_j);
-            const bool lower = gi >= gj;
-            const double P = __dmul_rn(
-                pv[c], __dmul_rn(sci, __longlong_as_double((long long)csc)));
-            dv[cc] = (a.skip & 8) ? P : finish_entry(P, lower ? sti : stj, lower ? stj : sti, gi == gj, a.euclid);
-            if (mirror && !(a.skip & 2) && gj >= a.row_lo && gj < a.row_hi) __stcs(mcol + (int64_t)c * a.ldd, dv[cc]);
-            rmin = fmin(rmin, dv[cc]);
+          const double fj = __shfl_sync(kFull, colf, c);
+          const double wv = (double)pw[c];
+          const bool lower = gi >= gj;
+          double d;
+          if (a.euclid) {
+            const double stj = __shfl_sync(kFull, stl, c);
+            const double t2 = __dadd_rn(__fma_rn(__dmul_rn(wv, rowf), fj, lower ? sti : stj),
+                                        lower ? stj : sti);
+            d = __double_as_longlong(t2) < 0 ? 0.0 : __dsqrt_rn(t2);
+          } else {
+            const double f_hi = lower ? rowf : fj, f_lo = lower ? fj : rowf;
+            d = __dsub_rn(1.0, __dmul_rn(__dmul_rn(wv, f_hi), f_lo));
+          }
+          long long bits = __double_as_longlong(d);
+          bits = (bits < 0 || gi == gj) ? 0 : bits;    // clamp at 0 (also -0); zero diagonal
+          db[cc] = bits;
+          dv[cc] = __longlong_as_double(bits);
+          if (c < cols_ok) {
+            if (mirror && gj >= a.row_lo && gj < a.row_hi) __stcs(mcol + (int64_t)c * a.ldd, dv[cc]);
+            rmin = bits < rmin ? bits : rmin;
           }
         }
-        if (bm_col && (tl.flags & TILE_MIRROR)) {
+        if (want_cmin) {
           // minima of these four columns over the warp's 32 rows (= one block of
           // four rows of D each): a halving exchange -- after two steps every
           // lane holds one column's partial minimum, three more finish it
-          double w[4];
+          long long w[4];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            w[cc] = (row_ok && j0 + h * 32 + c0 + cc < a.n) ? dv[cc] : pos_inf();
+          for (int cc = 0; cc < 4; ++cc) w[cc] = row_ok ? db[cc] : kInfBits;
           const bool b4 = lane & 16, b3 = lane & 8;
-          double k0 = b4 ? w[2] : w[0], k1 = b4 ? w[3] : w[1];
-          k0 = fmin(k0, __shfl_xor_sync(0xffffffffu, b4 ? w[0] : w[2], 16));
-          k1 = fmin(k1, __shfl_xor_sync(0xffffffffu, b4 ? w[1] : w[3], 16));
-          double m = fmin(b3 ? k1 : k0, __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8));
+          auto imin = [](long long x, long long y) { return x < y ? x : y; };
+          long long k0 = b4 ? w[2] : w[0], k1 = b4 ? w[3] : w[1];
+          k0 = imin(k0, __shfl_xor_sync(kFull, b4 ? w[0] : w[2], 16));
+          k1 = imin(k1, __shfl_xor_sync(kFull, b4 ? w[1] : w[3], 16));
+          long long m = imin(b3 ? k1 : k0, __shfl_xor_sync(kFull, b3 ? k0 : k1, 8));
 #pragma unroll
-          for (int o = 4; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+          for (int o = 4; o > 0; o >>= 1) m = imin(m, __shfl_xor_sync(kFull, m, o));
           const int c = c0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);
           const int64_t gj = j0 + h * 32 + c;
-          if ((lane & 7) == 0 && gj < a.n && gj >= a.row_lo && gj < a.row_hi && i0 + q * 32 < a.n)
-            bm_col[(int64_t)c * a.ldb] = m;
+          if ((lane & 7) == 0 && c < cols_ok && gj >= a.row_lo && gj < a.row_hi &&
+              i0 + q * 32 < a.n)
+            bm_col[(int64_t)c * a.ldb] = __longlong_as_double(m);
         }
-        if (direct && !(a.skip & 1)) {
-          const int64_t gj0 = j0 + h * 32 + c0;
-          if (a.vec_ok && gj0 + 3 < a.n) {
+        if (direct) {
+          if (a.vec_ok && c0 + 3 < cols_ok) {
             st_cs_v4(drow + c0, dv[0], dv[1], dv[2], dv[3]);
           } else {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc)
-              if (gj0 + cc < a.n) __stcs(drow + c0 + cc, dv[cc]);
+              if (c0 + cc < cols_ok) __stcs(drow + c0 + cc, dv[cc]);
           }
         }
       }
-      if (bm_row && direct && j0 + h * 32 < a.n) *bm_row = rmin;
+      if (bm_row && direct && cols_ok > 0) *bm_row = __longlong_as_double(rmin);
       if (a.dbg) e_p2 += clock64() - ec2;
     }
     if (a.dbg && threadIdx.x == 64) {
@@ -852,7 +868,7 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s, int 
     a.ldb = c->bmin_ld;
     const_cast<scedar_cells*>(c)->bmin_filled = true;
   }
-  a.skip = getenv("SCEDAR_B200_OZ_SKIP") ? atoi(getenv("SCEDAR_B200_OZ_SKIP")) : 0;
+  a.wshift = oz_wshift(o->n_chunks);
   a.vec_ok = a.ldd % 4 == 0;
   for (int r = 0; r < a.world; ++r)
     if (reinterpret_cast<uintptr_t>(a.stripe_ptr[r]) % 32 != 0) a.vec_ok = 0;
