@@ -28,3 +28,24 @@ for _ in range(reps):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 print("n={} p={} {}: ms {}".format(n, p, prec, ["%.3f" % t for t in ts]))
+
+# OZ_PROF_P2P="world,rank": that rank's share of the peer-store form, all stripes
+# local (one GPU) -- tile order and ownership without the NVLink stores
+if os.environ.get("OZ_PROF_P2P"):
+    from scedar_b200.stripes import partition
+    world, rank = (int(v) for v in os.environ["OZ_PROF_P2P"].split(","))
+    del d
+    torch.cuda.empty_cache()
+    parts = partition(n, world)
+    peers = dev.PeerStripes(parts, n, blockmin=bool(os.environ.get("OZ_PROF_BLOCKMIN")))
+    if os.environ.get("OZ_PROF_BLOCKMIN"):
+        cells.set_blockmin(peers.bmin_ptrs(), peers.ldb)
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dev.pdist_stripe_p2p(cells, peers, rank, precision=prec)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    print("p2p world={} rank={}: ms {}".format(world, rank, ["%.3f" % t for t in ts]))
