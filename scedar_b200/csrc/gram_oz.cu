@@ -1018,12 +1018,21 @@ int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
     o->host_tiles.clear();
     const int64_t CT = (n + ON - 1) / ON;
     const int64_t u0 = stripe_begin[rank] / OM, u1 = (stripe_begin[rank + 1] + OM - 1) / OM;
+    // Groups hold own row tiles of ONE parity: for a partner v of another rank the
+    // rule above picks every other u, so a mixed group would bring a column block
+    // in for half of its row tiles only.
     const int G = oz_group_rows();
-    for (int64_t g0 = u0; g0 < u1; g0 += G) {
-      const int64_t g1 = std::min<int64_t>(u1, g0 + G);
+    std::vector<int64_t> us;
+    const bool by_parity = getenv("SCEDAR_B200_OZ_P2P_MIXED") == nullptr;
+    for (int par = 0; par < 2; ++par)
+      for (int64_t u = u0; u < u1; ++u)
+        if (by_parity ? (u & 1) == par : par == 0) us.push_back(u);
+    for (size_t g0 = 0; g0 < us.size(); g0 += G) {
+      const size_t g1 = std::min(us.size(), g0 + (size_t)G);
       for (int64_t v = 0; v < RT; ++v)
         for (int64_t J = 2 * v; J < std::min<int64_t>(2 * v + 2, CT); ++J)
-          for (int64_t u = g0; u < g1; ++u) {
+          for (size_t gi = g0; gi < g1; ++gi) {
+            const int64_t u = us[gi];
             if (u == v) {
               o->host_tiles.push_back(OzTile{(int32_t)u, (int32_t)J, TILE_DIRECT, 0});
               continue;

@@ -470,7 +470,7 @@ class StripedDistanceMatrix(object):
         (imputed x, indicator int32 [n, p], (entries, cells) picked up)."""
         import math
         n, p = x.shape
-        curr = x.clone()
+        curr = x.clone(memory_format=torch.contiguous_format)
         nxt = torch.empty_like(curr)
         idc = torch.zeros((n, p), dtype=torch.int32, device=x.device)
         stats = torch.zeros(2, dtype=torch.int64, device=x.device)
@@ -480,13 +480,43 @@ class StripedDistanceMatrix(object):
             self.ops.impute_iter(curr, knn, n_do_i, min_present_val, i, nxt,
                                  idc, stats, r0, r1)
             if self.world > 1:
-                curr = self._gather(nxt[r0:r1])   # fresh [n, p]; nxt is scratch
+                self._exchange_imputed(curr, nxt, idc, i, r0, r1)
             else:
                 curr, nxt = nxt, curr
         if self.world > 1:
             idc = self._gather(idc[r0:r1])
             dist.all_reduce(stats, group=self.group)
         return curr, idc, tuple(int(v) for v in stats.tolist())
+
+    def _exchange_imputed(self, curr, nxt, idc, it, r0, r1):
+        """After iteration ``it`` every rank holds the new values of its own
+        rows in ``nxt``; they differ from ``curr`` exactly where the indicator
+        says ``it``.  Only those (position, value) pairs are exchanged and
+        written into every rank's ``curr`` -- bytes proportional to what the
+        iteration picked up, not to n * p."""
+        p = curr.shape[1]
+        own = (idc[r0:r1] == it).reshape(-1).nonzero().squeeze(1)
+        vals = nxt[r0:r1].reshape(-1)[own]
+        own = own + r0 * p                       # positions in the whole matrix
+        cnt = torch.tensor([own.numel()], dtype=torch.int64, device=curr.device)
+        cnts = torch.empty(self.world, dtype=torch.int64, device=curr.device)
+        dist.all_gather_into_tensor(cnts, cnt, group=self.group)
+        cnts = cnts.tolist()
+        m = max(cnts)
+        if m == 0:
+            return
+        pos_pad = torch.zeros(m, dtype=torch.int64, device=curr.device)
+        val_pad = torch.zeros(m, dtype=curr.dtype, device=curr.device)
+        pos_pad[:own.numel()] = own
+        val_pad[:own.numel()] = vals
+        pos_all = torch.empty(self.world * m, dtype=torch.int64, device=curr.device)
+        val_all = torch.empty(self.world * m, dtype=curr.dtype, device=curr.device)
+        dist.all_gather_into_tensor(pos_all, pos_pad, group=self.group)
+        dist.all_gather_into_tensor(val_all, val_pad, group=self.group)
+        flat = curr.view(-1)
+        for r, c in enumerate(cnts):
+            if c:
+                flat[pos_all[r * m:r * m + c]] = val_all[r * m:r * m + c]
 
     def condensed(self, dst=0):
         """``scipy.spatial.distance.squareform(D)`` (the input of
