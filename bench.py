@@ -389,7 +389,7 @@ def run_b200(a):
     def step(x, broadcast, timed_kernel=False):
         """One pass of the hot path.  With timed_kernel, CUDA events bracket
         the phases on the launching stream (read after the region ends)."""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] \
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] \
             if timed_kernel else None
         trace = [time.perf_counter()] if TRACE else None
         if ev:
@@ -413,6 +413,8 @@ def run_b200(a):
         if trace:
             trace.append(time.perf_counter())
         sdm.close()
+        if ev:
+            ev[4].record()
         if trace:
             trace.append(time.perf_counter())
             print("rank{} host ms: {}".format(rank, [
@@ -436,9 +438,11 @@ def run_b200(a):
     # ---- value: x resident in HBM -----------------------------------------
     for _ in range(a.warmup):
         step(x_dev, False)
-    sync_all()
+    # (rank 0 alone sets up NVML: before the barrier, or every other rank's timed
+    # region starts with the wait for it -- 14 ms at N = 8)
     clocks = ClockSampler(local) if (
         rank == 0 and not os.environ.get("SCEDAR_BENCH_NO_CLOCKS")) else None
+    sync_all()
     launches0 = lib.scedar_launch_count()
     t_host0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -457,6 +461,12 @@ def run_b200(a):
     phases = [[ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
               for ev in phase_events]
     prep_ms, gram_avg_ms, topk_ms = [sum(c) / len(c) for c in zip(*phases)]
+    if TRACE:
+        print("rank{} device ms: close {} | between steps {}".format(
+            rank, [round(ev[3].elapsed_time(ev[4]), 3) for ev in phase_events],
+            [round(a_[4].elapsed_time(b_[0]), 3)
+             for a_, b_ in zip(phase_events, phase_events[1:])]),
+            file=sys.stderr, flush=True)
 
     # ---- e2e: host x -> kNN lists on the host, through the public API ------
     # With several ranks the rows of x sit sharded over the ranks' pinned host

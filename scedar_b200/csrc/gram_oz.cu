@@ -1024,12 +1024,18 @@ int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
     const int G = oz_group_rows();
     std::vector<int64_t> us;
     const bool by_parity = getenv("SCEDAR_B200_OZ_P2P_MIXED") == nullptr;
+    const bool rotate = getenv("SCEDAR_B200_OZ_P2P_NOROTATE") == nullptr;
     for (int par = 0; par < 2; ++par)
       for (int64_t u = u0; u < u1; ++u)
         if (by_parity ? (u & 1) == par : par == 0) us.push_back(u);
     for (size_t g0 = 0; g0 < us.size(); g0 += G) {
       const size_t g1 = std::min(us.size(), g0 + (size_t)G);
-      for (int64_t v = 0; v < RT; ++v)
+      // every rank starts its sweep over the partners at its own stripe: at any
+      // time the ranks then store mirrored tiles into DIFFERENT peers (all of them
+      // sweeping from row tile 0 would aim every rank's NVLink traffic at one
+      // owner at a time)
+      for (int64_t vi = 0; vi < RT; ++vi) {
+        const int64_t v = rotate ? (u0 + vi) % RT : vi;
         for (int64_t J = 2 * v; J < std::min<int64_t>(2 * v + 2, CT); ++J)
           for (size_t gi = g0; gi < g1; ++gi) {
             const int64_t u = us[gi];
@@ -1043,6 +1049,7 @@ int launch_oz_stripe_p2p(const scedar_cells* c, int S, int rank, int world,
             if (by != rank || (owner(v) == rank && v > u)) continue;
             o->host_tiles.push_back(OzTile{(int32_t)u, (int32_t)J, TILE_DIRECT | TILE_MIRROR, 0});
           }
+      }
     }
   }
   SCEDAR_CHECK(oz_put_tiles(c, o, 1, rank, world, stripe_begin[rank], oz_group_rows(), s));
