@@ -474,8 +474,8 @@ def run_b200(a):
     # uploads its shard over its own PCIe link and the shards are all-gathered
     # over NVLink (stripes.gather_x) -- 1.6 GB cross the host links once in
     # total, in parallel, instead of through rank 0's link alone.
-    from scedar_b200.stripes import (gather_x, piece_layout, shard_rows,
-                                     take_shard)
+    from scedar_b200.stripes import (gather_x_from_host, piece_layout,
+                                     shard_rows, take_shard)
     sb, se = shard_rows(n, world)[rank]
     pipelined = world > 1 and prec != "fp64" and a.e2e_mode == "pipelined"
     if world > 1 and pipelined:
@@ -489,7 +489,10 @@ def run_b200(a):
         x_e2e = torch.empty((cap, p), dtype=torch.float64, device=dev)
     elif world > 1:
         shard_host = x_dev[sb:se].cpu().pin_memory()      # set-up, not timed
-        shard_dev = torch.empty((se - sb, p), dtype=torch.float64, device=dev)
+        rows_max = (n + world - 1) // world
+        shard_dev = torch.empty((rows_max, p), dtype=torch.float64, device=dev)
+        x_e2e = torch.empty((world * rows_max, p), dtype=torch.float64,
+                            device=dev)
 
     def e2e_step():
         if world == 1:
@@ -509,8 +512,10 @@ def run_b200(a):
             idx, dd = sdm.knn(k, EXCLUDE_FIRST)
             sdm.close()
         else:
-            shard_dev.copy_(shard_host, non_blocking=True)
-            idx, dd = step(gather_x(shard_dev, n), False)
+            # the shard goes up in four row ranges, each all-gathered over
+            # NVLink as it lands (under the rest of the upload)
+            idx, dd = step(gather_x_from_host(shard_host, n, shard_dev=shard_dev,
+                                              out=x_e2e), False)
         if rank == 0:
             idx_host.copy_(idx, non_blocking=True)
             dist_host.copy_(dd, non_blocking=True)
@@ -775,7 +780,8 @@ def run_b200(a):
                               world, " -- piece by piece (8 row pieces), the "
                               "contraction of a piece's rows running while "
                               "the next piece is uploaded and gathered"
-                              if pipelined else ""))},
+                              if pipelined else " range by range behind the "
+                              "upload (4 ranges)"))},
         "e2e_api": api,
         "gpu_launches": int(launches),
         "roofline": roof,

@@ -22,7 +22,7 @@ SDM_HOOKS = (
     "_validate_pdist", "_check_metric", "_cells", "_device_d", "_d_stripes",
     "_col_sort", "_knn_from_pdist", "release_device", "_is_sparse",
     "d_block", "_condensed_d", "_ref_hook", "_knn_by_full_sort", "_stripes_of",
-    "_gram_precision",
+    "_gram_precision", "_compute_device_d", "_knn_of_stripe",
 )
 SDM_STATIC_HOOKS = (
     "cosine_pdist", "correlation_pdist", "num_correct_dist_mat", "_static_pdist",
@@ -66,6 +66,7 @@ def install_sdm(cls):
         # HBM-side caches of the B200 path (not part of the reference's state)
         self._cells_lut = {}
         self._d_dev = None
+        self._bmin_dev = None
         self._knn_dev = None
         self._d_user = self._lazy_load_d is not None
 

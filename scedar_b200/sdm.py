@@ -28,6 +28,9 @@ from ._capi import (EXCLUDE_FIRST, EXCLUDE_SELF, METRIC_IDS, NCDM_ASYMMETRIC,
 DEVICE_D_CACHE_BYTES = 48 << 30
 # stripe size used when D is streamed to the host in pieces
 STRIPE_BYTES = 2 << 30
+# a dense host matrix of at least this size is uploaded range by range behind
+# the contraction instead of in one blocking copy
+UPLOAD_OVERLAP_BYTES = 64 << 20
 MAX_TOPK = 127
 FAST_MAX_K = 55     # the tensor-core pass re-ranks up to 64 candidates
 
@@ -153,6 +156,7 @@ class SampleDistanceMatrix(object):
         # device-side caches (not part of the reference's state)
         self._cells_lut = {}
         self._d_dev = None
+        self._bmin_dev = None   # block minima of _d_dev (INT8 split kernel only)
         self._d_user = d is not None
         self._knn_dev = None    # (k, exclude, metric, idx, dist) last lists in HBM
 
@@ -311,12 +315,47 @@ class SampleDistanceMatrix(object):
             free, _ = torch.cuda.mem_get_info()
             limit = max(limit, free // 2)
         if self._d_dev is None and n * n * 8 <= limit:
+            self._bmin_dev = None
             if self._lazy_load_d is not None:
                 self._d_dev = dev.to_device(self._lazy_load_d)
             else:
-                self._d_dev = self._cells(self._metric).pdist_symmetric(
-                    precision=self._gram_precision())
+                self._d_dev = self._compute_device_d()
         return self._d_dev
+
+    def _compute_device_d(self):
+        """The whole D of ``self._x`` into HBM.  With the INT8 split kernel the
+        block minima of D come with it (the selection then reads n/32 minima
+        per row instead of the row); a large dense host matrix that is not on
+        the device yet goes up range by range behind the contraction of the
+        rows already there (``device.pdist_symmetric_from_host``)."""
+        metric = self._metric
+        self._check_metric(metric)
+        prec = self._gram_precision()
+        n, p = self._x.shape
+        bmin = None
+        if prec in ("fp64_i8", "fp64_i8s6") and n >= 4096:
+            bmin = dev.new_blockmin(n, n)
+        if (metric not in self._cells_lut and not self._is_sparse
+                and prec != "fast" and n * p * 8 >= UPLOAD_OVERLAP_BYTES):
+            xh = torch.from_numpy(np.ascontiguousarray(self._x, dtype=np.float64))
+            cells, d = dev.pdist_symmetric_from_host(xh, metric, precision=prec,
+                                                     bmin=bmin)
+            self._cells_lut[metric] = cells
+        else:
+            cells = self._cells(metric)
+            if bmin is not None:
+                cells.set_blockmin([bmin])
+            d = cells.pdist_symmetric(precision=prec)
+        self._bmin_dev = bmin
+        return d
+
+    def _knn_of_stripe(self, stripe, r0, k, exclude):
+        """Top-k of the rows of a stripe yielded by ``_d_stripes``."""
+        bmin = getattr(self, "_bmin_dev", None)
+        if bmin is not None and stripe is self._d_dev:
+            return self._cells_lut[self._metric].knn_from_d_blockmin(
+                stripe, bmin, k, exclude, row_begin=r0)
+        return dev.knn_from_d(stripe, k, exclude, row_begin=r0)
 
     def _d_stripes(self):
         """Yield (row_begin, row_end, device stripe of D) covering all rows."""
@@ -505,7 +544,7 @@ class SampleDistanceMatrix(object):
             return i.cpu().numpy(), dd.cpu().numpy()
         parts = []
         for r0, r1, stripe in self._d_stripes():
-            i, dd = dev.knn_from_d(stripe, k, exclude, row_begin=r0)
+            i, dd = self._knn_of_stripe(stripe, r0, k, exclude)
             parts.append((i, dd))
             idx[r0:r1] = i.cpu().numpy()
             dist[r0:r1] = dd.cpu().numpy()
@@ -736,5 +775,6 @@ class SampleDistanceMatrix(object):
             c.close()
         self._cells_lut = {}
         self._d_dev = None
+        self._bmin_dev = None
         self._knn_dev = None
         torch.cuda.empty_cache()

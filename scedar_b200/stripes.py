@@ -64,6 +64,57 @@ def gather_x(x_rows, n, group=None):
     return out[:n]
 
 
+def gather_x_from_host(shard_host, n, group=None, shard_dev=None, out=None,
+                       device=None, chunks=4):
+    """``gather_x`` of row shards that still sit in the ranks' (pinned) HOST
+    buffers: the shard goes up in ``chunks`` row ranges on a copy stream and
+    every range is all-gathered on a communication stream as soon as it has
+    landed, so the NVLink exchange runs under the rest of the PCIe upload.
+    Returns the full [n, p] matrix (a view of ``out``, [world * ceil(n / world),
+    p]); work queued later on the current stream waits for it."""
+    world = dist.get_world_size(group)
+    chunk = (n + world - 1) // world
+    rows, p = shard_host.shape
+    device = device if device is not None else (
+        shard_dev.device if shard_dev is not None else shard_host.device)
+    if shard_dev is None:
+        shard_dev = torch.empty((chunk, p), dtype=shard_host.dtype, device=device)
+    if out is None:
+        out = torch.empty((world * chunk, p), dtype=shard_host.dtype,
+                          device=device)
+    assert shard_dev.shape[0] >= chunk and out.shape[0] >= world * chunk
+    on_gpu = out.is_cuda
+    if on_gpu:
+        from . import device as dev_
+        main = torch.cuda.current_stream()
+        copy, comm = dev_._copy_stream(), dev_._comm_stream()
+        copy.wait_stream(main)      # the buffers may still be read by earlier work
+        comm.wait_stream(main)
+    chunks = max(1, min(chunks, chunk))
+    for c in range(chunks):
+        c0, c1 = chunk * c // chunks, chunk * (c + 1) // chunks
+        if c1 <= c0:
+            continue
+        h1 = min(c1, rows)          # the last rank's shard may be short
+        views = [out[r * chunk + c0:r * chunk + c1] for r in range(world)]
+        if on_gpu:
+            with torch.cuda.stream(copy):
+                if h1 > c0:
+                    shard_dev[c0:h1].copy_(shard_host[c0:h1], non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(copy)
+            with torch.cuda.stream(comm):
+                comm.wait_event(up)
+                dist.all_gather(views, shard_dev[c0:c1], group=group)
+        else:
+            if h1 > c0:
+                shard_dev[c0:h1].copy_(shard_host[c0:h1])
+            dist.all_gather(views, shard_dev[c0:c1].contiguous(), group=group)
+    if on_gpu:
+        main.wait_stream(comm)
+    return out[:n]
+
+
 def piece_layout(n, world, n_pieces=8):
     """Row pieces for the pipelined multi-rank upload of x (``from_host_shards``):
     a list of ``(row_begin, row_end, rows_per_rank)``.  Piece boundaries are

@@ -195,3 +195,31 @@ def test_blockmin_guards(b200):
     with pytest.raises(ValueError):                        # ldb too small
         cells.set_blockmin([bmin], ldb=3)
     cells.close()
+
+
+def test_dropin_uses_minima_and_overlapped_upload(b200):
+    """Through the drop-in class: a dense host matrix large enough for the auto
+    policy's INT8 split kernel goes up range by range behind the contraction
+    (pageable source), D comes with its block minima, and the neighbour lists
+    -- selected through them -- equal the oracle's stable order on that D."""
+    import torch
+    from oracle import sdm_oracle as orc
+    from scedar_b200 import device as dev, synth
+    n, p, k = 6016, 1500, 15
+    x = synth.log_counts(n, p, seed=5)
+    sdm = b200.SampleDistanceMatrix(x, metric="correlation")
+    assert sdm._gram_precision() == "fp64_i8"
+    d = sdm._device_d()
+    assert sdm._bmin_dev is not None and tuple(d.shape) == (n, n)
+    # same matrix as the one-copy route
+    cells = dev.Cells.from_dense(dev.to_device(x), "correlation")
+    assert torch.equal(d, cells.pdist_symmetric(precision="fp64_i8"))
+    cells.close()
+    lut = sdm.s_knn_ind_lut(k)
+    want, _ = orc.knn_drop_first(d.cpu().numpy(), k)
+    assert np.array_equal(np.array([lut[i] for i in range(n)]), want)
+    ki, kd = sdm.s_knns(k)
+    ri, rd = orc.knns_precomputed(d.cpu().numpy(), k)
+    assert np.array_equal(np.asarray(ki), ri) and np.array_equal(np.asarray(kd), rd)
+    sdm.release_device()
+    assert sdm._bmin_dev is None

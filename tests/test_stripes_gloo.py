@@ -110,12 +110,17 @@ def _input_worker(rank, world, port, n, p, k, q):
         import scipy.sparse as sps
         from oracle import sdm_oracle as orc
         from scedar_b200.stripes import (StripedDistanceMatrix, gather_x,
-                                         shard_rows)
+                                         gather_x_from_host, shard_rows)
         rng = np.random.default_rng(9)
         xn = rng.random((n, p))
         b, e = shard_rows(n, world)[rank]
         full = gather_x(torch.from_numpy(xn[b:e].copy()), n)
         ok_gather = bool(np.array_equal(full.numpy(), xn))
+        # the chunked form (upload range by range, all-gather behind it)
+        for chunks in (1, 3, 1000):
+            full2 = gather_x_from_host(torch.from_numpy(xn[b:e].copy()), n,
+                                       device="cpu", chunks=chunks)
+            ok_gather = ok_gather and bool(np.array_equal(full2.numpy(), xn))
         xs = sps.random(n, p, density=0.2, format="csr", random_state=3).astype(np.float64)
         csr = None
         if rank == 0:
