@@ -337,7 +337,7 @@ class SampleDistanceMatrix(object):
             bmin = dev.new_blockmin(n, n)
         if (metric not in self._cells_lut and not self._is_sparse
                 and prec != "fast" and n * p * 8 >= UPLOAD_OVERLAP_BYTES):
-            xh = torch.from_numpy(np.ascontiguousarray(self._x, dtype=np.float64))
+            xh = np.ascontiguousarray(self._x, dtype=np.float64)
             cells, d = dev.pdist_symmetric_from_host(xh, metric, precision=prec,
                                                      bmin=bmin)
             self._cells_lut[metric] = cells

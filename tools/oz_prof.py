@@ -25,6 +25,8 @@ for _ in range(reps):
     a.record()
     cells.pdist_symmetric(out=d, precision=prec)
     b.record()
+    if os.environ.get("OZ_PROF_BLOCKMIN"):
+        cells.knn_from_d_blockmin(d, bmin, 15)
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 print("n={} p={} {}: ms {}".format(n, p, prec, ["%.3f" % t for t in ts]))
