@@ -77,10 +77,14 @@ def parse():
                          "steps may take; the sample shrinks to fit")
     ap.add_argument("--check-rows", type=int, default=64)
     ap.add_argument("--e2e-mode", default=os.environ.get(
-        "SCEDAR_BENCH_E2E_MODE", "simple"), choices=["simple", "pipelined"],
-        help="N > 1: 'simple' uploads the row shards, all-gathers x and runs "
-             "the step; 'pipelined' overlaps upload, all-gather and contraction "
-             "over 8 row pieces (StripedDistanceMatrix.from_host_shards)")
+        "SCEDAR_BENCH_E2E_MODE", "pieces"),
+        choices=["simple", "pipelined", "pieces"],
+        help="N > 1: 'pieces' (default) holds every rank's own stripe on its "
+             "host and overlaps upload, copy-engine exchange and contraction "
+             "over growing pieces of every stripe "
+             "(StripedDistanceMatrix.from_host_stripes); 'simple' uploads the "
+             "row shards, all-gathers x and runs the step; 'pipelined' is the "
+             "row-ordered form (from_host_shards)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the dmma_path / fast_path / e2e_api extras")
@@ -478,7 +482,13 @@ def run_b200(a):
                                      shard_rows, take_shard)
     sb, se = shard_rows(n, world)[rank]
     pipelined = world > 1 and prec != "fp64" and a.e2e_mode == "pipelined"
-    if world > 1 and pipelined:
+    pieces = world > 1 and prec != "fp64" and a.e2e_mode == "pieces"
+    if pieces:
+        # by-stripe shards: rank r holds the rows of its own D stripe
+        from scedar_b200.device import PeerStripes as _PS
+        shard_host = x_dev[r0:r1].cpu().pin_memory()      # set-up, not timed
+        xpeers = _PS([(0, n)] * world, p, rank=rank)
+    elif world > 1 and pipelined:
         # piece-interleaved row shards: rank r holds its 1/N of every row piece
         layout = piece_layout(n, world, 8)
         shard_host = take_shard(x_dev[:n], layout, rank, world).cpu() \
@@ -502,6 +512,14 @@ def run_b200(a):
             sdm = StripedDistanceMatrix.from_host(x_host, a.metric, out=d_buf,
                                                   x_dev=x_dev, precision=prec,
                                                   bmin=bmin_buf)
+            idx, dd = sdm.knn(k, EXCLUDE_FIRST)
+            sdm.close()
+        elif pieces:
+            sdm = StripedDistanceMatrix.from_host_stripes(
+                shard_host, (n, p), peers, xpeers, metric=a.metric,
+                precision=prec,
+                n_pieces=int(os.environ["SCEDAR_BENCH_PIECES"])
+                if os.environ.get("SCEDAR_BENCH_PIECES") else None)
             idx, dd = sdm.knn(k, EXCLUDE_FIRST)
             sdm.close()
         elif pipelined:
@@ -671,6 +689,8 @@ def run_b200(a):
         del d_buf
         peers.close()
         peers = None
+        if pieces:
+            xpeers.close()
 
     # ---- e2e_api (N = 1): the plugin call a scedar user makes ----------------
     api = None
@@ -780,8 +800,13 @@ def run_b200(a):
                               world, " -- piece by piece (8 row pieces), the "
                               "contraction of a piece's rows running while "
                               "the next piece is uploaded and gathered"
-                              if pipelined else " range by range behind the "
-                              "upload (4 ranges)"))},
+                              if pipelined else
+                              " range by range behind the upload (4 ranges)"
+                              if not pieces else
+                              " -- by stripe: growing pieces (1/16 ... 1/2) of every stripe, pushed "
+                              "into the peers' x buffers by copy engines while "
+                              "the pairs of the pieces already there are "
+                              "contracted"))},
         "e2e_api": api,
         "gpu_launches": int(launches),
         "roofline": roof,

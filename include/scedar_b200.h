@@ -136,6 +136,17 @@ int scedar_cells_alloc(int64_t n, int64_t p, int metric, void* stream,
 int scedar_cells_fill_rows(scedar_cells_t* cells, const double* x_rows,
                            int64_t ldx, int64_t row_begin, int64_t row_end,
                            void* stream);
+/* The same with the Gram diagonal -- the per-cell statistic the DMMA and 3xFP16
+ * kernels read -- optional (with_stat = 0): many small ranges then cost one
+ * preparation pass each instead of a preparation pass and a 128-row tile
+ * contraction.  The INT8 split kernels take their statistic from the byte
+ * slices and need nothing else; before any other kernel uses the handle, run
+ * scedar_cells_stat_rows over the rows that were filled without it. */
+int scedar_cells_fill_rows_ex(scedar_cells_t* cells, const double* x_rows,
+                              int64_t ldx, int64_t row_begin, int64_t row_end,
+                              int with_stat, void* stream);
+int scedar_cells_stat_rows(scedar_cells_t* cells, int64_t row_begin,
+                           int64_t row_end, void* stream);
 
 /* Stream-ordered on the stream the cells were created on (work that reads the
  * cells on another stream must have been synchronised with it). */
@@ -185,6 +196,22 @@ int scedar_pdist_p2p_rows(const scedar_cells_t* cells, int precision, int rank,
                           double* const* stripe_ptr, int64_t ldd,
                           int64_t row_begin, int64_t row_end, int reserve_sms,
                           void* stream);
+
+/* Piece form of scedar_pdist_stripe_p2p, for x that sits row-sharded BY STRIPE in
+ * the ranks' host memories and is uploaded and exchanged in n_pieces pieces, piece
+ * q being the q-th part of EVERY stripe (piece_of_tile[T], T < ceil(n / 128): the
+ * piece that brings row tile T; scedar_cells_alloc + scedar_cells_fill_rows as
+ * the rows land).  Launch `piece` contracts the pairs of row tiles whose later
+ * tile arrives with that piece, owned and oriented as in scedar_pdist_stripe_p2p
+ * (tile into the rank's own stripe, mirrored tile over NVLink), so every rank
+ * gets the same share of every launch while the next piece is on its way.
+ * Launches 0 .. n_pieces-1 on every rank yield the matrix of
+ * scedar_pdist_stripe_p2p bit for bit.  INT8 split kernels only. */
+int scedar_pdist_p2p_pieces(const scedar_cells_t* cells, int precision, int rank,
+                            int world, const int64_t* stripe_begin,
+                            double* const* stripe_ptr, int64_t ldd,
+                            const int32_t* piece_of_tile, int piece, int n_pieces,
+                            int reserve_sms, void* stream);
 
 /* Stripe buffers that can be mapped by the peer processes of one node
  * (cudaMalloc + CUDA IPC).  handle64 is a 64-byte opaque blob to ship to the

@@ -35,6 +35,9 @@ SIGNATURES = {
                                    POINTER(c_void_p)]),
     "scedar_cells_fill_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64,
                                        c_int64, c_void_p]),
+    "scedar_cells_fill_rows_ex": (c_int, [c_void_p, c_void_p, c_int64, c_int64,
+                                          c_int64, c_int, c_void_p]),
+    "scedar_cells_stat_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "scedar_pdist_lower_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p,
                                         c_int64, c_void_p]),
     "scedar_pdist_lower_rows_prec": (c_int, [c_void_p, c_int, c_int64, c_int64,
@@ -59,6 +62,10 @@ SIGNATURES = {
                                       POINTER(c_int64), POINTER(c_void_p),
                                       c_int64, c_int64, c_int64, c_int,
                                       c_void_p]),
+    "scedar_pdist_p2p_pieces": (c_int, [c_void_p, c_int, c_int, c_int,
+                                        POINTER(c_int64), POINTER(c_void_p),
+                                        c_int64, POINTER(ctypes.c_int32), c_int,
+                                        c_int, c_int, c_void_p]),
     "scedar_stripe_alloc": (c_int, [ctypes.c_size_t, POINTER(c_void_p)]),
     "scedar_stripe_free": (c_int, [c_void_p]),
     "scedar_stripe_export": (c_int, [c_void_p, c_void_p]),

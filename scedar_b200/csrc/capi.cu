@@ -274,6 +274,22 @@ int scedar_cells_alloc(int64_t n, int64_t p, int metric, void* stream, scedar_ce
 
 int scedar_cells_fill_rows(scedar_cells_t* c, const double* x_rows, int64_t ldx,
                            int64_t row_begin, int64_t row_end, void* stream) {
+  return scedar_cells_fill_rows_ex(c, x_rows, ldx, row_begin, row_end, 1, stream);
+}
+
+int scedar_cells_stat_rows(scedar_cells_t* c, int64_t row_begin, int64_t row_end, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  if (row_begin < 0 || row_end < row_begin || row_end > c->n)
+    return fail(SCEDAR_ERR_ARG, "row range must satisfy 0 <= row_begin <= row_end <= n");
+  if (row_begin % kRowPad != 0 || (row_end % kRowPad != 0 && row_end != c->n))
+    return fail(SCEDAR_ERR_ARG, "row ranges must be 128-aligned (the last one may end at n)");
+  if (row_end == row_begin) return SCEDAR_OK;
+  return launch_gram_diag_rows(c, row_begin, row_end == c->n ? c->n_pad : row_end,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int scedar_cells_fill_rows_ex(scedar_cells_t* c, const double* x_rows, int64_t ldx,
+                              int64_t row_begin, int64_t row_end, int with_stat, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
   if (row_begin < 0 || row_end < row_begin || row_end > c->n)
@@ -287,6 +303,10 @@ int scedar_cells_fill_rows(scedar_cells_t* c, const double* x_rows, int64_t ldx,
   const int64_t pad_end = row_end == c->n ? c->n_pad : row_end;
   SCEDAR_CHECK(launch_prep_dense(x_rows, row_end - row_begin, c->p, ldx, c->metric,
                                  c->xw + row_begin * c->p_pad, pad_end - row_begin, c->p_pad, s));
+  // the Gram diagonal (the statistic of the DMMA / 3xFP16 kernels) may be left
+  // to one later scedar_cells_stat_rows pass: the INT8 split kernels take theirs
+  // from the slices
+  if (!with_stat) return SCEDAR_OK;
   return launch_gram_diag_rows(c, row_begin, pad_end, s);
 }
 
@@ -392,6 +412,26 @@ int scedar_pdist_p2p_rows(const scedar_cells_t* c, int precision, int rank, int 
                 "(precision fp64_i8 / fp64_i8s6)");
   return launch_oz_p2p_rows(c, S, rank, world, stripe_begin, stripe_ptr, ldd, row_begin, row_end,
                             reserve_sms, static_cast<cudaStream_t>(stream));
+}
+
+int scedar_pdist_p2p_pieces(const scedar_cells_t* c, int precision, int rank, int world,
+                            const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
+                            const int32_t* piece_of_tile, int piece, int n_pieces,
+                            int reserve_sms, void* stream) {
+  if (!c) return fail(SCEDAR_ERR_ARG, "cells handle is NULL");
+  SCEDAR_CHECK(check_precision(precision));
+  if (!stripe_begin || !stripe_ptr || !piece_of_tile)
+    return fail(SCEDAR_ERR_ARG, "NULL stripe / piece table");
+  if (ldd < c->n) return fail(SCEDAR_ERR_ARG, "ldd must be >= n");
+  if (reserve_sms < 0) return fail(SCEDAR_ERR_ARG, "reserve_sms must be >= 0");
+  if (c->n == 0) return SCEDAR_OK;
+  const int S = oz_slices(c, precision);
+  if (!S)
+    return fail(SCEDAR_ERR_UNSUPPORTED,
+                "the piece form of the peer-store contraction runs on the INT8 split kernel "
+                "(precision fp64_i8 / fp64_i8s6)");
+  return launch_oz_p2p_pieces(c, S, rank, world, stripe_begin, stripe_ptr, ldd, piece_of_tile,
+                              piece, n_pieces, reserve_sms, static_cast<cudaStream_t>(stream));
 }
 
 // ---- PCA producer pieces ------------------------------------------------------

@@ -145,6 +145,10 @@ int launch_oz_lower_rows(const scedar_cells* c, int S, int64_t row_begin, int64_
 int launch_oz_p2p_rows(const scedar_cells* c, int S, int rank, int world,
                        const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
                        int64_t row_begin, int64_t row_end, int reserve_sms, cudaStream_t s);
+int launch_oz_p2p_pieces(const scedar_cells* c, int S, int rank, int world,
+                         const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
+                         const int32_t* piece_of_tile, int piece, int n_pieces, int reserve_sms,
+                         cudaStream_t s);
 // capi.cu: the FP64 kNN of a row range (fused when k+1 <= 32); oz_S = 6 / 7
 // computes the distances with the INT8 split kernel instead of DMMA
 int knn_stripe_fp64(const scedar_cells* c, int k, int exclude, int64_t row_begin,

@@ -1147,4 +1147,102 @@ int launch_oz_p2p_rows(const scedar_cells* c, int S, int rank, int world,
   return oz_launch(c, o, a, s, reserve_sms);
 }
 
+// Piece form of the peer-store contraction, for cells that arrive in `pieces` of
+// row tiles taken from EVERY stripe at once (piece_of_tile[T] = the piece that
+// brings row tile T; a rank's host shard is its own stripe, so piece q is the
+// q-th part of every stripe).  Launch q computes the tile pairs {u, v} whose
+// later tile arrives with piece q, under the ownership and orientation of
+// launch_oz_stripe_p2p: a rank contracts its own row tiles against everybody's,
+// stores the tile into its own stripe and only the mirrored tile over NVLink,
+// and every rank gets the same share of every launch.  Called for q = 0, 1, ...
+// on every rank it yields the matrix of launch_oz_stripe_p2p bit for bit.
+int launch_oz_p2p_pieces(const scedar_cells* c, int S, int rank, int world,
+                         const int64_t* stripe_begin, double* const* stripe_ptr, int64_t ldd,
+                         const int32_t* piece_of_tile, int piece, int n_pieces, int reserve_sms,
+                         cudaStream_t s) {
+  if (world < 1 || world > kOzPeers) return fail(SCEDAR_ERR_ARG, "world must be in 1..16");
+  if (rank < 0 || rank >= world) return fail(SCEDAR_ERR_ARG, "rank out of range");
+  if (piece < 0 || piece >= n_pieces) return fail(SCEDAR_ERR_ARG, "piece out of range");
+  const int64_t n = c->n;
+  for (int r = 0; r <= world; ++r) {
+    const int64_t b = stripe_begin[r];
+    if (!(b % OM == 0 || b == n) || (r > 0 && b < stripe_begin[r - 1]))
+      return fail(SCEDAR_ERR_ARG, "stripes must be ascending and 128-row aligned");
+  }
+  if (stripe_begin[0] != 0 || stripe_begin[world] != n)
+    return fail(SCEDAR_ERR_ARG, "stripes must cover [0, n)");
+  const int64_t RT = (n + OM - 1) / OM;
+  for (int64_t T = 0; T < RT; ++T)
+    if (piece_of_tile[T] < 0 || piece_of_tile[T] >= n_pieces)
+      return fail(SCEDAR_ERR_ARG, "piece_of_tile entries must be in [0, n_pieces)");
+  OzState* o = nullptr;
+  SCEDAR_CHECK(oz_alloc(c, S, s, &o));
+  // slice the row tiles this piece brought (runs of consecutive tiles; the last
+  // tile of the matrix takes the padding rows with it)
+  for (int64_t T = 0; T < RT;) {
+    if (piece_of_tile[T] != piece) {
+      ++T;
+      continue;
+    }
+    int64_t T1 = T;
+    while (T1 < RT && piece_of_tile[T1] == piece) ++T1;
+    const int64_t e = T1 == RT ? c->n_pad : T1 * OM;
+    SCEDAR_CHECK(oz_slice_rows(c, o, T * OM, std::min<int64_t>(e, c->n_pad), s));
+    T = T1;
+  }
+  if (n_pieces == 1) o->sliced_all = true;
+  auto owner = [&](int64_t T) {
+    int r = 0;
+    while (r + 1 < world && T * OM >= stripe_begin[r + 1]) ++r;
+    return r;
+  };
+  // key: the layout is a function of (n, world, n_pieces) for the callers in
+  // this package; a different table under the same key would need its own mode
+  long long key = 1469598103934665603ll;
+  for (int64_t T = 0; T < RT; ++T) key = (key ^ piece_of_tile[T]) * 1099511628211ll;
+  if (!oz_have_tiles(c, o, 4, rank * 64 + world, piece * 64 + n_pieces, key, oz_group_rows())) {
+    o->host_tiles.clear();
+    const int64_t CT = (n + ON - 1) / ON;
+    const int64_t u0 = stripe_begin[rank] / OM, u1 = (stripe_begin[rank + 1] + OM - 1) / OM;
+    const int G = oz_group_rows();
+    std::vector<int64_t> us;
+    for (int par = 0; par < 2; ++par)
+      for (int64_t u = u0; u < u1; ++u)
+        if ((u & 1) == par && piece_of_tile[u] <= piece) us.push_back(u);
+    for (size_t g0 = 0; g0 < us.size(); g0 += G) {
+      const size_t g1 = std::min(us.size(), g0 + (size_t)G);
+      for (int64_t vi = 0; vi < RT; ++vi) {
+        const int64_t v = (u0 + vi) % RT;
+        if (piece_of_tile[v] > piece) continue;
+        for (int64_t J = 2 * v; J < std::min<int64_t>(2 * v + 2, CT); ++J)
+          for (size_t gi = g0; gi < g1; ++gi) {
+            const int64_t u = us[gi];
+            if (std::max(piece_of_tile[u], piece_of_tile[v]) != piece) continue;
+            if (u == v) {
+              o->host_tiles.push_back(OzTile{(int32_t)u, (int32_t)J, TILE_DIRECT, 0});
+              continue;
+            }
+            const int64_t hi = std::max(u, v), lo = std::min(u, v);
+            const int by = owner(((hi + lo) & 1) == 0 ? hi : lo);
+            if (by != rank || (owner(v) == rank && v > u)) continue;
+            o->host_tiles.push_back(OzTile{(int32_t)u, (int32_t)J, TILE_DIRECT | TILE_MIRROR, 0});
+          }
+      }
+    }
+  }
+  SCEDAR_CHECK(oz_put_tiles(c, o, 4, rank * 64 + world, piece * 64 + n_pieces, key,
+                            oz_group_rows(), s));
+  OzArgs a{};
+  a.ldd = ldd;
+  a.world = world;
+  for (int r = 0; r < world; ++r) {
+    a.stripe_begin[r] = stripe_begin[r];
+    a.stripe_ptr[r] = stripe_ptr[r];
+  }
+  a.stripe_begin[world] = stripe_begin[world];
+  a.row_lo = 0;
+  a.row_hi = n;
+  return oz_launch(c, o, a, s, reserve_sms);
+}
+
 }  // namespace scedar

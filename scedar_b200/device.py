@@ -100,18 +100,27 @@ class Cells(object):
             int(n), int(p), METRIC_IDS[metric], _stream(), ctypes.byref(h)))
         return cls(h, n, p, metric)
 
-    def fill_rows(self, x_rows, row_begin):
+    def fill_rows(self, x_rows, row_begin, with_stat=True):
         """Prepare the cells [row_begin, row_begin + len(x_rows)) from a
-        float64 device tensor (128-aligned ranges, the last one ends at n)."""
+        float64 device tensor (128-aligned ranges, the last one ends at n).
+        ``with_stat=False`` leaves the Gram diagonal (the statistic of the DMMA
+        and 3xFP16 kernels; the INT8 split kernels do not read it) to a later
+        ``stat_rows`` pass."""
         x_rows = _f64(x_rows)
         if x_rows.dim() != 2 or x_rows.shape[1] != self.p:
             raise ValueError("x_rows has shape (rows, n_features)")
         if x_rows.stride(1) != 1 and self.p > 1:
             x_rows = x_rows.contiguous()
         ldx = x_rows.stride(0) if x_rows.shape[0] > 1 else max(self.p, 1)
-        _capi.check(_capi.load().scedar_cells_fill_rows(
+        _capi.check(_capi.load().scedar_cells_fill_rows_ex(
             self._h, _ptr(x_rows), max(ldx, self.p), int(row_begin),
-            int(row_begin) + x_rows.shape[0], _stream()))
+            int(row_begin) + x_rows.shape[0], int(bool(with_stat)), _stream()))
+
+    def stat_rows(self, row_begin=0, row_end=None):
+        """The Gram diagonal of rows filled with ``with_stat=False``."""
+        row_end = self.n if row_end is None else row_end
+        _capi.check(_capi.load().scedar_cells_stat_rows(
+            self._h, int(row_begin), int(row_end), _stream()))
 
     def pdist_lower_rows(self, row_begin, row_end, out, precision="fp64"):
         """Rows [row_begin, row_end) of the lower triangle of the whole
@@ -451,6 +460,18 @@ def pdist_p2p_rows(cells, peers, rank, row_begin, row_end, precision="fp64_i8",
     _capi.check(_capi.load().scedar_pdist_p2p_rows(
         cells._h, PRECISION_IDS[precision], rank, peers.world, begins, ptrs,
         peers.n, int(row_begin), int(row_end), int(reserve_sms), _stream()))
+
+
+def pdist_p2p_pieces(cells, peers, rank, piece_of_tile, piece, n_pieces,
+                     precision="fp64_i8", reserve_sms=0):
+    """Piece form of ``pdist_stripe_p2p`` (INT8 split kernels): the pairs of
+    row tiles whose later tile arrived with ``piece`` (``piece_of_tile``: int32
+    per row tile), owned and oriented as in the whole-matrix form."""
+    begins, ptrs = peers.tables()
+    table = (ctypes.c_int32 * len(piece_of_tile))(*[int(v) for v in piece_of_tile])
+    _capi.check(_capi.load().scedar_pdist_p2p_pieces(
+        cells._h, PRECISION_IDS[precision], rank, peers.world, begins, ptrs,
+        peers.n, table, int(piece), int(n_pieces), int(reserve_sms), _stream()))
 
 
 # ---------------------------------------------------------------------------

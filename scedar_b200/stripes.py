@@ -135,6 +135,42 @@ def piece_layout(n, world, n_pieces=8):
     return out
 
 
+GROWING_PIECES = (1 / 16, 1 / 8, 1 / 4, 1 / 2, 1.0)
+"""Cumulative fractions of a stripe that the pieces of the by-stripe pipeline
+bring: the work a piece unlocks grows with the square of what has arrived, so
+the first piece is small (the contraction starts almost at once) and every
+later upload hides behind a longer contraction."""
+
+
+def stripe_pieces(stripes, n, n_pieces=8, cuts=None):
+    """Pieces for the by-stripe pipelined upload (``from_host_stripes``): piece q
+    is the q-th part of EVERY stripe, in whole row tiles -- ``n_pieces`` equal
+    parts, or up to the cumulative fractions ``cuts`` (ascending, last = 1).
+    Returns ``(piece_of_tile, ranges)``: the piece of each of the ceil(n / 128)
+    row tiles, and ``ranges[q][r]`` = the rows ``(begin, end)`` of stripe r that
+    piece q brings (possibly empty)."""
+    if cuts is None:
+        cuts = [(q + 1) / n_pieces for q in range(n_pieces)]
+    cuts = list(cuts)
+    assert cuts and abs(cuts[-1] - 1.0) < 1e-12 and cuts == sorted(cuts)
+    n_pieces = len(cuts)
+    tiles = (n + TILE - 1) // TILE
+    piece_of_tile = [0] * tiles
+    ranges = [[(0, 0)] * len(stripes) for _ in range(n_pieces)]
+    for r, (b, e) in enumerate(stripes):
+        t0, t1 = b // TILE, (e + TILE - 1) // TILE
+        if e <= b:
+            t1 = t0
+        for q in range(n_pieces):
+            a0 = t0 + (int((t1 - t0) * cuts[q - 1] + 1e-9) if q else 0)
+            a1 = t0 + (int((t1 - t0) * cuts[q] + 1e-9) if q + 1 < n_pieces
+                       else t1 - t0)
+            for t in range(a0, a1):
+                piece_of_tile[t] = q
+            ranges[q][r] = (min(a0 * TILE, n), min(a1 * TILE, n))
+    return piece_of_tile, ranges
+
+
 def take_shard(x, layout, rank, world):
     """Rank ``rank``'s host shard of x for ``layout``: its sub-range of every
     piece, one after the other, each padded with zero rows to the piece's
@@ -328,6 +364,90 @@ class StripedDistanceMatrix(object):
             device.pdist_p2p_rows(self.cells, peers, rank, b, e,
                                   precision=precision, reserve_sms=reserve_sms)
             off += m
+        self._fence()              # every peer store has landed
+        self.d_stripe = peers.tensor(rank)
+        return self
+
+    @classmethod
+    def from_host_stripes(cls, shard_host, shape, peers, xpeers,
+                          metric="correlation", precision="fp64_i8", group=None,
+                          n_pieces=None, reserve_sms=2):
+        """Several ranks, x row-sharded BY STRIPE over the ranks' pinned HOST
+        buffers (``shard_host`` = the rows of this rank's own D stripe): upload,
+        exchange and contraction as a pipeline over pieces, piece q being the
+        q-th part of every stripe (``stripe_pieces``: ``n_pieces`` equal parts,
+        default the growing ``GROWING_PIECES``).  A rank copies
+        its part of piece q over its own PCIe link into its x buffer, pushes it
+        into every peer's x buffer with copy-engine transfers over NVLink
+        (``xpeers``: ``device.PeerStripes([(0, n)] * world, p)``, one [n, p]
+        buffer per rank) and a one-element all-reduce tells everybody that the
+        piece is complete; the cells it brought are then prepared and the pairs
+        of row tiles whose later tile just arrived are contracted
+        (``device.pdist_p2p_pieces``: the ownership and orientation of the
+        whole-matrix form, so every rank gets an equal share of every piece and
+        only mirrored tiles cross NVLink) while the next piece is on its way.
+        ``reserve_sms`` SMs stay free for the all-reduce kernels.  On return D
+        (this rank's stripe of ``peers``, with its block minima) is complete on
+        every rank, bit-identical to ``compute_d(peers=...)``."""
+        from . import device
+        self = cls.__new__(cls)
+        self.ops = _DeviceOps()
+        self.group = group
+        self.distributed = True
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.n, self.p = shape
+        n, p, world, rank = self.n, self.p, self.world, self.rank
+        self.metric, self.precision = metric, precision
+        self.stripes = partition(n, world)
+        self.row_begin, self.row_end = self.stripes[rank]
+        assert tuple(shard_host.shape) == (self.row_end - self.row_begin, p)
+        if n_pieces is None:
+            piece_of_tile, ranges = stripe_pieces(self.stripes, n,
+                                                  cuts=GROWING_PIECES)
+        else:
+            piece_of_tile, ranges = stripe_pieces(self.stripes, n, n_pieces)
+        n_pieces = len(ranges)
+        xs = [xpeers.tensor(r) for r in range(world)]       # [n, p] per rank
+        mine = xs[rank]
+        self.d_device = mine.device
+        main = torch.cuda.current_stream()
+        copy, comm = device._copy_stream(), device._comm_stream()
+        self._fence()          # nobody still reads a D stripe or an x buffer
+        copy.wait_stream(main)
+        comm.wait_stream(main)
+        self.cells = device.Cells.alloc(n, p, metric)
+        self.bmin = None
+        if getattr(peers, "blockmin", False) and precision in I8_PRECISIONS:
+            self.cells.set_blockmin(peers.bmin_ptrs(), peers.ldb)
+            self.bmin = peers.bmin_tensor(rank)
+        for q in range(n_pieces):
+            b, e = ranges[q][rank]
+            with torch.cuda.stream(copy):
+                if e > b:
+                    mine[b:e].copy_(shard_host[b - self.row_begin:e - self.row_begin],
+                                    non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(copy)
+            with torch.cuda.stream(comm):
+                comm.wait_event(up)
+                if e > b:
+                    for r in range(world):
+                        if r != rank:
+                            xs[r][b:e].copy_(mine[b:e], non_blocking=True)
+                self._fence()          # on comm: every rank has pushed piece q
+                landed = torch.cuda.Event()
+                landed.record(comm)
+            main.wait_event(landed)
+            for r in range(world):
+                rb, re_ = ranges[q][r]
+                if re_ > rb:
+                    self.cells.fill_rows(mine[rb:re_], rb, with_stat=False)
+            device.pdist_p2p_pieces(
+                self.cells, peers, rank, piece_of_tile, q, n_pieces,
+                precision=precision,
+                reserve_sms=reserve_sms if q + 1 < n_pieces else 0)
+        self.cells.stat_rows()     # one pass: the handle is complete for any kernel
         self._fence()              # every peer store has landed
         self.d_stripe = peers.tensor(rank)
         return self

@@ -133,7 +133,7 @@ def test_peer_store_forms_single_gpu_emulation(b200):
     import torch
     from scedar_b200 import device as dev
     from scedar_b200._capi import EXCLUDE_SELF
-    from scedar_b200.stripes import partition, piece_layout
+    from scedar_b200.stripes import partition, piece_layout, stripe_pieces
     n, p = 1900, 90
     x = torch.from_numpy(case(21, n, p)).cuda()
     for metric in ("correlation", "euclidean"):
@@ -143,7 +143,7 @@ def test_peer_store_forms_single_gpu_emulation(b200):
         nb = want.shape[1]
         for world in (2, 3, 8):
             parts = partition(n, world)
-            for form in ("stripe", "rows"):
+            for form in ("stripe", "rows", "pieces1", "pieces3", "pieces8", "pieces0"):
                 peers = dev.PeerStripes(parts, n, blockmin=True)
                 for r in range(world):
                     peers.tensor(r).fill_(-7.0)
@@ -152,10 +152,25 @@ def test_peer_store_forms_single_gpu_emulation(b200):
                 for r in range(world):
                     if form == "stripe":
                         dev.pdist_stripe_p2p(cells, peers, r, precision="fp64_i8")
+                    elif form.startswith("pieces"):
+                        continue
                     else:
                         for b, e, _ in piece_layout(n, world, 3):
                             dev.pdist_p2p_rows(cells, peers, r, b, e,
                                                precision="fp64_i8")
+                if form.startswith("pieces"):
+                    # pieces of every stripe at once, launch q on every rank
+                    nq = int(form[6:])
+                    if nq:
+                        table, _ = stripe_pieces(parts, n, nq)
+                    else:           # the growing default of from_host_stripes
+                        from scedar_b200.stripes import GROWING_PIECES
+                        table, rg = stripe_pieces(parts, n, cuts=GROWING_PIECES)
+                        nq = len(rg)
+                    for q in range(nq):
+                        for r in range(world):
+                            dev.pdist_p2p_pieces(cells, peers, r, table, q, nq,
+                                                 precision="fp64_i8")
                 torch.cuda.synchronize()
                 for r, (b, e) in enumerate(parts):
                     assert torch.equal(peers.tensor(r), full[b:e]), (metric, world, form, r)

@@ -137,3 +137,33 @@ def test_piece_layout_and_shards():
                 xd[b + r * m:b + (r + 1) * m] = shards[r][off:off + m]
             off += m
         assert torch.equal(xd[:n], x)
+
+
+def test_stripe_pieces_cover_every_tile_once():
+    """Pieces of the by-stripe pipelined upload: every row tile belongs to one
+    piece, a piece takes a contiguous part of every stripe, in order."""
+    from scedar_b200.stripes import partition, stripe_pieces
+    for n, world, nq in ((100000, 8, 8), (1900, 3, 8), (130, 2, 4), (3005, 8, 3),
+                         (128, 1, 8), (1, 2, 2)):
+        parts = partition(n, world)
+        if nq == 3:
+            from scedar_b200.stripes import GROWING_PIECES
+            table, ranges = stripe_pieces(parts, n, cuts=GROWING_PIECES)
+            nq = len(GROWING_PIECES)
+        else:
+            table, ranges = stripe_pieces(parts, n, nq)
+        tiles = (n + 127) // 128
+        assert len(table) == tiles and all(0 <= q < nq for q in table)
+        for r, (b, e) in enumerate(parts):
+            pos = b
+            for q in range(nq):
+                rb, re_ = ranges[q][r]
+                if re_ > rb:
+                    assert rb == pos and rb % 128 == 0
+                    assert all(table[t] == q for t in range(rb // 128, (re_ + 127) // 128))
+                    pos = re_
+            assert pos == e or e <= b
+        # non-decreasing inside a stripe
+        for b, e in parts:
+            seq = table[b // 128:(e + 127) // 128]
+            assert seq == sorted(seq)

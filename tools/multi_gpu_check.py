@@ -68,7 +68,7 @@ def main():
     xh = synth.blobs(n, p, seed=3) if rank == 0 else None
     x = dev.to_device(xh) if rank == 0 else None
     sdm = StripedDistanceMatrix(x, "euclidean", shape=(n, p), device=device)
-    peers = sdm.make_peer_stripes()
+    peers = dev.PeerStripes(sdm.stripes, n, rank=rank, blockmin=True)
     _, t_d = timed(lambda: sdm.compute_d(peers=peers))
     out["d_p2p_ms"] = round(t_d, 2)
     idx, dd = sdm.knn(k, EXCLUDE_FIRST)
@@ -169,6 +169,26 @@ def main():
         flag = torch.tensor([1.0 if same else 0.0], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         assert float(flag.item()) == 1.0, "pipelined D ({}) differs".format(prec)
+        # the by-stripe pipeline: every rank holds its own stripe's rows on the
+        # host; pieces of every stripe at once, copy-engine exchange over NVLink
+        xpeers = dev.PeerStripes([(0, n)] * world, p, rank=rank)
+        shard2 = xb[s8.row_begin:s8.row_end].cpu().pin_memory()
+        peers.tensor(rank).fill_(-6.0)
+        for _ in range(2):
+            s10, t_pc = timed(lambda: StripedDistanceMatrix.from_host_stripes(
+                shard2, (n, p), peers, xpeers, metric="euclidean", precision=prec))
+            k_i, k_d = s10.knn(k, EXCLUDE_SELF)
+            s10.close()
+        out["d_pieces_{}_ms".format(prec)] = round(t_pc, 2)
+        same = bool(torch.equal(d1[s8.row_begin:s8.row_end], peers.tensor(rank)))
+        r_i, r_d = dev.knn_from_d(d1, k, EXCLUDE_SELF)
+        same = same and bool(torch.equal(k_i, r_i) and torch.equal(k_d, r_d))
+        flag = torch.tensor([1.0 if same else 0.0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert float(flag.item()) == 1.0, "by-stripe pipelined D ({}) differs".format(prec)
+        torch.cuda.synchronize()
+        dist.barrier()
+        xpeers.close()
         del d1
         s8.close()
     peers.close()
