@@ -51,6 +51,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TRACE = bool(os.environ.get("SCEDAR_BENCH_TRACE"))
+# tools/umma_probe sustained (profiles/r02_umma_sustained.log): the S = 7 MMA
+# schedule alone, random operand bytes, power-capped: 3,819-3,905 TOP/s executed
+INT8_MMA_ONLY_SUSTAINED_TOPS = 3860.0
 METRIC = "cell_pair_distances_per_s"
 UNIT = "pairs/s"
 
@@ -765,6 +768,13 @@ def run_b200(a):
                            "MAC/cycle/SM); of measured".format(bf16),
             "frac_of_burst_peak": executed / (2.0 * peaks.get(
                 "bf16_tflops", 1640.9)),
+            # what THIS instruction schedule sustains on this board from
+            # operands resident in shared memory (no TMA, no epilogue), random
+            # operand bytes, 170 ms under the power cap:
+            # profiles/r02_umma_sustained.log
+            "int8_mma_only_sustained_tops": INT8_MMA_ONLY_SUSTAINED_TOPS,
+            "frac_of_int8_mma_only_sustained": (
+                executed / INT8_MMA_ONLY_SUSTAINED_TOPS),
             "vs_fp64_dmma_peak": achieved / fp64_peak_tflops()}
     roof.update({"algorithmic_flops_per_launch": alg_flops,
                  "ms_per_launch": gram_avg_ms,

@@ -328,7 +328,7 @@ __device__ __forceinline__ void tmem_cp(uint32_t taddr, uint64_t sdesc) {
   asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 __global__ void __launch_bounds__(128, 1)
-rate2_kernel(int N, int mode, int iters, unsigned long long* out) {
+rate2_kernel(int N, int mode, int iters, unsigned long long* out, int random_fill = 0) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -340,7 +340,8 @@ rate2_kernel(int N, int mode, int iters, unsigned long long* out) {
   volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(g + (bars - base) + 64);
   const int warp = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < (bars - base) / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(g)[i] = 0x01020301u;
+    reinterpret_cast<uint32_t*>(g)[i] =
+        random_fill ? (i * 2654435761u ^ (i >> 7) * 40503u ^ 0x9e3779b9u) * 2246822519u : 0x01020301u;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x == 0) {
     mbar_init(done, 1);
@@ -782,6 +783,41 @@ static void run_rate(int N, int S, int mode) {
   cudaFree(out);
 }
 
+// ---- sustained: the stacked S = 7 schedule from RESIDENT operands for ~0.2 s on all
+// SMs -- what the tensor pipe alone delivers under the board's power cap.
+static void run_sustained() {
+  const int units = 148;
+  const int smem = 1024 + 7 * 8192 + 16 * 4096 + 256;
+  unsigned long long* out;
+  CK(cudaMalloc(&out, sizeof(unsigned long long) * 2 * units));
+  CK(cudaFuncSetAttribute(rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int rnd = 0; rnd < 2; ++rnd)
+  for (int iters : {300, 20000, 150000}) {
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaEventRecord(e0));
+      rate2_kernel<<<units, 128, smem>>>(0, 2, iters, out, rnd);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      std::vector<unsigned long long> h(2 * units);
+      CK(cudaMemcpy(h.data(), out, sizeof(unsigned long long) * 2 * units, cudaMemcpyDeviceToHost));
+      const double ksteps = (double)iters * 2.0;    // 32-byte K steps (10 MMAs each)
+      const double cyc = (double)h[0] / ksteps;
+      // executed INT8 MACs per K step per SM: 28 products x 128 x 64 x 32
+      const double tops = 2.0 * 28 * 128 * 64 * 32 * ksteps * units / (ms * 1e-3) * 1e-12;
+      printf("sustained S=7 schedule, %s operands, %6d iterations: %8.3f ms, %.1f cycles per K step, "
+             "%.0f ns per K step, SM clock %.0f MHz, %.0f TOP/s executed\n",
+             rnd ? "random-byte" : "constant", iters, ms, cyc, ms * 1e6 / ksteps,
+             cyc / (ms * 1e6 / ksteps) * 1e3, tops);
+    }
+  }
+  cudaFree(out);
+}
+
 static void run_contend_all() {
   run_contend<0>("no work", 0);
   run_contend<1>("DFMA", 4);
@@ -798,6 +834,10 @@ static void run_contend_all() {
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
+  if (argc > 1 && std::string(argv[1]) == "sustained") {
+    run_sustained();
+    return 0;
+  }
   if (argc > 1 && std::string(argv[1]) == "contend") {
     run_contend_all();
     return 0;
