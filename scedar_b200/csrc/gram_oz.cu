@@ -149,7 +149,15 @@ struct OzArgs {
   double* bmin_ptr[kOzPeers];
   int64_t ldb;
   int wshift;   // fraction bits of the integer weighted sums (oz_wshift)
+  int park_ns;  // suspend-time hint of the mbarrier waits (0: plain try_wait loop)
 };
+
+__device__ __forceinline__ void oz_wait(uint32_t bar, uint32_t parity, int park_ns) {
+  if (park_ns > 0)
+    mbar_wait_parked(bar, parity, (uint32_t)park_ns);
+  else
+    mbar_wait(bar, parity);
+}
 
 // Weighted sum of the diagonal accumulators minus the offset terms, as ONE
 // 64-bit integer.  hi (unit 1) and lo (unit 2^-8(S-3)) are exact: diagonal d
@@ -366,7 +374,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         coords(it, i0, j0, ks);
 #pragma unroll
         for (int sl = 0; sl < S; ++sl) {
-          mbar_wait(empty_a + 8 * sl, (uint32_t)((it & 1) ^ 1));
+          oz_wait(empty_a + 8 * sl, (uint32_t)((it & 1) ^ 1), a.park_ns);
           mbar_expect_tx(full_a + 8 * sl, A_SLAB);
           tma_load_2d(ring_a + sl * A_SLAB, &map_a, ks * OKB, (int)(sl * a.n_pl) + i0,
                       full_a + 8 * sl);
@@ -376,7 +384,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int i0, j0, ks;
         coords(it, i0, j0, ks);
         const uint32_t buf = (uint32_t)(it & 1), ph = (uint32_t)((it >> 1) & 1);
-        mbar_wait(empty_b + 8 * buf, ph ^ 1);
+        oz_wait(empty_b + 8 * buf, ph ^ 1, a.park_ns);
         mbar_expect_tx(full_b + 8 * buf, B_STAGE);
         const uint32_t st = ring_b + buf * B_STAGE;
 #pragma unroll
@@ -403,20 +411,20 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int ks0 = 0; ks0 < KS; ks0 += OZ_CHUNK_SLABS, ++tcount) {
         // a new K chunk (or tile): the epilogue has drained the accumulators
         long long c0 = a.dbg ? clock64() : 0;
-        mbar_wait(tempty, (tcount & 1) ^ 1);
+        oz_wait(tempty, (tcount & 1) ^ 1, a.park_ns);
         if (a.dbg) w_tempty += clock64() - c0;
         tc::fence_after();
         const int kc_end = KS - ks0 < OZ_CHUNK_SLABS ? KS - ks0 : OZ_CHUNK_SLABS;
         for (int kc = 0; kc < kc_end; ++kc, ++it) {
           const uint32_t buf = it & 1;
           c0 = a.dbg ? clock64() : 0;
-          mbar_wait(full_b + 8 * buf, (it >> 1) & 1);
+          oz_wait(full_b + 8 * buf, (it >> 1) & 1, a.park_ns);
           if (a.dbg) w_full += clock64() - c0;
           const uint64_t db = tc::desc_sw128(ring_b + buf * B_STAGE);
 #pragma unroll
           for (int sl = 0; sl < S; ++sl) {
             c0 = a.dbg ? clock64() : 0;
-            mbar_wait(full_a + 8 * sl, it & 1);
+            oz_wait(full_a + 8 * sl, it & 1, a.park_ns);
             if (a.dbg) w_full += clock64() - c0;
             tc::fence_after();
             const uint64_t da = tc::desc_sw128(ring_a + sl * A_SLAB);
@@ -541,7 +549,7 @@ gram_oz_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const long long hic = (row_ok ? __ldg(a.hi + gi * a.n_chunks + ch) : 0) + c0c;
         const long long loc = row_ok ? __ldg(a.lo + gi * a.n_chunks + ch) : 0;
         ec0 = a.dbg ? clock64() : 0;
-        mbar_wait(tfull, tcount & 1);
+        oz_wait(tfull, tcount & 1, a.park_ns);
         ec1 = a.dbg ? clock64() : 0;
         if (a.dbg) e_wait += ec1 - ec0;
         tc::fence_after();
@@ -869,6 +877,9 @@ int oz_launch(const scedar_cells* c, OzState* o, OzArgs& a, cudaStream_t s, int 
     const_cast<scedar_cells*>(c)->bmin_filled = true;
   }
   a.wshift = oz_wshift(o->n_chunks);
+  // parked waits (a suspend-time hint on mbarrier.try_wait) instead of spinning:
+  // ~1 % under the power cap (224-229 -> 221-227 ms at 100k x 2000); 0 = spin
+  a.park_ns = getenv("SCEDAR_B200_OZ_PARK_NS") ? atoi(getenv("SCEDAR_B200_OZ_PARK_NS")) : 2000;
   a.vec_ok = a.ldd % 4 == 0;
   for (int r = 0; r < a.world; ++r)
     if (reinterpret_cast<uintptr_t>(a.stripe_ptr[r]) % 32 != 0) a.vec_ok = 0;

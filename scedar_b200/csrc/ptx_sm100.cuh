@@ -46,6 +46,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   } while (!ok);
 }
+// The same wait with a suspend-time hint: the hardware parks the thread for up to
+// `ns` nanoseconds per attempt (it wakes as soon as the phase completes), so a
+// long wait costs a handful of polls instead of a spin.
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    if (!ok && clock64() - t0 > 8000000000LL) {
+      printf("scedar: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  } while (!ok);
+}
 // The same wait for register-starved loops (the FP64 Gram consumers hold 128
 // accumulator registers): 32-bit clock, no printf call on the time-out path.
 __device__ __forceinline__ void mbar_wait_lite(uint32_t bar, uint32_t parity) {
