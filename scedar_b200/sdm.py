@@ -28,9 +28,12 @@ from ._capi import (EXCLUDE_FIRST, EXCLUDE_SELF, METRIC_IDS, NCDM_ASYMMETRIC,
 DEVICE_D_CACHE_BYTES = 48 << 30
 # stripe size used when D is streamed to the host in pieces
 STRIPE_BYTES = 2 << 30
-# a dense host matrix of at least this size is uploaded range by range behind
-# the contraction instead of in one blocking copy
+# a dense host matrix of at least this size AND this many cells is uploaded range
+# by range behind the contraction instead of in one blocking copy (with fewer
+# cells the contraction is too short to hide anything: config 1, 3,005 x 19,972,
+# contracts in 2 ms and uploads in 70)
 UPLOAD_OVERLAP_BYTES = 64 << 20
+UPLOAD_OVERLAP_MIN_CELLS = 20000
 MAX_TOPK = 127
 FAST_MAX_K = 55     # the tensor-core pass re-ranks up to 64 candidates
 
@@ -336,7 +339,8 @@ class SampleDistanceMatrix(object):
         if prec in ("fp64_i8", "fp64_i8s6") and n >= 4096:
             bmin = dev.new_blockmin(n, n)
         if (metric not in self._cells_lut and not self._is_sparse
-                and prec != "fast" and n * p * 8 >= UPLOAD_OVERLAP_BYTES):
+                and prec != "fast" and n * p * 8 >= UPLOAD_OVERLAP_BYTES
+                and n >= UPLOAD_OVERLAP_MIN_CELLS):
             xh = np.ascontiguousarray(self._x, dtype=np.float64)
             cells, d = dev.pdist_symmetric_from_host(xh, metric, precision=prec,
                                                      bmin=bmin)

@@ -212,7 +212,7 @@ def test_blockmin_guards(b200):
     cells.close()
 
 
-def test_dropin_uses_minima_and_overlapped_upload(b200):
+def test_dropin_uses_minima_and_overlapped_upload(b200, monkeypatch):
     """Through the drop-in class: a dense host matrix large enough for the auto
     policy's INT8 split kernel goes up range by range behind the contraction
     (pageable source), D comes with its block minima, and the neighbour lists
@@ -220,6 +220,8 @@ def test_dropin_uses_minima_and_overlapped_upload(b200):
     import torch
     from oracle import sdm_oracle as orc
     from scedar_b200 import device as dev, synth
+    from scedar_b200 import sdm as sdm_mod
+    monkeypatch.setattr(sdm_mod, "UPLOAD_OVERLAP_MIN_CELLS", 0)   # take that route here
     n, p, k = 6016, 1500, 15
     x = synth.log_counts(n, p, seed=5)
     sdm = b200.SampleDistanceMatrix(x, metric="correlation")
